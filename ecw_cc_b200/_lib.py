@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI in include/ecw_b200.h (one prototype per entry point)."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libecw_b200.so")
+_SRC = ["gemm.cu", "ewise.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp", "ccs_plan.cpp"]
+
+ECW_HAS_ALPHA = 1
+ECW_EQUATION = 2
+
+
+class EcwError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", s) for s in _SRC]
+    deps = srcs + [os.path.join(_HERE, "csrc", h) for h in ("plan.h", "kernels.h", "ccsd_plan.h")]
+    deps.append(os.path.join(_HERE, "..", "include", "ecw_b200.h"))
+    if not force and os.path.exists(LIB_PATH):
+        mt = os.path.getmtime(LIB_PATH)
+        if all(os.path.getmtime(d) <= mt for d in deps):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"] + srcs + ["-o", LIB_PATH]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class _Lib(object):
+    """Lazy loader: importing the package must work before the library is built
+    (`__graft_entry__.build()` imports it right after compiling)."""
+
+    def __init__(self):
+        self._dll = None
+
+    def _load(self):
+        if self._dll is not None:
+            return self._dll
+        if not os.path.exists(LIB_PATH):
+            raise EcwError("libecw_b200.so is not built (run `python -c 'import ecw_cc_b200; ecw_cc_b200.build()'`); "
+                           "there is no CPU fallback for the ECW-CC residual path")
+        d = ctypes.CDLL(LIB_PATH)
+        c_p, c_i, c_l, c_d, c_s = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_char_p
+        sig = {
+            "ecw_ctx_create": (c_i, [ctypes.POINTER(c_p), c_i, c_i]),
+            "ecw_ctx_destroy": (None, [c_p]),
+            "ecw_last_error": (c_s, [c_p]),
+            "ecw_version": (c_s, []),
+            "ecw_slot_elems": (c_l, [c_p, c_s]),
+            "ecw_bind": (c_i, [c_p, c_s, c_p]),
+            "ecw_eris_pack_from_dense": (c_i, [c_p, c_p, c_p, c_p]),
+            "ecw_eris_synthetic": (c_i, [c_p, c_d, c_p]),
+            "ecw_synth_tensor": (c_i, [c_i, c_p, c_i, c_i, c_l, c_l, c_d, c_p]),
+            "ecw_workspace_bytes": (c_l, [c_p, c_s, c_i]),
+            "ecw_set_workspace": (c_i, [c_p, c_p, c_l]),
+            "ecw_ccsd_tupdate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_p, c_p, c_p]),
+            "ecw_ccsd_lupdate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_p, c_p, c_p]),
+            "ecw_ccsd_gamma": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+            "ecw_ccsd_energy": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p]),
+            "ecw_subdiff": (c_i, [c_p, c_p, c_d, c_p, c_l, c_p]),
+            "ecw_plan_dump": (c_l, [c_p, c_s, c_i, c_p, c_l]),
+            "ecw_plan_flops": (c_d, [c_p, c_s, c_i]),
+            "ecw_plan_launches": (c_l, [c_p, c_s, c_i]),
+            "ecw_dgemm": (c_i, [c_i, c_i, c_l, c_l, c_l, c_d, c_p, c_l, c_p, c_l, c_d, c_p, c_l, c_i, c_p]),
+            "ecw_profile_enable": (c_i, [c_p, c_i]),
+            "ecw_profile_dump": (c_l, [c_p, c_p, c_l]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(d, name)
+            fn.restype = res
+            fn.argtypes = args
+        self._dll = d
+        self.symbols = sorted(sig)
+        return d
+
+    def __getattr__(self, name):
+        return getattr(self._load(), name)
+
+
+lib = _Lib()

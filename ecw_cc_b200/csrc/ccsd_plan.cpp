@@ -1,0 +1,423 @@
+// ccsd_plan.cpp — plan builders for the spin-orbital CCSD residual path.
+//
+// Each builder states the reference equations as binary contractions over the
+// constant integral layouts of the eris container; the contraction list is
+// the one proven equal to the reference in oracle/refactored_np.py (same index
+// strings, same order).  Reference: CCSD.py:248-338 (tupdate), :346-413
+// (T intermediates), :419-535 (lupdate), :543-623 (Linter), :136-182 (rdm1),
+// :224-242 (energy).  Differences from the reference factorisation, all exact
+// identities (DESIGN.md "Algorithm"):
+//   * Wvvvv (CCSD.py:396-402) is never formed: its tau.oovv part is folded into
+//     Woooo (coefficient 1/4 -> 1/2), its t1.ovvv part becomes Y[ijma].t1;
+//   * wvvvo (CCSD.py:602-605) is never formed: each of its four pieces is
+//     contracted with l2 first;
+//   * the two particle-particle ladders and all o^4 terms run on
+//     antisymmetry-packed pairs  p(a<b) = b(b-1)/2 + a;
+//   * ring terms run in the particle-hole layout X[(ia),(jb)].
+#include "ccsd_plan.h"
+
+namespace ecw {
+
+namespace {
+
+struct Slots {
+  int64_t o, v, n, po, pv;
+  Tensor t1, t2, l1, l2, fsp, fock, out1, out2, rdm1;
+  Tensor foo, fov, fvo, fvv;
+  Tensor oooo, ooov, oovv, oovv_ph, ovov_ph, ovvv, oooo_p, oovv_p, ovvv_p, ovvv_p2, vvvv_p;
+  explicit Slots(const Sizes& z) {
+    o = z.nocc; v = z.nvir; n = o + v; po = npair(o); pv = npair(v);
+    t1 = make_tensor(S_T1, 0, {o, v});
+    t2 = make_tensor(S_T2, 0, {o, o, v, v});
+    l1 = make_tensor(S_L1, 0, {o, v});
+    l2 = make_tensor(S_L2, 0, {o, o, v, v});
+    fsp = make_tensor(S_FSP, 0, {n, n});
+    fock = make_tensor(S_FOCK, 0, {n, n});
+    out1 = make_tensor(S_OUT1, 0, {o, v});
+    out2 = make_tensor(S_OUT2, 0, {o, o, v, v});
+    rdm1 = make_tensor(S_RDM1, 0, {n, n});
+    foo = block2(fsp, 0, o, 0, o);
+    fov = block2(fsp, 0, o, o, v);
+    fvo = block2(fsp, o, v, 0, o);
+    fvv = block2(fsp, o, v, o, v);
+    oooo = make_tensor(S_OOOO, 0, {o, o, o, o});
+    ooov = make_tensor(S_OOOV, 0, {o, o, o, v});
+    oovv = make_tensor(S_OOVV, 0, {o, o, v, v});
+    oovv_ph = make_tensor(S_OOVV_PH, 0, {o, v, o, v});
+    ovov_ph = make_tensor(S_OVOV_PH, 0, {o, v, o, v});
+    ovvv = make_tensor(S_OVVV, 0, {o, v, v, v});
+    oooo_p = make_tensor(S_OOOO_P, 0, {po, po});
+    oovv_p = make_tensor(S_OOVV_P, 0, {po, pv});
+    ovvv_p = make_tensor(S_OVVV_P, 0, {o, v, pv});
+    ovvv_p2 = make_tensor(S_OVVV_P, 0, {o * v, pv});
+    vvvv_p = make_tensor(S_VVVV_P, 0, {pv, pv});
+  }
+};
+
+// r2[ijab] += P(ij)P(ab) ring[iajb]; x is an o2v2 scratch.
+void add_antisym_ph(Plan& P, const Tensor& ring, const Tensor& x, const Tensor& r2) {
+  P.permute(1.0, ring, "iajb", 0.0, x, "ijab", "ph->ijab");
+  P.permute(-1.0, ring, "jaib", 1.0, x, "ijab", "P(ij)");
+  P.axpby(1.0, x, 1.0, r2);
+  P.permute(-1.0, x, "ijba", 1.0, r2, "ijab", "P(ab)");
+}
+
+// scal[k] = CCSD correlation-energy functional (CCSD.py:236-240 / :608-610)
+void emit_energy(Plan& P, const Slots& s, const Tensor& fov_dense, int k) {
+  P.dot(1.0, fov_dense, s.t1, 0.0, k);
+  P.dot(0.25, s.t2, s.oovv, 1.0, k);
+  Tensor G = P.tmp({s.o, s.v});
+  P.contract(1.0, s.oovv_ph, "menf", s.t1, "nf", 0.0, G, "me");
+  P.dot(0.5, s.t1, G, 1.0, k);
+  P.release(G);
+}
+
+}  // namespace
+
+void build_ccsd_energy(Plan& P, const Sizes& z) {
+  Slots s(z);
+  Tensor f = P.tmp({s.o, s.v});
+  P.axpby(1.0, s.fov, 0.0, f);
+  emit_energy(P, s, f, 0);
+  P.release(f);
+}
+
+void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
+  Slots s(z);
+  const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv;
+  const bool shift = !equation && !has_alpha;  // CCSD.py:283-285
+  const Tensor &t1 = s.t1, &t2 = s.t2, &r1 = s.out1, &r2 = s.out2;
+
+  Tensor tau = P.tmp({o, o, v, v});
+  P.tau(t2, t1, 1.0, tau);                                   // make_tau, CCSD.py:346-353
+  Tensor tau_p = P.tmp({po, pv});
+  P.pack(1.0, tau, 3, 0.0, tau_p);
+  P.release(tau);
+  Tensor ttl = P.tmp({o, o, v, v});
+  P.tau(t2, t1, 0.5, ttl);                                   // tau_tilde (fac=0.5)
+  Tensor t2ph = P.tmp({o, v, o, v});
+  P.permute(1.0, t2, "ijab", 0.0, t2ph, "iajb", "t2 ph layout");
+
+  // one-body intermediates, CCSD.py:355-387
+  Tensor Fov = P.tmp({o, v});
+  P.axpby(1.0, s.fov, 0.0, Fov);
+  P.contract(1.0, s.oovv_ph, "menf", t1, "nf", 1.0, Fov, "me", "cc_Fov");
+  Tensor Fvv = P.tmp({v, v});
+  P.axpby(1.0, s.fvv, 0.0, Fvv);
+  P.contract(-0.5, s.fov, "me", t1, "ma", 1.0, Fvv, "ae", "cc_Fvv");
+  P.contract(-1.0, s.ovvv, "maef", t1, "mf", 1.0, Fvv, "ae", "cc_Fvv vovv");
+  P.contract(-0.5, ttl, "mnfa", s.oovv, "mnfe", 1.0, Fvv, "ae", "cc_Fvv tau~");
+  Tensor Foo = P.tmp({o, o});
+  P.axpby(1.0, s.foo, 0.0, Foo);
+  P.contract(0.5, s.fov, "me", t1, "ie", 1.0, Foo, "mi", "cc_Foo");
+  P.contract(1.0, s.ooov, "mnie", t1, "ne", 1.0, Foo, "mi", "cc_Foo ooov");
+  P.contract(0.5, s.oovv, "mnef", ttl, "inef", 1.0, Foo, "mi", "cc_Foo tau~");
+  P.release(ttl);
+  if (shift) {
+    P.diag_add(Fvv, -1.0, s.fock, o);
+    P.diag_add(Foo, -1.0, s.fock, 0);
+  }
+
+  // T1 residual, CCSD.py:288-294
+  P.axpby(1.0, s.fov, 0.0, r1);
+  P.contract(1.0, t1, "ie", Fvv, "ae", 1.0, r1, "ia");
+  P.contract(-1.0, Foo, "mi", t1, "ma", 1.0, r1, "ia");
+  P.contract(1.0, t2ph, "iame", Fov, "me", 1.0, r1, "ia");
+  P.contract(-1.0, s.ovov_ph, "ianf", t1, "nf", 1.0, r1, "ia");
+  P.contract(-0.5, t2, "imef", s.ovvv, "maef", 1.0, r1, "ia", "T1 ovvv");
+  P.contract(0.5, t2, "mnea", s.ooov, "mnie", 1.0, r1, "ia");
+
+  // T2 residual, CCSD.py:297-314
+  Tensor x = P.tmp({o, o, v, v});
+  Tensor F1 = P.tmp({v, v});
+  P.axpby(1.0, Fvv, 0.0, F1);
+  P.contract(-0.5, t1, "mb", Fov, "me", 1.0, F1, "be");
+  P.contract(1.0, t2, "ijae", F1, "be", 0.0, x, "ijab");
+  P.axpby(1.0, s.oovv, 0.0, r2);
+  P.axpby(1.0, x, 1.0, r2);
+  P.permute(-1.0, x, "ijba", 1.0, r2, "ijab");
+  P.release(F1);
+  Tensor F2 = P.tmp({o, o});
+  P.axpby(1.0, Foo, 0.0, F2);
+  P.contract(0.5, t1, "je", Fov, "me", 1.0, F2, "mj");
+  P.contract(1.0, F2, "mj", t2, "imab", 0.0, x, "ijab");
+  P.axpby(-1.0, x, 1.0, r2);
+  P.permute(1.0, x, "jiab", 1.0, r2, "ijab");
+  P.release(F2);
+
+  // packed accumulator [ij_p, ab_p]: hh ladder + pp ladder + (t1.ovvv part of Wvvvv)
+  Tensor w4 = P.tmp({o, o, o, o});
+  P.contract(1.0, s.ooov, "mnie", t1, "je", 0.0, w4, "mnij");
+  Tensor Woo_p = P.tmp({po, po});
+  P.axpby(1.0, s.oooo_p, 0.0, Woo_p);
+  P.pack(1.0, w4, 3 | 4, 1.0, Woo_p);
+  P.release(w4);
+  P.contract(1.0, s.oovv_p, "mf", tau_p, "if", 1.0, Woo_p, "mi", "Woooo tau.oovv (K3 folded)");
+  Tensor acc_p = P.tmp({po, pv});
+  P.contract(1.0, Woo_p, "mi", tau_p, "ma", 0.0, acc_p, "ia", "hh ladder");
+  P.release(Woo_p);
+  P.contract(1.0, tau_p, "if", s.vvvv_p, "af", 1.0, acc_p, "ia", "K1 pp ladder");
+  Tensor Y_p = P.tmp({po, o * v});
+  P.contract(-2.0, tau_p, "if", s.ovvv_p2, "qf", 0.0, Y_p, "iq", "R9 Y[ijma]");
+  P.release(tau_p);
+  Tensor Z = P.tmp({po, v, v});
+  P.contract(1.0, reshape(Y_p, {po, o, v}), "pma", t1, "mb", 0.0, Z, "pab");
+  P.release(Y_p);
+  P.pack(-0.5, reshape(Z, {po, 1, v, v}), 2 | 4, 1.0, acc_p);
+  P.release(Z);
+  P.unpack(1.0, acc_p, 3, 1.0, r2);
+  P.release(acc_p);
+
+  // ring, CCSD.py:306-310 with Wovvo (CCSD.py:404-413) as W'[(me),(jb)]
+  Tensor Wph = P.tmp({o, v, o, v});
+  P.contract(0.5, s.oovv_ph, "menf", t2ph, "nfjb", 0.0, Wph, "mejb", "R1 Wovvo");
+  P.contract(1.0, s.ovvv, "mbef", t1, "jf", 1.0, Wph, "mejb");
+  P.contract(1.0, t1, "nb", s.ooov, "mnje", 1.0, Wph, "mejb");
+  Tensor U = P.tmp({o, o, v, o});
+  P.contract(1.0, s.oovv, "mnef", t1, "jf", 0.0, U, "mnej");
+  P.contract(-1.0, t1, "nb", U, "mnej", 1.0, Wph, "mejb");
+  P.release(U);
+  P.axpby(-1.0, s.ovov_ph, 1.0, Wph);
+  Tensor ring = P.tmp({o, v, o, v});
+  P.contract(1.0, t2ph, "iame", Wph, "mejb", 0.0, ring, "iajb", "R2 ring");
+  P.release(Wph);
+  Tensor Q = P.tmp({o, v, o, o});
+  P.contract(1.0, s.ovov_ph, "jbme", t1, "ie", 0.0, Q, "jbmi");
+  P.contract(1.0, t1, "ma", Q, "jbmi", 1.0, ring, "iajb");
+  P.release(Q);
+  add_antisym_ph(P, ring, x, r2);
+  P.release(ring);
+  P.release(t2ph);
+
+  P.contract(-1.0, t1, "ie", s.ovvv, "jeab", 0.0, x, "ijab");
+  P.axpby(1.0, x, 1.0, r2);
+  P.permute(-1.0, x, "jiab", 1.0, r2, "ijab");
+  P.contract(1.0, t1, "ma", s.ooov, "ijmb", 0.0, x, "ijab");
+  P.axpby(-1.0, x, 1.0, r2);
+  P.permute(1.0, x, "ijba", 1.0, r2, "ijab");
+  P.release(x);
+  P.release(Fov);
+  P.release(Fvv);
+  P.release(Foo);
+
+  P.finish(r1, t1, s.fock, (int)o, 2, has_alpha, equation, 0.0, r1);
+  P.finish(r2, t2, s.fock, (int)o, 4, has_alpha, equation, 0.0, r2);
+}
+
+void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
+  Slots s(z);
+  const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv;
+  const bool shift = !equation && !has_alpha;  // CCSD.py:449-456 (Q2)
+  const Tensor &t1 = s.t1, &t2 = s.t2, &l1 = s.l1, &l2 = s.l2, &r1 = s.out1, &r2 = s.out2;
+
+  Tensor tau = P.tmp({o, o, v, v});
+  P.tau(t2, t1, 1.0, tau);     // antisymmetric part of CCSD.py:565 (all uses contract an antisymmetric pair)
+  Tensor tau_p = P.tmp({po, pv});
+  P.pack(1.0, tau, 3, 0.0, tau_p);
+  Tensor l2_p = P.tmp({po, pv});
+  P.pack(1.0, l2, 3, 0.0, l2_p);
+  Tensor t2ph = P.tmp({o, v, o, v});
+  P.permute(1.0, t2, "ijab", 0.0, t2ph, "iajb", "t2 ph layout");
+  Tensor l2ph = P.tmp({o, v, o, v});
+  P.permute(1.0, l2, "ijab", 0.0, l2ph, "iajb", "l2 ph layout");
+
+  // ---- Linter, CCSD.py:543-623
+  Tensor Fov = P.tmp({o, v});   // = fov1 (:474) = tmp (:504) = (:580)
+  P.axpby(1.0, s.fov, 0.0, Fov);
+  P.contract(1.0, s.oovv_ph, "menf", t1, "nf", 1.0, Fov, "me");
+  Tensor v1 = P.tmp({v, v});
+  P.axpby(1.0, s.fvv, 0.0, v1);
+  P.contract(-1.0, s.fov, "ja", t1, "jb", 1.0, v1, "ba");
+  P.contract(-1.0, s.ovvv, "jbac", t1, "jc", 1.0, v1, "ba", "v1 ovvv");
+  P.contract(-0.5, tau, "jkcb", s.oovv, "jkca", 1.0, v1, "ba");
+  Tensor v2 = P.tmp({o, o});
+  P.axpby(1.0, s.foo, 0.0, v2);
+  P.contract(1.0, s.fov, "ib", t1, "jb", 1.0, v2, "ij");
+  P.contract(-1.0, s.ooov, "kijb", t1, "kb", 1.0, v2, "ij");
+  P.contract(0.5, s.oovv, "ikbc", tau, "jkbc", 1.0, v2, "ij");
+  P.release(tau);
+
+  Tensor v4ph = P.tmp({o, v, o, v});   // [(kc),(jb)] = v4[j,c,b,k]
+  P.contract(1.0, t2ph, "kcld", s.oovv_ph, "ldjb", 0.0, v4ph, "kcjb", "R3 v4");
+  P.axpby(-1.0, s.ovov_ph, 1.0, v4ph);
+
+  Tensor v5T = P.tmp({o, v});          // v5T[j,b] = v5[b,j]
+  P.permute(1.0, s.fvo, "bj", 0.0, v5T, "jb");
+  P.contract(1.0, t2ph, "jbkc", s.fov, "kc", 1.0, v5T, "jb");
+  Tensor q = P.tmp({o, o});
+  P.contract(1.0, Fov, "kc", t1, "jc", 0.0, q, "kj");
+  P.contract(1.0, q, "kj", t1, "kb", 1.0, v5T, "jb");
+  P.release(q);
+  P.contract(0.5, s.ooov, "kljc", t2, "klcb", 1.0, v5T, "jb");
+  P.contract(-0.5, t2, "jkdc", s.ovvv, "kbdc", 1.0, v5T, "jb", "v5 ovvv");
+
+  Tensor w3T = P.tmp({o, v});          // w3T[k,c] = w3[c,k]
+  P.axpby(1.0, v5T, 0.0, w3T);
+  P.release(v5T);
+  P.contract(1.0, v4ph, "kcjb", t1, "jb", 1.0, w3T, "kc");
+  P.contract(1.0, t1, "kb", v1, "cb", 1.0, w3T, "kc");
+  P.contract(-1.0, v2, "jk", t1, "jc", 1.0, w3T, "kc");
+
+  // hole-hole pieces, packed [ij_p, kl_p]
+  Tensor woo_p = P.tmp({po, po});
+  P.axpby(0.5, s.oooo_p, 0.0, woo_p);
+  P.contract(0.5, s.oovv_p, "if", tau_p, "kf", 1.0, woo_p, "ik", "v3");
+  Tensor y4 = P.tmp({o, o, o, o});
+  P.contract(1.0, s.ooov, "jilc", t1, "kc", 0.0, y4, "jilk");
+  P.pack(0.5, y4, 3 | 4, 1.0, woo_p);
+  P.release(y4);
+  Tensor lt_p = P.tmp({po, po});
+  P.contract(2.0, l2_p, "if", tau_p, "kf", 0.0, lt_p, "ik", "l2.tau");
+
+  Tensor S = P.tmp({o, o, v, o});
+  P.contract(1.0, s.oovv, "ljbd", t1, "kd", 0.0, S, "ljbk");
+  Tensor wph = P.tmp({o, v, o, v});    // wovvo as [(kc),(jb)]
+  P.axpby(1.0, v4ph, 0.0, wph);
+  P.contract(1.0, t1, "lc", S, "ljbk", 1.0, wph, "kcjb");
+  P.release(S);
+  P.contract(-1.0, t1, "lc", s.ooov, "ljkb", 1.0, wph, "kcjb");
+  P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
+
+  Tensor wo_p = P.tmp({o * v, po});
+  P.contract(0.5, s.ovvv_p2, "qf", tau_p, "kf", 0.0, wo_p, "qk", "R4 wovoo");
+  P.release(tau_p);
+  Tensor wovoo = P.tmp({o, v, o, o});
+  P.unpack(1.0, wo_p, 2, 0.0, wovoo);
+  P.release(wo_p);
+  P.permute(0.5, s.ooov, "jkic", 1.0, wovoo, "icjk");
+  P.contract(1.0, v4ph, "kcib", t1, "jb", 1.0, wovoo, "icjk");
+  P.contract(-1.0, t2ph, "kclb", s.ooov, "lijb", 1.0, wovoo, "icjk", "wovoo ooov.t2");
+
+  // ---- m3, CCSD.py:461-470, packed [ij_p, ab_p]
+  Tensor m3_p = P.tmp({po, pv});
+  P.contract(2.0, woo_p, "ik", l2_p, "ka", 0.0, m3_p, "ia", "l2.woooo");
+  P.release(woo_p);
+  P.contract(0.5, lt_p, "ik", s.oovv_p, "ka", 1.0, m3_p, "ia");
+  Tensor l2t1 = P.tmp({o, o, v, o});
+  P.contract(1.0, l2, "ijcd", t1, "kd", 0.0, l2t1, "ijck");
+  Tensor a_full = P.tmp({o, o, o, v});
+  P.permute(1.0, l2t1, "ijck", 0.0, a_full, "ijkc");
+  Tensor a_p = P.tmp({po, o * v});
+  P.pack(1.0, reshape(a_full, {o, o, o * v, 1}), 1, 0.0, a_p);
+  P.release(a_full);
+  P.contract(1.0, a_p, "pq", s.ovvv_p2, "qa", 1.0, m3_p, "pa", "R6 ovvv.(l2 t1)");
+  P.release(a_p);
+  P.contract(1.0, l2_p, "if", s.vvvv_p, "af", 1.0, m3_p, "ia", "K2 pp ladder");
+  P.release(l2_p);
+  Tensor m3 = P.tmp({o, o, v, v});
+  P.unpack(1.0, m3_p, 3, 0.0, m3);
+  P.release(m3_p);
+
+  Tensor m_vv = P.tmp({v, v});
+  P.contract(0.5, t2, "klcb", l2, "klca", 0.0, m_vv, "ba");
+  Tensor m_oo = P.tmp({o, o});
+  P.contract(0.5, l2, "kicd", t2, "kjcd", 0.0, m_oo, "ij");
+  Tensor x_vv = P.tmp({v, v});
+  P.axpby(1.0, m_vv, 0.0, x_vv);
+  P.contract(1.0, l1, "ka", t1, "kb", 1.0, x_vv, "ba");
+  Tensor x_oo = P.tmp({o, o});
+  P.axpby(1.0, m_oo, 0.0, x_oo);
+  P.contract(1.0, l1, "ic", t1, "kc", 1.0, x_oo, "ik");
+  if (shift) {  // after w3 (which uses the unshifted v1, v2)
+    P.diag_add(v1, -1.0, s.fock, o);
+    P.diag_add(v2, -1.0, s.fock, 0);
+  }
+
+  // ---- L2 residual, CCSD.py:472-488
+  P.axpby(1.0, s.oovv, 0.0, r2);
+  P.axpby(1.0, m3, 1.0, r2);
+  Tensor ring = P.tmp({o, v, o, v});
+  P.contract(1.0, l2ph, "iakc", wph, "kcjb", 0.0, ring, "iajb", "R7 ring");
+  P.release(wph);
+  P.contract(1.0, l1, "ia", Fov, "jb", 1.0, ring, "iajb");
+  Tensor y = P.tmp({o, o, v, v});
+  add_antisym_ph(P, ring, y, r2);
+  P.release(ring);
+  P.contract(1.0, l1, "ka", s.ooov, "ijkb", 0.0, y, "ijab");
+  P.contract(-1.0, l2, "ijac", v1, "cb", 1.0, y, "ijab");
+  P.contract(1.0, x_vv, "ca", s.oovv, "ijcb", 1.0, y, "ijab");
+  P.axpby(-1.0, y, 1.0, r2);
+  P.permute(1.0, y, "ijba", 1.0, r2, "ijab");
+  P.contract(1.0, l1, "qc", s.ovvv, "pcrs", 0.0, y, "pqrs");
+  P.contract(1.0, v2, "qk", l2, "kprs", 1.0, y, "pqrs");
+  P.contract(-1.0, x_oo, "pk", s.oovv, "kqrs", 1.0, y, "pqrs");
+  P.axpby(1.0, y, 1.0, r2);
+  P.permute(-1.0, y, "qprs", 1.0, r2, "pqrs");
+  P.release(y);
+
+  // ---- L1 residual, CCSD.py:490-506
+  P.axpby(1.0, s.fov, 0.0, r1);
+  P.contract(-1.0, s.ovov_ph, "jbia", l1, "jb", 1.0, r1, "ia");
+  P.contract(1.0, l1, "ib", v1, "ba", 1.0, r1, "ia");
+  P.contract(-1.0, v2, "ij", l1, "ja", 1.0, r1, "ia");
+  P.contract(-1.0, wovoo, "icjk", l2, "kjca", 1.0, r1, "ia");
+  P.release(wovoo);
+  // -(l2 . wvvvo) with wvvvo never formed (four pieces):
+  P.contract(1.0, l2t1, "ikcj", v4ph, "kcja", 1.0, r1, "ia", "wvvvo: v4.t1");
+  P.release(l2t1);
+  P.release(v4ph);
+  Tensor lt = P.tmp({o, o, o, o});
+  P.unpack(1.0, lt_p, 3, 0.0, lt);
+  P.release(lt_p);
+  P.contract(-0.25, lt, "ikjl", s.ooov, "jlka", 1.0, r1, "ia", "wvvvo: ooov.tau");
+  P.release(lt);
+  P.contract(-0.5, l2, "ikbc", s.ovvv, "kabc", 1.0, r1, "ia", "wvvvo: ovvv");
+  Tensor Xph = P.tmp({o, v, o, v});
+  P.contract(1.0, l2ph, "ibjc", t2ph, "jckd", 0.0, Xph, "ibkd", "R8 l2.t2");
+  P.contract(1.0, Xph, "ibkd", s.ovvv, "kbda", 1.0, r1, "ia", "wvvvo: ovvv.t2 (K4 refactored)");
+  P.release(Xph);
+  P.contract(1.0, m3, "ijab", t1, "jb", 1.0, r1, "ia");
+  P.release(m3);
+  P.contract(1.0, l2ph, "iajb", w3T, "jb", 1.0, r1, "ia");
+  P.release(l2ph);
+  Tensor zz = P.tmp({o, v});
+  P.axpby(1.0, t1, 0.0, zz);
+  P.contract(1.0, t2ph, "jbkc", l1, "kc", 1.0, zz, "jb");
+  P.release(t2ph);
+  P.contract(-1.0, x_vv, "bd", t1, "jd", 1.0, zz, "jb");
+  P.contract(-1.0, m_oo, "lj", t1, "lb", 1.0, zz, "jb");
+  P.contract(1.0, s.oovv_ph, "iajb", zz, "jb", 1.0, r1, "ia");
+  P.release(zz);
+  P.contract(-1.0, s.ovvv, "icba", x_vv, "bc", 1.0, r1, "ia", "L1 ovvv.x_vv");
+  P.contract(-1.0, s.ooov, "jika", x_oo, "kj", 1.0, r1, "ia");
+  P.contract(-1.0, m_oo, "ik", Fov, "ka", 1.0, r1, "ia");
+  P.contract(-1.0, m_vv, "ca", Fov, "ic", 1.0, r1, "ia");
+
+  if (shift) {  // energy term, CCSD.py:509-510
+    Tensor f = P.tmp({o, v});
+    P.axpby(1.0, s.fov, 0.0, f);
+    emit_energy(P, s, f, 0);
+    P.release(f);
+    P.scale_dev(r1, 1.0, -1.0, 0);
+    P.scale_dev(r2, 1.0, -1.0, 0);
+  }
+  P.release(Fov); P.release(v1); P.release(v2); P.release(w3T);
+  P.release(m_vv); P.release(m_oo); P.release(x_vv); P.release(x_oo);
+
+  P.finish(r1, l1, s.fock, (int)o, 2, has_alpha, equation, 0.0, r1);
+  P.finish(r2, l2, s.fock, (int)o, 4, has_alpha, equation, 0.0, r2);
+}
+
+void build_ccsd_gamma(Plan& P, const Sizes& z) {
+  Slots s(z);
+  const int64_t o = s.o, v = s.v;
+  const Tensor &t1 = s.t1, &t2 = s.t2, &l1 = s.l1, &l2 = s.l2;
+  // gamma_inter, CCSD.py:165-182
+  Tensor D = P.tmp({o, o});
+  P.contract(1.0, l2, "imef", t2, "jmef", 0.0, D, "ij", "rdm1 oo");
+  Tensor doo = P.tmp({o, o});
+  P.axpby(-0.5, D, 0.0, doo);
+  P.contract(-1.0, l1, "ie", t1, "je", 1.0, doo, "ij");
+  Tensor dvv = P.tmp({v, v});
+  P.contract(0.5, t2, "mnea", l2, "mneb", 0.0, dvv, "ab", "rdm1 vv");
+  P.contract(1.0, t1, "ma", l1, "mb", 1.0, dvv, "ab");
+  Tensor dvoT = P.tmp({o, v});
+  P.axpby(1.0, t1, 0.0, dvoT);
+  P.contract(1.0, t2, "imae", l1, "me", 1.0, dvoT, "ia", "rdm1 vo");
+  P.contract(-0.5, D, "mi", t1, "ma", 1.0, dvoT, "ia");
+  P.contract(-1.0, t1, "ie", dvv, "ae", 1.0, dvoT, "ia");
+  P.rdm1(doo, dvoT, l1, dvv, s.rdm1);   // CCSD.py:154-160
+  P.release(D); P.release(doo); P.release(dvv); P.release(dvoT);
+}
+
+}  // namespace ecw

@@ -1,0 +1,432 @@
+// ewise.cu — bandwidth-bound kernels of the CC residual path (sm_100a):
+// strided N-d permute/axpby (tiled transpose when the contiguous axis moves),
+// split-K reduction, tau, antisymmetric pair pack/unpack, the residual->update
+// "finish" kernel (soft-threshold + denominators, CCSD.py:316-338 and
+// utilities.py:26-73), deterministic dot products, rdm1 assembly.
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace ecw {
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline unsigned grid_for(int64_t n, int per_block, int64_t cap = 148LL * 32) {
+  int64_t b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  return (unsigned)std::min<int64_t>(b, cap);
+}
+
+// ------------------------------------------------------------------ permute
+struct PermK {
+  const double* in;
+  double* out;
+  int nd;                       // number of "rest" dims (linear kernel: all dims)
+  int64_t dim[KMAXD], sin[KMAXD], sout[KMAXD];
+  int64_t d_fi, d_fo;           // tiled kernel: extents of the two fast axes
+  int64_t fi_sin, fi_sout, fo_sin, fo_sout;
+  int64_t total;
+  double alpha, beta;
+};
+
+// Same contiguous axis on both sides (or no unit stride at all): plain strided copy,
+// dims ordered so the last one is the fast axis.
+__global__ void __launch_bounds__(EW_THREADS) permute_linear_kernel(PermK p) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < p.total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = idx, oi = 0, oo = 0;
+#pragma unroll
+    for (int d = KMAXD - 1; d >= 0; --d) {
+      if (d < p.nd) {
+        int64_t q = rem / p.dim[d];
+        int64_t c = rem - q * p.dim[d];
+        rem = q;
+        oi += c * p.sin[d];
+        oo += c * p.sout[d];
+      }
+    }
+    double v = p.alpha * p.in[oi];
+    if (p.beta != 0.0) v += p.beta * p.out[oo];
+    p.out[oo] = v;
+  }
+}
+
+// The contiguous axis differs: 32x32 shared-memory transpose over (fi, fo); the
+// remaining axes are enumerated by the block index.
+__global__ void __launch_bounds__(256) permute_tiled_kernel(PermK p) {
+  __shared__ double tile[32][33];
+  const int64_t tiles_i = (p.d_fi + 31) / 32, tiles_o = (p.d_fo + 31) / 32;
+  int64_t b = blockIdx.x;
+  const int64_t ti = b % tiles_i; b /= tiles_i;
+  const int64_t to = b % tiles_o; b /= tiles_o;
+  int64_t oi = 0, oo = 0;
+#pragma unroll
+  for (int d = KMAXD - 1; d >= 0; --d) {
+    if (d < p.nd) {
+      int64_t q = b / p.dim[d];
+      int64_t c = b - q * p.dim[d];
+      b = q;
+      oi += c * p.sin[d];
+      oo += c * p.sout[d];
+    }
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int64_t i0 = ti * 32, o0 = to * 32;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    int64_t ii = i0 + tx, jo = o0 + r;
+    if (ii < p.d_fi && jo < p.d_fo) tile[r][tx] = p.in[oi + ii * p.fi_sin + jo * p.fo_sin];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    int64_t ii = i0 + r, jo = o0 + tx;
+    if (ii < p.d_fi && jo < p.d_fo) {
+      int64_t off = oo + ii * p.fi_sout + jo * p.fo_sout;
+      double v = p.alpha * tile[tx][r];
+      if (p.beta != 0.0) v += p.beta * p.out[off];
+      p.out[off] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) fill_kernel(double* c, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    c[i] = v;
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+reduce_kernel(const double* __restrict__ part, int64_t nz, int64_t M, int64_t N, double* C, int64_t sr,
+              int64_t sc, double alpha, double beta) {
+  const int64_t mn = M * N;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < mn; e += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t z = 0; z < nz; ++z) s += part[z * mn + e];
+    int64_t m = e / N, n = e - m * N;
+    int64_t off = m * sr + n * sc;
+    double v = alpha * s;
+    if (beta != 0.0) v += beta * C[off];
+    C[off] = v;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+tau_kernel(const double* __restrict__ t2, const double* __restrict__ t1, double* __restrict__ out, int o, int v,
+           double coef) {
+  const int64_t vv = (int64_t)v * v, total = (int64_t)o * o * vv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t ij = idx / vv, ab = idx - ij * vv;
+    int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
+    int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
+    double x = t1[i * v + a] * t1[j * v + b] - t1[i * v + b] * t1[j * v + a];
+    out[idx] = t2[idx] + coef * x;
+  }
+}
+
+// packed pair index k = hi(hi-1)/2 + lo  (lo < hi)
+__device__ __forceinline__ void pair_decode(int64_t k, int64_t& lo, int64_t& hi) {
+  int64_t h = (int64_t)((1.0 + sqrt(1.0 + 8.0 * (double)k)) * 0.5);
+  while (h * (h - 1) / 2 > k) --h;
+  while ((h + 1) * h / 2 <= k) ++h;
+  hi = h;
+  lo = k - h * (h - 1) / 2;
+}
+
+__global__ void __launch_bounds__(EW_THREADS) pack_kernel(PackArgs p, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / cols, c = idx - r * cols;
+    int64_t i0, i1, i2, i3;
+    if (p.flags & 1) pair_decode(r, i0, i1);
+    else { i0 = r / p.d1; i1 = r - i0 * p.d1; }
+    if (p.flags & 2) pair_decode(c, i2, i3);
+    else { i2 = c / p.d3; i3 = c - i2 * p.d3; }
+    const double* s = p.src + i0 * p.s0 + i1 * p.s1;
+    double val = s[i2 * p.s2 + i3 * p.s3];
+    if (p.flags & 4) val -= s[i3 * p.s2 + i2 * p.s3];
+    double* d = p.dst + r * p.ld + c;
+    double out = p.alpha * val;
+    if (p.beta != 0.0) out += p.beta * *d;
+    *d = out;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) unpack_kernel(PackArgs p, int64_t total) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = idx;
+    int64_t i3 = rem % p.d3; rem /= p.d3;
+    int64_t i2 = rem % p.d2; rem /= p.d2;
+    int64_t i1 = rem % p.d1;
+    int64_t i0 = rem / p.d1;
+    double sign = 1.0;
+    bool zero = false;
+    int64_t r, c;
+    if (p.flags & 1) {
+      if (i0 == i1) zero = true;
+      int64_t lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+      if (i0 > i1) sign = -sign;
+      r = hi * (hi - 1) / 2 + lo;
+    } else r = i0 * p.d1 + i1;
+    if (p.flags & 2) {
+      if (i2 == i3) zero = true;
+      int64_t lo = i2 < i3 ? i2 : i3, hi = i2 < i3 ? i3 : i2;
+      if (i2 > i3) sign = -sign;
+      c = hi * (hi - 1) / 2 + lo;
+    } else c = i2 * p.d3 + i3;
+    double val = zero ? 0.0 : sign * p.src[r * p.ld + c];
+    double* d = p.dst + i0 * p.s0 + i1 * p.s1 + i2 * p.s2 + i3 * p.s3;
+    double out = p.alpha * val;
+    if (p.beta != 0.0) out += p.beta * *d;
+    *d = out;
+  }
+}
+
+// utilities.subdiff (utilities.py:53-67): v > 0 -> e + alpha; otherwise soft threshold (Q1)
+__device__ __forceinline__ double subdiff(double e, double v, double alpha) {
+  if (v > 0.0) return e + alpha;
+  if (e < -alpha) return e + alpha;
+  if (e > alpha) return e - alpha;
+  return 0.0;
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+subdiff_kernel(const double* __restrict__ e, const double* __restrict__ v, double alpha, double* out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = subdiff(e[i], v[i], alpha);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+finish_kernel(const double* r, const double* __restrict__ amp, const double* __restrict__ fock, int64_t ldf,
+              double* out, int o, int v, int rank, int has_alpha, int equation, double alpha) {
+  extern __shared__ double eps[];
+  const int n = o + v;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) eps[i] = fock[(int64_t)i * ldf + i];
+  __syncthreads();
+  const int64_t vv = (int64_t)v * v;
+  const int64_t total = rank == 2 ? (int64_t)o * v : (int64_t)o * o * vv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double d;
+    if (rank == 2) {
+      int i = (int)(idx / v), a = (int)(idx - (int64_t)i * v);
+      d = eps[i] - eps[o + a];
+    } else {
+      int64_t ij = idx / vv, ab = idx - ij * vv;
+      int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
+      int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
+      d = (eps[i] - eps[o + a]) + (eps[j] - eps[o + b]);
+    }
+    double e = r[idx], res;
+    if (has_alpha) {
+      double t = amp[idx];
+      double w = rank == 4 ? subdiff(e, t, alpha) : e;   // L1 only on doubles (Q3)
+      res = equation ? w : (w + t * d) / d;
+    } else {
+      res = equation ? e : e / d;
+    }
+    out[idx] = res;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+dot_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* partial) {
+  __shared__ double sh[EW_THREADS];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += a[i] * b[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = EW_THREADS / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+dot_final_kernel(const double* partial, int nb, double* scal, double alpha, double beta) {
+  __shared__ double sh[EW_THREADS];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = EW_THREADS / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *scal = (beta != 0.0 ? beta * *scal : 0.0) + alpha * sh[0];
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+scale_dev_kernel(double* c, int64_t n, const double* scal, double d0, double d1) {
+  const double f = d0 + d1 * *scal;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    c[i] *= f;
+}
+
+__global__ void diag_add_kernel(double* c, int64_t ldc, int64_t m, const double* fock, int64_t ldf, int64_t foff,
+                                double alpha) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+    c[i * ldc + i] += alpha * fock[(foff + i) * ldf + foff + i];
+}
+
+// CCSD.py:154-160
+__global__ void __launch_bounds__(EW_THREADS)
+rdm1_kernel(const double* __restrict__ doo, const double* __restrict__ dvoT, const double* __restrict__ l1,
+            const double* __restrict__ dvv, double* out, int o, int v) {
+  const int n = o + v;
+  const int64_t total = (int64_t)n * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int p = (int)(idx / n), q = (int)(idx - (int64_t)p * n);
+    double val;
+    if (p < o && q < o) {
+      val = (doo[p * o + q] + doo[q * o + p]) * 0.5;
+      if (p == q) val += 1.0;
+    } else if (p < o) {
+      val = (l1[p * v + (q - o)] + dvoT[p * v + (q - o)]) * 0.5;
+    } else if (q < o) {
+      val = (l1[q * v + (p - o)] + dvoT[q * v + (p - o)]) * 0.5;
+    } else {
+      int a = p - o, b = q - o;
+      val = (dvv[(int64_t)a * v + b] + dvv[(int64_t)b * v + a]) * 0.5;
+    }
+    out[idx] = val;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_permute(const PermArgs& a, cudaStream_t st) {
+  // squeeze unit dims and merge adjacent dims that are contiguous on both sides
+  int64_t dim[KMAXD], si[KMAXD], so[KMAXD];
+  int nd = 0;
+  int64_t total = 1;
+  for (int d = 0; d < a.nd; ++d) {
+    total *= a.dim[d];
+    if (a.dim[d] == 1) continue;
+    if (nd > 0 && si[nd - 1] == a.sin[d] * a.dim[d] && so[nd - 1] == a.sout[d] * a.dim[d]) {
+      dim[nd - 1] *= a.dim[d];
+      si[nd - 1] = a.sin[d];
+      so[nd - 1] = a.sout[d];
+    } else {
+      dim[nd] = a.dim[d]; si[nd] = a.sin[d]; so[nd] = a.sout[d];
+      ++nd;
+    }
+  }
+  if (total == 0) return cudaSuccess;
+  if (nd == 0) { dim[0] = 1; si[0] = 1; so[0] = 1; nd = 1; }
+  int fi = 0, fo = 0;
+  for (int d = 1; d < nd; ++d) {
+    if (si[d] < si[fi]) fi = d;
+    if (so[d] < so[fo]) fo = d;
+  }
+  PermK k{};
+  k.in = a.in; k.out = a.out; k.alpha = a.alpha; k.beta = a.beta; k.total = total;
+  if (fi == fo) {
+    int n = 0;
+    for (int d = 0; d < nd; ++d)
+      if (d != fo) { k.dim[n] = dim[d]; k.sin[n] = si[d]; k.sout[n] = so[d]; ++n; }
+    k.dim[n] = dim[fo]; k.sin[n] = si[fo]; k.sout[n] = so[fo]; ++n;
+    k.nd = n;
+    permute_linear_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(k);
+  } else {
+    int n = 0;
+    int64_t rest = 1;
+    for (int d = 0; d < nd; ++d)
+      if (d != fo && d != fi) { k.dim[n] = dim[d]; k.sin[n] = si[d]; k.sout[n] = so[d]; rest *= dim[d]; ++n; }
+    k.nd = n;
+    k.d_fi = dim[fi]; k.fi_sin = si[fi]; k.fi_sout = so[fi];
+    k.d_fo = dim[fo]; k.fo_sin = si[fo]; k.fo_sout = so[fo];
+    int64_t blocks = ((k.d_fi + 31) / 32) * ((k.d_fo + 31) / 32) * rest;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    permute_tiled_kernel<<<(unsigned)blocks, 256, 0, st>>>(k);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill(double* c, int64_t n, double value, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  fill_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, st>>>(c, n, value);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, double* C, int64_t sr, int64_t sc,
+                          double alpha, double beta, cudaStream_t st) {
+  if (M * N <= 0) return cudaSuccess;
+  reduce_kernel<<<grid_for(M * N, EW_THREADS), EW_THREADS, 0, st>>>(part, nz, M, N, C, sr, sc, alpha, beta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double coef, cudaStream_t st) {
+  int64_t total = (int64_t)o * o * v * v;
+  if (total <= 0) return cudaSuccess;
+  tau_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(t2, t1, out, o, v, coef);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const PackArgs& a, cudaStream_t st) {
+  int64_t rows = (a.flags & 1) ? a.d0 * (a.d0 - 1) / 2 : a.d0 * a.d1;
+  int64_t cols = (a.flags & 2) ? a.d2 * (a.d2 - 1) / 2 : a.d2 * a.d3;
+  if (rows * cols <= 0) return cudaSuccess;
+  pack_kernel<<<grid_for(rows * cols, EW_THREADS * 2), EW_THREADS, 0, st>>>(a, rows, cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(const PackArgs& a, cudaStream_t st) {
+  int64_t total = a.d0 * a.d1 * a.d2 * a.d3;
+  if (total <= 0) return cudaSuccess;
+  unpack_kernel<<<grid_for(total, EW_THREADS * 2), EW_THREADS, 0, st>>>(a, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finish(const double* r, const double* amp, const double* fock, int64_t ldf, double* out, int o,
+                          int v, int rank, int has_alpha, int equation, double alpha, cudaStream_t st) {
+  int64_t total = rank == 2 ? (int64_t)o * v : (int64_t)o * o * v * v;
+  if (total <= 0) return cudaSuccess;
+  size_t sm = sizeof(double) * (size_t)(o + v);
+  finish_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, sm, st>>>(r, amp, fock, ldf, out, o, v, rank,
+                                                                        has_alpha, equation, alpha);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_subdiff(const double* e, const double* v, double alpha, double* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  subdiff_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, st>>>(e, v, alpha, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dot(const double* a, const double* b, int64_t n, double* partial, int nblocks, double* scal,
+                       double alpha, double beta, cudaStream_t st) {
+  int nb = (int)std::min<int64_t>(nblocks, std::max<int64_t>(1, (n + EW_THREADS - 1) / EW_THREADS));
+  dot_partial_kernel<<<nb, EW_THREADS, 0, st>>>(a, b, n, partial);
+  dot_final_kernel<<<1, EW_THREADS, 0, st>>>(partial, nb, scal, alpha, beta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale_dev(double* c, int64_t n, const double* scal, double d0, double d1, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  scale_dev_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, st>>>(c, n, scal, d0, d1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diag_add(double* c, int64_t ldc, int64_t m, const double* fock, int64_t ldf, int64_t foff,
+                            double alpha, cudaStream_t st) {
+  if (m <= 0) return cudaSuccess;
+  diag_add_kernel<<<grid_for(m, 128), 128, 0, st>>>(c, ldc, m, fock, ldf, foff, alpha);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rdm1(const double* doo, const double* dvoT, const double* l1, const double* dvv, double* out,
+                        int o, int v, cudaStream_t st) {
+  int64_t total = (int64_t)(o + v) * (o + v);
+  rdm1_kernel<<<grid_for(total, EW_THREADS), EW_THREADS, 0, st>>>(doo, dvoT, l1, dvv, out, o, v);
+  return cudaGetLastError();
+}
+
+}  // namespace ecw

@@ -1,0 +1,74 @@
+// kernels.h — launchers of the hand-written sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ecw {
+
+struct GemmArgs {
+  const double* A;
+  const double* B;
+  double* C;
+  int64_t M, N, K, lda, ldb, ldc, sA, sB, sC, batch, splitk, kchunk;
+  int ta, tb;
+  double alpha, beta;
+  int vecA, vecB, vecC;   // filled by launch_gemm (16-byte cp.async / double2 stores allowed)
+};
+
+int gemm_pick_config(int64_t M, int64_t N);
+cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st, int force_cfg = -1);
+
+constexpr int KMAXD = 6;
+struct PermArgs {
+  const double* in;
+  double* out;
+  int nd;
+  int64_t dim[KMAXD], sin[KMAXD], sout[KMAXD];
+  double alpha, beta;
+};
+cudaError_t launch_permute(const PermArgs& a, cudaStream_t st);
+
+cudaError_t launch_fill(double* c, int64_t n, double value, cudaStream_t st);
+// partial[z][M*N] -> C[m*sr + n*sc] = alpha*sum + beta*C
+cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, double* C, int64_t sr,
+                          int64_t sc, double alpha, double beta, cudaStream_t st);
+// out[ijab] = t2[ijab] + coef*(t1[ia]t1[jb] - t1[ib]t1[ja])
+cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double coef, cudaStream_t st);
+
+struct PackArgs {
+  const double* src;   // 4-index view (pack) / matrix (unpack)
+  double* dst;
+  int64_t d0, d1, d2, d3;          // dims of the 4-index side
+  int64_t s0, s1, s2, s3;          // strides of the 4-index side
+  int64_t ld;                      // leading dim of the matrix side
+  int flags;
+  double alpha, beta;
+};
+cudaError_t launch_pack(const PackArgs& a, cudaStream_t st);
+cudaError_t launch_unpack(const PackArgs& a, cudaStream_t st);
+
+// residual -> update (CCSD.py:316-338); fock is the bare n x n Fock matrix
+cudaError_t launch_finish(const double* r, const double* amp, const double* fock, int64_t ldf, double* out,
+                          int o, int v, int rank, int has_alpha, int equation, double alpha, cudaStream_t st);
+cudaError_t launch_subdiff(const double* e, const double* v, double alpha, double* out, int64_t n, cudaStream_t st);
+cudaError_t launch_dot(const double* a, const double* b, int64_t n, double* partial, int nblocks, double* scal,
+                       double alpha, double beta, cudaStream_t st);
+cudaError_t launch_scale_dev(double* c, int64_t n, const double* scal, double d0, double d1, cudaStream_t st);
+cudaError_t launch_diag_add(double* c, int64_t ldc, int64_t m, const double* fock, int64_t ldf, int64_t foff,
+                            double alpha, cudaStream_t st);
+cudaError_t launch_rdm1(const double* doo, const double* dvoT, const double* l1, const double* dvv, double* out,
+                        int o, int v, cudaStream_t st);
+
+// synthetic, function-defined inputs (DESIGN.md "Synthetic inputs"); kind selects the tensor
+enum SynthKind : int {
+  SY_OOOO = 0, SY_OOOV, SY_OOVV, SY_OOVV_PH, SY_OVOV_PH, SY_OVVV, SY_OOOO_P, SY_OOVV_P, SY_OVVV_P, SY_VVVV_P,
+  SY_FOCK, SY_FSP, SY_T1, SY_L1, SY_T2, SY_L2
+};
+// row0/nrows restrict generation to a leading-index range (shards of vvvv_p / ovvv)
+cudaError_t launch_synth(int kind, double* out, int o, int v, int64_t row0, int64_t nrows, double scale,
+                         cudaStream_t st);
+// constant layouts derived from dense canonical blocks
+cudaError_t launch_eris_layouts_from_dense(const double* oovv, const double* ovov, double* oovv_ph, double* ovov_ph,
+                                           int o, int v, cudaStream_t st);
+
+}  // namespace ecw

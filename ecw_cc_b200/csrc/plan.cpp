@@ -1,0 +1,638 @@
+// plan.cpp — plan container, workspace arena and the binary-contraction
+// lowering (TTGT with batch / split-K / layout search).  Host-only C++.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <sstream>
+
+namespace ecw {
+
+int64_t npair(int64_t n) { return n * (n - 1) / 2; }
+
+const char* slot_name(int s) {
+  static const char* names[] = {
+      "ws", "t1", "t2", "l1", "l2", "fsp", "fock", "out1", "out2", "rdm1", "scal",
+      "oooo", "ooov", "oovv", "oovv_ph", "ovov_ph", "ovvv", "oooo_p", "oovv_p", "ovvv_p", "vvvv_p",
+      "a0", "a1", "a2", "a3", "a4", "a5", "a6", "a7", "a8", "a9",
+      "b0", "b1", "b2", "b3", "b4", "b5", "b6", "b7"};
+  if (s < 0 || s >= S_COUNT) return "?";
+  return names[s];
+}
+
+Tensor make_tensor(int slot, int64_t off, std::initializer_list<int64_t> dims) {
+  Tensor t;
+  t.slot = slot;
+  t.off = off;
+  t.nd = (int)dims.size();
+  if (t.nd > MAXD) throw PlanError("tensor rank > MAXD");
+  int i = 0;
+  for (auto d : dims) t.dim[i++] = d;
+  int64_t s = 1;
+  for (i = t.nd - 1; i >= 0; --i) { t.str[i] = s; s *= t.dim[i]; }
+  return t;
+}
+
+static bool is_contig(const Tensor& t) {
+  int64_t s = 1;
+  for (int i = t.nd - 1; i >= 0; --i) {
+    if (t.dim[i] != 1 && t.str[i] != s) return false;
+    s *= t.dim[i];
+  }
+  return true;
+}
+
+Tensor reshape(const Tensor& t, std::initializer_list<int64_t> dims) {
+  if (!is_contig(t)) throw PlanError("reshape of non-contiguous view");
+  Tensor r = make_tensor(t.slot, t.off, dims);
+  if (r.size() != t.size()) throw PlanError("reshape size mismatch");
+  return r;
+}
+
+Tensor block2(const Tensor& m, int64_t r0, int64_t nr, int64_t c0, int64_t nc) {
+  if (m.nd != 2) throw PlanError("block2 needs a matrix");
+  Tensor r = m;
+  r.off = m.off + r0 * m.str[0] + c0 * m.str[1];
+  r.dim[0] = nr;
+  r.dim[1] = nc;
+  return r;
+}
+
+Tensor transpose2(const Tensor& m) {
+  if (m.nd != 2) throw PlanError("transpose2 needs a matrix");
+  Tensor r = m;
+  std::swap(r.dim[0], r.dim[1]);
+  std::swap(r.str[0], r.str[1]);
+  return r;
+}
+
+Tensor slice0(const Tensor& t, int64_t i0, int64_t n) {
+  Tensor r = t;
+  r.off = t.off + i0 * t.str[0];
+  r.dim[0] = n;
+  return r;
+}
+
+// ---------------------------------------------------------------- arena
+int64_t Arena::alloc(int64_t n) {
+  n = (n + 31) / 32 * 32;  // 256-byte granularity
+  if (n == 0) n = 32;
+  for (size_t i = 0; i < blks.size(); ++i) {
+    if (!blks[i].used && blks[i].size >= n) {
+      if (blks[i].size > n) {
+        Blk rest{blks[i].off + n, blks[i].size - n, false};
+        blks[i].size = n;
+        blks.insert(blks.begin() + i + 1, rest);
+      }
+      blks[i].used = true;
+      return blks[i].off;
+    }
+  }
+  int64_t end = blks.empty() ? 0 : blks.back().off + blks.back().size;
+  if (!blks.empty() && !blks.back().used) {  // grow the trailing free block
+    blks.back().size = n;
+    blks.back().used = true;
+    peak = std::max(peak, blks.back().off + n);
+    return blks.back().off;
+  }
+  blks.push_back(Blk{end, n, true});
+  peak = std::max(peak, end + n);
+  return end;
+}
+
+void Arena::release(int64_t off) {
+  for (size_t i = 0; i < blks.size(); ++i) {
+    if (blks[i].off == off && blks[i].used) {
+      blks[i].used = false;
+      if (i + 1 < blks.size() && !blks[i + 1].used) {
+        blks[i].size += blks[i + 1].size;
+        blks.erase(blks.begin() + i + 1);
+      }
+      if (i > 0 && !blks[i - 1].used) {
+        blks[i - 1].size += blks[i].size;
+        blks.erase(blks.begin() + i);
+      }
+      return;
+    }
+  }
+  throw PlanError("arena: release of unknown block");
+}
+
+Tensor Plan::tmpv(const std::vector<int64_t>& dims) {
+  Tensor t;
+  t.slot = S_WS;
+  t.nd = (int)dims.size();
+  if (t.nd > MAXD) throw PlanError("tensor rank > MAXD");
+  int64_t s = 1;
+  for (int i = t.nd - 1; i >= 0; --i) { t.dim[i] = dims[i]; t.str[i] = s; s *= dims[i]; }
+  t.off = arena.alloc(s);
+  return t;
+}
+
+Tensor Plan::tmp(std::initializer_list<int64_t> dims) { return tmpv(std::vector<int64_t>(dims)); }
+
+void Plan::release(const Tensor& t) {
+  if (t.slot != S_WS) throw PlanError("release of non-workspace tensor");
+  arena.release(t.off);
+}
+
+// ---------------------------------------------------------------- simple ops
+void Plan::permute(double alpha, const Tensor& A, const char* sa, double beta, const Tensor& C,
+                   const char* sc, const char* note) {
+  int n = (int)strlen(sc);
+  if ((int)strlen(sa) != n || A.nd != n || C.nd != n) throw PlanError(std::string("permute rank mismatch: ") + sa + "->" + sc);
+  Op op;
+  op.kind = OP_PERMUTE;
+  op.alpha = alpha;
+  op.beta = beta;
+  op.c = C;
+  op.a = A;
+  for (int p = 0; p < n; ++p) {
+    const char* q = strchr(sa, sc[p]);
+    if (!q) throw PlanError(std::string("permute label mismatch: ") + sa + "->" + sc);
+    int qi = (int)(q - sa);
+    if (A.dim[qi] != C.dim[p]) throw PlanError(std::string("permute dim mismatch: ") + sa + "->" + sc);
+    op.a.dim[p] = A.dim[qi];
+    op.a.str[p] = A.str[qi];
+  }
+  op.note = std::string(note) + " [" + sa + "->" + sc + "]";
+  perm_bytes += 8.0 * (double)C.size() * (beta != 0.0 ? 3.0 : 2.0);
+  ops.push_back(op);
+}
+
+void Plan::axpby(double alpha, const Tensor& A, double beta, const Tensor& C, const char* note) {
+  static const char* lab = "pqrstu";
+  if (A.nd != C.nd) throw PlanError("axpby rank mismatch");
+  std::string s(lab, lab + A.nd);
+  permute(alpha, A, s.c_str(), beta, C, s.c_str(), note);
+}
+
+void Plan::fill(const Tensor& C, double value) {
+  Op op;
+  op.kind = OP_FILL;
+  op.c = C;
+  op.alpha = value;
+  ops.push_back(op);
+}
+
+void Plan::tau(const Tensor& t2, const Tensor& t1, double coef, const Tensor& out) {
+  Op op;
+  op.kind = OP_TAU;
+  op.a = t2;
+  op.b = t1;
+  op.c = out;
+  op.alpha = coef;
+  ops.push_back(op);
+}
+
+void Plan::pack(double alpha, const Tensor& a4, int flags, double beta, const Tensor& c2) {
+  if (a4.nd != 4 || c2.nd != 2) throw PlanError("pack: need 4-index source and matrix destination");
+  int64_t rows = (flags & 1) ? npair(a4.dim[0]) : a4.dim[0] * a4.dim[1];
+  int64_t cols = (flags & 2) ? npair(a4.dim[2]) : a4.dim[2] * a4.dim[3];
+  if ((flags & 1) && a4.dim[0] != a4.dim[1]) throw PlanError("pack: first pair dims differ");
+  if ((flags & 6) && a4.dim[2] != a4.dim[3]) throw PlanError("pack: second pair dims differ");
+  if (rows != c2.dim[0] || cols != c2.dim[1]) throw PlanError("pack: destination shape mismatch");
+  Op op;
+  op.kind = OP_PACK;
+  op.a = a4;
+  op.c = c2;
+  op.alpha = alpha;
+  op.beta = beta;
+  op.i0 = flags;
+  ops.push_back(op);
+}
+
+void Plan::unpack(double alpha, const Tensor& a2, int flags, double beta, const Tensor& c4) {
+  if (c4.nd != 4 || a2.nd != 2) throw PlanError("unpack: need matrix source and 4-index destination");
+  int64_t rows = (flags & 1) ? npair(c4.dim[0]) : c4.dim[0] * c4.dim[1];
+  int64_t cols = (flags & 2) ? npair(c4.dim[2]) : c4.dim[2] * c4.dim[3];
+  if (rows != a2.dim[0] || cols != a2.dim[1]) throw PlanError("unpack: source shape mismatch");
+  Op op;
+  op.kind = OP_UNPACK;
+  op.a = a2;
+  op.c = c4;
+  op.alpha = alpha;
+  op.beta = beta;
+  op.i0 = flags;
+  ops.push_back(op);
+}
+
+void Plan::finish(const Tensor& resid, const Tensor& amp, const Tensor& fock, int nocc, int rank,
+                  int has_alpha, int equation, double alpha, const Tensor& out) {
+  Op op;
+  op.kind = OP_FINISH;
+  op.a = resid;
+  op.b = amp;
+  op.d = fock;
+  op.c = out;
+  op.i0 = nocc;
+  op.i1 = rank;
+  op.i2 = has_alpha;
+  op.i3 = equation;
+  op.alpha = alpha;
+  ops.push_back(op);
+}
+
+void Plan::dot(double alpha, const Tensor& A, const Tensor& B, double beta, int k) {
+  if (A.nd != B.nd) throw PlanError("dot rank mismatch");
+  for (int i = 0; i < A.nd; ++i) if (A.dim[i] != B.dim[i]) throw PlanError("dot shape mismatch");
+  Op op;
+  op.kind = OP_DOT;
+  op.a = A;
+  op.b = B;
+  op.alpha = alpha;
+  op.beta = beta;
+  op.i0 = k;
+  // per-block partial sums (deterministic two-stage reduction)
+  op.i1 = 1024;
+  op.c = tmp({op.i1});
+  ops.push_back(op);
+  release(op.c);
+}
+
+void Plan::scale_dev(const Tensor& C, double d0, double d1, int k) {
+  Op op;
+  op.kind = OP_SCALE_DEV;
+  op.c = C;
+  op.d0 = d0;
+  op.d1 = d1;
+  op.i0 = k;
+  ops.push_back(op);
+}
+
+void Plan::diag_add(const Tensor& Cmat, double alpha, const Tensor& fock, int64_t foff) {
+  Op op;
+  op.kind = OP_DIAG_ADD;
+  op.c = Cmat;
+  op.d = fock;
+  op.alpha = alpha;
+  op.i0 = foff;
+  ops.push_back(op);
+}
+
+void Plan::rdm1(const Tensor& doo, const Tensor& dvoT, const Tensor& l1, const Tensor& dvv, const Tensor& out) {
+  Op op;
+  op.kind = OP_RDM1;
+  op.a = doo;
+  op.b = dvoT;
+  op.d = l1;
+  op.e = dvv;
+  op.c = out;
+  ops.push_back(op);
+}
+
+void Plan::ewise(int sub, const Tensor& a, const Tensor& b, const Tensor& c, double alpha, double beta,
+                 int64_t i1, int64_t i2) {
+  Op op;
+  op.kind = OP_EWISE;
+  op.a = a;
+  op.b = b;
+  op.c = c;
+  op.alpha = alpha;
+  op.beta = beta;
+  op.i0 = sub;
+  op.i1 = i1;
+  op.i2 = i2;
+  ops.push_back(op);
+}
+
+// ---------------------------------------------------------------- contraction engine
+namespace {
+
+struct Group {
+  bool ok = true;
+  int64_t dim = 1;
+  int64_t str = 0;   // stride of the merged index (0 for an empty group)
+};
+
+// Merge the labels `g` (ordered) of tensor T (labels s) into one index.
+Group merge(const Tensor& T, const char* s, const std::string& g) {
+  Group r;
+  int64_t next_str = -1;  // stride the next (more significant) label must have
+  for (int k = (int)g.size() - 1; k >= 0; --k) {
+    const char* q = strchr(s, g[k]);
+    if (!q) { r.ok = false; return r; }
+    int p = (int)(q - s);
+    if (T.dim[p] == 1) continue;
+    if (next_str < 0) {
+      r.str = T.str[p];
+      r.dim = T.dim[p];
+      next_str = T.str[p] * T.dim[p];
+    } else {
+      if (T.str[p] != next_str) { r.ok = false; return r; }
+      r.dim *= T.dim[p];
+      next_str = T.str[p] * T.dim[p];
+    }
+  }
+  return r;
+}
+
+struct MatView {
+  bool rm = false, cm = false;   // row-major (cols contiguous) / col-major (rows contiguous) possible
+  int64_t ld_rm = 0, ld_cm = 0;
+  int64_t rows = 1, cols = 1;
+  bool any = false;              // both groups mergeable (arbitrary strides)
+  int64_t sr = 0, scol = 0;
+};
+
+MatView mat_view(const Tensor& T, const char* s, const std::string& rows, const std::string& cols) {
+  MatView m;
+  Group r = merge(T, s, rows), c = merge(T, s, cols);
+  if (!r.ok || !c.ok) return m;
+  m.any = true;
+  m.rows = r.dim;
+  m.cols = c.dim;
+  m.sr = r.str;
+  m.scol = c.str;
+  if (c.dim == 1 || c.str == 1) {
+    m.rm = true;
+    m.ld_rm = (r.dim == 1) ? std::max<int64_t>(c.dim, 1) : r.str;
+    if (m.ld_rm < c.dim) m.rm = false;
+  }
+  if (r.dim == 1 || r.str == 1) {
+    m.cm = true;
+    m.ld_cm = (c.dim == 1) ? std::max<int64_t>(r.dim, 1) : c.str;
+    if (m.ld_cm < r.dim) m.cm = false;
+  }
+  return m;
+}
+
+std::string ordered(const std::string& set, const char* order) {
+  std::string r;
+  for (const char* p = order; *p; ++p)
+    if (set.find(*p) != std::string::npos) r.push_back(*p);
+  return r;
+}
+
+std::string minus(const std::string& a, const std::string& b) {
+  std::string r;
+  for (char c : a) if (b.find(c) == std::string::npos) r.push_back(c);
+  return r;
+}
+
+int64_t dims_of(const std::string& g, const std::map<char, int64_t>& dm) {
+  int64_t n = 1;
+  for (char c : g) n *= dm.at(c);
+  return n;
+}
+
+struct Choice {
+  double cost = 1e300;
+  std::string bt, om, on, ok;
+  int bcls = 0;  // 0 none, 1 I, 2 J, 3 K
+  bool a_dir = false, b_dir = false, c_dir = false, c_swap = false;
+  int ta = 0, tb = 0;
+  int64_t lda = 0, ldb = 0, ldc = 0, sA = 0, sB = 0, sC = 0;
+  int64_t c_sr = 0, c_sc = 0;   // strided-C target for the reduce path
+};
+
+}  // namespace
+
+void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
+                    double beta, const Tensor& C, const char* sc, const char* note) {
+  std::string tag = std::string(sa) + "," + sb + "->" + sc;
+  if ((int)strlen(sa) != A.nd || (int)strlen(sb) != B.nd || (int)strlen(sc) != C.nd)
+    throw PlanError("contract rank mismatch: " + tag);
+  std::map<char, int64_t> dm;
+  auto reg = [&](const Tensor& T, const char* s) {
+    for (int i = 0; i < T.nd; ++i) {
+      auto it = dm.find(s[i]);
+      if (it == dm.end()) dm[s[i]] = T.dim[i];
+      else if (it->second != T.dim[i]) throw PlanError("contract dim mismatch for '" + std::string(1, s[i]) + "' in " + tag);
+    }
+  };
+  reg(A, sa); reg(B, sb); reg(C, sc);
+  std::string I, J, K;
+  for (auto& kv : dm) {
+    bool ia = strchr(sa, kv.first), ib = strchr(sb, kv.first), ic = strchr(sc, kv.first);
+    if (ia && ic && !ib) I.push_back(kv.first);
+    else if (ib && ic && !ia) J.push_back(kv.first);
+    else if (ia && ib && !ic) K.push_back(kv.first);
+    else throw PlanError("contract: unsupported label pattern in " + tag);
+  }
+  const int64_t szA = A.size(), szB = B.size(), szC = C.size();
+
+  // candidate batch sets
+  std::vector<std::string> cands{""};
+  for (auto& kv : dm) cands.push_back(std::string(1, kv.first));
+  for (int p = 0; p + 1 < C.nd; ++p) {
+    char x = sc[p], y = sc[p + 1];
+    bool bi = I.find(x) != std::string::npos && I.find(y) != std::string::npos;
+    bool bj = J.find(x) != std::string::npos && J.find(y) != std::string::npos;
+    if (bi || bj) cands.push_back(std::string{x, y});
+  }
+
+  Choice best;
+  for (auto& bt : cands) {
+    int bcls = 0;
+    if (!bt.empty()) bcls = I.find(bt[0]) != std::string::npos ? 1 : (J.find(bt[0]) != std::string::npos ? 2 : 3);
+    int64_t nb = dims_of(bt, dm);
+    if (!bt.empty() && nb == 1) continue;
+    // batch strides
+    Group gA, gB, gC;
+    if (bcls == 1 || bcls == 3) { gA = merge(A, sa, bt); if (!gA.ok) continue; }
+    if (bcls == 2 || bcls == 3) { gB = merge(B, sb, bt); if (!gB.ok) continue; }
+    if (bcls == 1 || bcls == 2) { gC = merge(C, sc, bt); if (!gC.ok) continue; }
+    std::string Ir = minus(I, bt), Jr = minus(J, bt), Kr = minus(K, bt);
+    int64_t Md = dims_of(Ir, dm), Nd = dims_of(Jr, dm);
+    for (int m = 0; m < 2; ++m)
+      for (int n = 0; n < 2; ++n)
+        for (int k = 0; k < 2; ++k) {
+          Choice ch;
+          ch.bt = bt;
+          ch.bcls = bcls;
+          ch.om = ordered(Ir, m ? sc : sa);
+          ch.on = ordered(Jr, n ? sc : sb);
+          ch.ok = ordered(Kr, k ? sb : sa);
+          MatView va = mat_view(A, sa, ch.om, ch.ok);
+          MatView vb = mat_view(B, sb, ch.ok, ch.on);
+          MatView vc = mat_view(C, sc, ch.om, ch.on);
+          double cost = 0.0;
+          if (va.rm) { ch.a_dir = true; ch.ta = 0; ch.lda = va.ld_rm; }
+          else if (va.cm) { ch.a_dir = true; ch.ta = 1; ch.lda = va.ld_cm; }
+          else cost += 2.0 * szA;
+          if (vb.rm) { ch.b_dir = true; ch.tb = 0; ch.ldb = vb.ld_rm; }
+          else if (vb.cm) { ch.b_dir = true; ch.tb = 1; ch.ldb = vb.ld_cm; }
+          else cost += 2.0 * szB;
+          if (bcls == 3) {
+            // reduce path: any strided C target works
+            if (vc.any) { ch.c_dir = true; ch.c_sr = vc.sr; ch.c_sc = vc.scol; }
+            else cost += 3.0 * szC;
+            cost += 2.0 * (double)nb * Md * Nd + 0.5;
+          } else {
+            if (vc.rm) { ch.c_dir = true; ch.ldc = vc.ld_rm; ch.c_sr = vc.sr; ch.c_sc = vc.scol; }
+            else if (vc.cm) { ch.c_dir = true; ch.c_swap = true; ch.ldc = vc.ld_cm; ch.c_sr = vc.sr; ch.c_sc = vc.scol; }
+            else cost += (beta != 0.0 ? 3.0 : 2.0) * szC;
+            if (vc.any && !ch.c_dir) { ch.c_sr = vc.sr; ch.c_sc = vc.scol; }
+            if (bcls != 0) cost += 0.25;
+            // many tiny batched GEMMs are slow: discourage when the per-batch problem is small
+            if (bcls != 0 && (double)Md * Nd < 1024.0) cost += 1e3 * (double)nb;
+          }
+          ch.sA = (bcls == 1 || bcls == 3) ? gA.str : 0;
+          ch.sB = (bcls == 2 || bcls == 3) ? gB.str : 0;
+          ch.sC = (bcls == 1 || bcls == 2) ? gC.str : 0;
+          ch.cost = cost;
+          if (cost < best.cost) best = ch;
+        }
+  }
+  if (best.cost >= 1e299) throw PlanError("contract: no lowering for " + tag);
+
+  const Choice& ch = best;
+  const int64_t nb = ch.bt.empty() ? 1 : dims_of(ch.bt, dm);
+  const int64_t Md = dims_of(ch.om, dm), Nd = dims_of(ch.on, dm), Kd = dims_of(ch.ok, dm);
+  auto dimvec = [&](const std::string& g) {
+    std::vector<int64_t> v;
+    for (char c : g) v.push_back(dm.at(c));
+    return v;
+  };
+  std::vector<Tensor> to_free;
+
+  Op g;
+  g.kind = OP_GEMM;
+  g.M = Md; g.N = Nd; g.K = Kd;
+  g.batch = nb;
+  g.alpha = alpha;
+  g.note = std::string(note) + " [" + tag + "]";
+
+  // ---- A operand
+  if (ch.a_dir) {
+    g.a = A; g.ta = ch.ta; g.lda = ch.lda; g.sA = ch.sA;
+  } else {
+    std::string lay = ((ch.bcls == 1 || ch.bcls == 3) ? ch.bt : std::string()) + ch.om + ch.ok;
+    std::vector<int64_t> dv = dimvec(lay);
+    if (dv.empty()) dv.push_back(1);
+    Tensor tA = tmpv(dv);
+    if (lay.empty()) lay = "";  // scalar case cannot occur (A has rank>=1)
+    permute(1.0, A, sa, 0.0, tA, lay.c_str(), "engine:A");
+    to_free.push_back(tA);
+    g.a = tA; g.ta = 0; g.lda = std::max<int64_t>(Kd, 1);
+    g.sA = (ch.bcls == 1 || ch.bcls == 3) ? Md * Kd : 0;
+  }
+  // ---- B operand
+  if (ch.b_dir) {
+    g.b = B; g.tb = ch.tb; g.ldb = ch.ldb; g.sB = ch.sB;
+  } else {
+    std::string lay = ((ch.bcls == 2 || ch.bcls == 3) ? ch.bt : std::string()) + ch.ok + ch.on;
+    Tensor tB = tmpv(dimvec(lay));
+    permute(1.0, B, sb, 0.0, tB, lay.c_str(), "engine:B");
+    to_free.push_back(tB);
+    g.b = tB; g.tb = 0; g.ldb = std::max<int64_t>(Nd, 1);
+    g.sB = (ch.bcls == 2 || ch.bcls == 3) ? Kd * Nd : 0;
+  }
+
+  // ---- split-K decision (only when there is no free-index batch)
+  int64_t R = (ch.bcls == 3) ? nb : 1;
+  int64_t S = 1;
+  if (ch.bcls == 0 || ch.bcls == 3) {
+    int64_t tiles = ((Md + 127) / 128) * ((Nd + 127) / 128) * R;
+    if (tiles < 2 * sm_count && Kd >= 1024) {
+      S = std::min<int64_t>((2 * sm_count + tiles - 1) / tiles, Kd / 512);
+      while (S > 1 && (double)S * R * Md * Nd * 8.0 > 512e6) --S;
+      if (S < 2) S = 1;
+    }
+  }
+
+  if (R * S > 1) {
+    // GEMM into partials [R*S, M, N], then reduce into the target
+    Tensor part = tmp({R * S, Md, Nd});
+    g.c = part; g.ldc = std::max<int64_t>(Nd, 1); g.sC = Md * Nd; g.beta = 0.0;
+    g.batch = R * S;
+    g.splitk = S;
+    g.kchunk = S > 1 ? ((Kd + S - 1) / S + 15) / 16 * 16 : Kd;
+    if (S > 1) {  // chunks may not be empty for any s
+      while (S > 1 && (S - 1) * g.kchunk >= Kd) { --S; }
+      g.splitk = S; g.batch = R * S;
+    }
+    gemm_flops += 2.0 * (double)Md * Nd * Kd * (double)R;
+    ops.push_back(g);
+    Op r;
+    r.kind = OP_REDUCE;
+    r.a = part;
+    r.i0 = R * S;
+    r.M = Md; r.N = Nd;
+    r.alpha = 1.0;
+    r.note = g.note;
+    if (ch.c_dir) {
+      r.c = C; r.beta = beta; r.i1 = ch.c_sr; r.i2 = ch.c_sc;
+      if (Md == 1) r.i1 = 0;
+      if (Nd == 1) r.i2 = 0;
+      ops.push_back(r);
+    } else {
+      std::string lay = ch.om + ch.on;
+      std::vector<int64_t> dv = dimvec(lay);
+      if (dv.empty()) dv.push_back(1);
+      Tensor tC = tmpv(dv);
+      r.c = tC; r.beta = 0.0; r.i1 = Nd; r.i2 = 1;
+      ops.push_back(r);
+      permute(1.0, tC, lay.c_str(), beta, C, sc, "engine:C");
+      release(tC);
+    }
+    release(part);
+  } else {
+    if (ch.c_dir) {
+      g.c = C; g.ldc = ch.ldc; g.sC = ch.sC; g.beta = beta;
+      if (ch.c_swap) {  // compute C^T = B^T A^T
+        std::swap(g.a, g.b);
+        std::swap(g.M, g.N);
+        std::swap(g.sA, g.sB);
+        int ta = g.ta, tb = g.tb;
+        int64_t lda = g.lda, ldb = g.ldb;
+        g.ta = !tb; g.tb = !ta; g.lda = ldb; g.ldb = lda;
+      }
+      gemm_flops += 2.0 * (double)Md * Nd * Kd * (double)nb;
+      ops.push_back(g);
+    } else {
+      std::string lay = ((ch.bcls == 1 || ch.bcls == 2) ? ch.bt : std::string()) + ch.om + ch.on;
+      std::vector<int64_t> dv = dimvec(lay);
+      if (dv.empty()) dv.push_back(1);
+      Tensor tC = tmpv(dv);
+      g.c = tC; g.ldc = std::max<int64_t>(Nd, 1); g.sC = Md * Nd; g.beta = 0.0;
+      gemm_flops += 2.0 * (double)Md * Nd * Kd * (double)nb;
+      ops.push_back(g);
+      permute(1.0, tC, lay.c_str(), beta, C, sc, "engine:C");
+      release(tC);
+    }
+  }
+  for (auto& t : to_free) release(t);
+}
+
+// ---------------------------------------------------------------- dump
+static void dump_tensor(std::ostringstream& o, const char* key, const Tensor& t) {
+  o << "\"" << key << "\":";
+  if (!t.valid()) { o << "null"; return; }
+  o << "{\"slot\":\"" << slot_name(t.slot) << "\",\"off\":" << t.off << ",\"dim\":[";
+  for (int i = 0; i < t.nd; ++i) o << (i ? "," : "") << t.dim[i];
+  o << "],\"str\":[";
+  for (int i = 0; i < t.nd; ++i) o << (i ? "," : "") << t.str[i];
+  o << "]}";
+}
+
+std::string Plan::dump_json() const {
+  static const char* kn[] = {"gemm", "reduce", "permute", "fill", "tau", "pack", "unpack", "finish",
+                             "dot", "scale_dev", "diag_add", "rdm1", "ewise"};
+  std::ostringstream o;
+  o.precision(17);
+  o << "{\"workspace_elems\":" << arena.peak << ",\"gemm_flops\":" << gemm_flops
+    << ",\"perm_bytes\":" << perm_bytes << ",\"ops\":[";
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const Op& p = ops[i];
+    if (i) o << ",";
+    o << "\n{\"kind\":\"" << kn[p.kind] << "\",";
+    dump_tensor(o, "a", p.a); o << ",";
+    dump_tensor(o, "b", p.b); o << ",";
+    dump_tensor(o, "c", p.c); o << ",";
+    dump_tensor(o, "d", p.d); o << ",";
+    dump_tensor(o, "e", p.e); o << ",";
+    o << "\"alpha\":" << p.alpha << ",\"beta\":" << p.beta << ",\"M\":" << p.M << ",\"N\":" << p.N
+      << ",\"K\":" << p.K << ",\"lda\":" << p.lda << ",\"ldb\":" << p.ldb << ",\"ldc\":" << p.ldc
+      << ",\"sA\":" << p.sA << ",\"sB\":" << p.sB << ",\"sC\":" << p.sC << ",\"batch\":" << p.batch
+      << ",\"ta\":" << p.ta << ",\"tb\":" << p.tb << ",\"splitk\":" << p.splitk << ",\"kchunk\":" << p.kchunk
+      << ",\"i0\":" << p.i0 << ",\"i1\":" << p.i1 << ",\"i2\":" << p.i2 << ",\"i3\":" << p.i3
+      << ",\"d0\":" << p.d0 << ",\"d1\":" << p.d1 << ",\"note\":\"" << p.note << "\"}";
+  }
+  o << "\n]}";
+  return o.str();
+}
+
+}  // namespace ecw

@@ -1,0 +1,138 @@
+// plan.h — execution plans for the coupled-cluster residual path.
+//
+// A Plan is a flat list of device operations (GEMMs, index permutes, a few
+// fused element-wise kernels) over buffer *slots*: caller-owned amplitude /
+// Fock / output arrays, the constant integral layouts of the eris container,
+// and one workspace arena whose offsets are fixed at plan-build time.  The
+// builders in ccsd_plan.cpp / ccs_plan.cpp state the reference equations
+// (CCSD.py:136-623, CCS.py:23-1518) as binary tensor contractions; the
+// contraction engine here lowers each one to (optional permutes) + one FP64
+// tensor-core GEMM.  Plans are pure host data: building one touches no CUDA
+// API, so the lowering can be inspected (ecw_plan_dump) and is replayed on the
+// stream by exec.cu, optionally captured into a CUDA graph.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+namespace ecw {
+
+constexpr int MAXD = 6;
+
+// Buffer slots.  Everything the kernels touch is (slot, element offset).
+enum Slot : int {
+  S_WS = 0,       // workspace arena (caller allocated, ecw_workspace_bytes)
+  S_T1, S_T2, S_L1, S_L2, S_FSP, S_FOCK,        // inputs (device, FP64, C order)
+  S_OUT1, S_OUT2, S_RDM1, S_SCAL,               // outputs; S_SCAL = 16 device scalars
+  // constant integral layouts (eris container)
+  S_OOOO, S_OOOV, S_OOVV, S_OOVV_PH, S_OVOV_PH, S_OVVV,
+  S_OOOO_P, S_OOVV_P, S_OVVV_P, S_VVVV_P,
+  // generic argument slots for the CCS entry points
+  S_A0, S_A1, S_A2, S_A3, S_A4, S_A5, S_A6, S_A7, S_A8, S_A9,
+  S_B0, S_B1, S_B2, S_B3, S_B4, S_B5, S_B6, S_B7,
+  S_COUNT
+};
+const char* slot_name(int s);
+
+struct Tensor {
+  int slot = -1;
+  int64_t off = 0;
+  int nd = 0;
+  int64_t dim[MAXD] = {0};
+  int64_t str[MAXD] = {0};
+  int64_t size() const { int64_t n = 1; for (int i = 0; i < nd; ++i) n *= dim[i]; return n; }
+  bool valid() const { return slot >= 0; }
+};
+
+Tensor make_tensor(int slot, int64_t off, std::initializer_list<int64_t> dims);
+Tensor reshape(const Tensor& t, std::initializer_list<int64_t> dims);   // contiguous only
+Tensor block2(const Tensor& m, int64_t r0, int64_t nr, int64_t c0, int64_t nc);  // 2-D sub-block
+Tensor transpose2(const Tensor& m);
+Tensor slice0(const Tensor& t, int64_t i0, int64_t n);                   // leading-dim range
+
+enum OpKind : int {
+  OP_GEMM = 0,    // C = alpha op(A) op(B) + beta C   (batched / split-K)
+  OP_REDUCE,      // C = alpha sum_z P[z] + beta C
+  OP_PERMUTE,     // C[..] = alpha A[perm ..] + beta C   (strided N-d copy)
+  OP_FILL,        // C = alpha
+  OP_TAU,         // C = t2 + alpha (t1 x t1 antisymmetrised)
+  OP_PACK,        // antisymmetric pair packing of a 4-index view
+  OP_UNPACK,      // inverse (scatter with signs)
+  OP_FINISH,      // residual -> update / subdiff (CCSD.py:316-338)
+  OP_DOT,         // scal[k] = beta scal[k] + alpha <A,B>
+  OP_SCALE_DEV,   // C *= d0 + d1 * scal[k]
+  OP_DIAG_ADD,    // C[i,i] += alpha * fock[off+i, off+i]
+  OP_RDM1,        // assemble the symmetrised rdm1 (CCSD.py:154-160)
+  OP_EWISE,       // small CCS element-wise helpers (sub-kind in i0)
+};
+
+struct Op {
+  int kind = 0;
+  Tensor a, b, c, d, e;       // operands (meaning per kind)
+  double alpha = 1.0, beta = 0.0;
+  // GEMM
+  int64_t M = 0, N = 0, K = 0, lda = 0, ldb = 0, ldc = 0;
+  int64_t sA = 0, sB = 0, sC = 0, batch = 1;
+  int ta = 0, tb = 0;         // 0: K-contiguous A / N-contiguous B (row-major), 1: transposed
+  int64_t splitk = 1, kchunk = 0;
+  // generic ints / doubles
+  int64_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+  double d0 = 0.0, d1 = 0.0;
+  std::string note;
+};
+
+struct Arena {
+  struct Blk { int64_t off, size; bool used; };
+  std::vector<Blk> blks;
+  int64_t peak = 0;
+  int64_t alloc(int64_t n);
+  void release(int64_t off);
+};
+
+struct PlanError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+class Plan {
+ public:
+  std::vector<Op> ops;
+  Arena arena;
+  int sm_count = 148;
+  double gemm_flops = 0.0;     // sum of 2MNK over GEMM ops (executed flops)
+  double perm_bytes = 0.0;     // bytes moved by engine-inserted permutes
+
+  Tensor tmp(std::initializer_list<int64_t> dims);
+  Tensor tmpv(const std::vector<int64_t>& dims);
+  void release(const Tensor& t);
+
+  // C[sc] = alpha * sum_K A[sa] B[sb] + beta * C[sc]
+  void contract(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
+                double beta, const Tensor& C, const char* sc, const char* note = "");
+  // C[sc] = alpha * A[sa] + beta * C[sc]   (sa is a permutation of sc)
+  void permute(double alpha, const Tensor& A, const char* sa, double beta, const Tensor& C,
+               const char* sc, const char* note = "");
+  void axpby(double alpha, const Tensor& A, double beta, const Tensor& C, const char* note = "");
+  void fill(const Tensor& C, double value);
+  void tau(const Tensor& t2, const Tensor& t1, double coef, const Tensor& out);
+  // pack/unpack: flags bit0 = first pair packed, bit1 = second pair packed,
+  //              bit2 = antisymmetrise second pair while packing (x[..rs]-x[..sr])
+  void pack(double alpha, const Tensor& a4, int flags, double beta, const Tensor& c2);
+  void unpack(double alpha, const Tensor& a2, int flags, double beta, const Tensor& c4);
+  void finish(const Tensor& resid, const Tensor& amp, const Tensor& fock, int nocc, int rank,
+              int has_alpha, int equation, double alpha, const Tensor& out);
+  void dot(double alpha, const Tensor& A, const Tensor& B, double beta, int k);
+  void scale_dev(const Tensor& C, double d0, double d1, int k);
+  void diag_add(const Tensor& Cmat, double alpha, const Tensor& fock, int64_t foff);
+  void rdm1(const Tensor& doo, const Tensor& dvoT, const Tensor& l1, const Tensor& dvv, const Tensor& out);
+  void ewise(int sub, const Tensor& a, const Tensor& b, const Tensor& c, double alpha, double beta,
+             int64_t i1 = 0, int64_t i2 = 0);
+
+  int64_t workspace_elems() const { return arena.peak; }
+  std::string dump_json() const;
+
+ private:
+  void emit_gemm(Op op, bool allow_split);
+};
+
+int64_t npair(int64_t n);
+
+}  // namespace ecw

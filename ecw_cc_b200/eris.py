@@ -1,0 +1,163 @@
+"""Device-resident integral container.
+
+Consumes the attribute surface of the reference `Eris.geris` (Eris.py:132-154:
+`fock, nocc, oooo, ooov, oovv, ovov, ovvv, vvvv`, numpy arrays of
+antisymmetrised <pq||rs>) and keeps the constant layouts the kernels read
+(include/ecw_b200.h, "integral container").  Construction of integrals from a
+molecule (PySCF ao2mo, Eris.py:47-128) is out of scope.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import lib, EcwError
+
+_LAYOUTS = ("oooo", "ooov", "oovv", "ovvv", "oovv_ph", "ovov_ph", "oooo_p", "oovv_p", "ovvv_p", "vvvv_p")
+SYNTH_KIND = dict(oooo=0, ooov=1, oovv=2, oovv_ph=3, ovov_ph=4, ovvv=5, oooo_p=6, oovv_p=7, ovvv_p=8, vvvv_p=9,
+                  fock=10, fsp=11, t1=12, l1=13, t2=14, l2=15)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise EcwError("no CUDA device: the ECW-CC residual path has no CPU implementation")
+    return torch
+
+
+class DeviceEris(object):
+    """Owns the C context, the bound integral layouts and the workspace."""
+
+    def __init__(self, nocc, nvir, device=None):
+        torch = _torch()
+        self.nocc = int(nocc)
+        self.nvir = int(nvir)
+        self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+        self._h = ctypes.c_void_p()
+        if lib.ecw_ctx_create(ctypes.byref(self._h), self.nocc, self.nvir) != 0:
+            raise EcwError("ecw_ctx_create failed")
+        self.buf = {}
+        self._ws = None
+        self._scal = torch.zeros(16, dtype=torch.float64, device=self.device)
+        self._bind("scal", self._scal)
+        self.fock = None          # host numpy (reference attribute `eris.fock`)
+        self.fock_dev = None
+        self.mo_occ = np.concatenate([np.ones(self.nocc), np.zeros(self.nvir)])
+        self.EHF = 0.0
+
+    # -- plumbing ------------------------------------------------------------
+    def __del__(self):
+        try:
+            if self._h:
+                lib.ecw_ctx_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            msg = lib.ecw_last_error(self._h)
+            raise EcwError("%s: %s" % (what, msg.decode() if msg else "error"))
+
+    def stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def _bind(self, name, tensor):
+        self.check(lib.ecw_bind(self._h, name.encode(), tensor.data_ptr()), "ecw_bind(%s)" % name)
+
+    def _alloc_layout(self, name):
+        torch = _torch()
+        n = lib.ecw_slot_elems(self._h, name.encode())
+        if n < 0:
+            raise EcwError("unknown layout %s" % name)
+        t = torch.empty(max(int(n), 1), dtype=torch.float64, device=self.device)
+        self.buf[name] = t
+        self._bind(name, t)
+        return t
+
+    def ensure_workspace(self, func, flags):
+        torch = _torch()
+        need = lib.ecw_workspace_bytes(self._h, func.encode(), flags)
+        if need < 0:
+            self.check(-1, "ecw_workspace_bytes(%s)" % func)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(max(int(need), 256), dtype=torch.uint8, device=self.device)
+            self.check(lib.ecw_set_workspace(self._h, self._ws.data_ptr(), self._ws.numel()), "ecw_set_workspace")
+
+    def set_fock(self, fock):
+        torch = _torch()
+        self.fock = np.ascontiguousarray(fock, dtype=np.float64)
+        self.fock_dev = torch.from_numpy(self.fock).to(self.device)
+
+    # -- constructors ----------------------------------------------------------
+    @classmethod
+    def from_geris(cls, eris, device=None):
+        """Upload a reference-style container (numpy blocks, Eris.py:132-150)."""
+        torch = _torch()
+        fock = np.asarray(eris.fock)
+        nocc = int(eris.nocc)
+        self = cls(nocc, fock.shape[0] - nocc, device)
+        self.set_fock(fock)
+        for name in ("oooo", "ooov", "oovv", "ovvv"):
+            t = torch.from_numpy(np.ascontiguousarray(getattr(eris, name), dtype=np.float64)).to(self.device)
+            self.buf[name] = t.reshape(-1)
+            self._bind(name, self.buf[name])
+        for name in ("oovv_ph", "ovov_ph", "oooo_p", "oovv_p", "ovvv_p", "vvvv_p"):
+            self._alloc_layout(name)
+        ovov = torch.from_numpy(np.ascontiguousarray(eris.ovov, dtype=np.float64)).to(self.device)
+        vvvv = torch.from_numpy(np.ascontiguousarray(eris.vvvv, dtype=np.float64)).to(self.device)
+        self.check(lib.ecw_eris_pack_from_dense(self._h, ovov.data_ptr(), vvvv.data_ptr(), self.stream()),
+                   "ecw_eris_pack_from_dense")
+        torch.cuda.current_stream(self.device).synchronize()
+        for attr in ("mo_occ", "EHF", "orbspin"):
+            if hasattr(eris, attr):
+                setattr(self, attr, getattr(eris, attr))
+        return self
+
+    @classmethod
+    def synthetic(cls, nocc, nvir, device=None, scale=0.01):
+        """Function-defined synthetic integrals generated in place on the device."""
+        torch = _torch()
+        self = cls(nocc, nvir, device)
+        for name in _LAYOUTS:
+            self._alloc_layout(name)
+        self.check(lib.ecw_eris_synthetic(self._h, float(scale), self.stream()), "ecw_eris_synthetic")
+        n = self.nocc + self.nvir
+        self.fock_dev = self.synth_tensor("fock", (n, n))
+        self.fock = self.fock_dev.cpu().numpy()
+        torch.cuda.current_stream(self.device).synchronize()
+        return self
+
+    def synth_tensor(self, kind, shape, scale=0.01):
+        """Synthetic fock / fsp / t1 / l1 / t2 / l2 on the device."""
+        torch = _torch()
+        out = torch.empty(shape, dtype=torch.float64, device=self.device)
+        rc = lib.ecw_synth_tensor(SYNTH_KIND[kind], out.data_ptr(), self.nocc, self.nvir, 0, int(shape[0]),
+                                  float(scale), self.stream())
+        if rc != 0:
+            raise EcwError("ecw_synth_tensor(%s) failed" % kind)
+        return out
+
+    # -- reference attribute surface (host views on demand) ----------------------
+    def _host(self, name, shape):
+        return self.buf[name][: int(np.prod(shape))].reshape(shape).cpu().numpy()
+
+    @property
+    def oovv(self):
+        o, v = self.nocc, self.nvir
+        return self._host("oovv", (o, o, v, v))
+
+    @property
+    def ooov(self):
+        o, v = self.nocc, self.nvir
+        return self._host("ooov", (o, o, o, v))
+
+    @property
+    def oooo(self):
+        o = self.nocc
+        return self._host("oooo", (o, o, o, o))
+
+    @property
+    def ovvv(self):
+        o, v = self.nocc, self.nvir
+        return self._host("ovvv", (o, v, v, v))

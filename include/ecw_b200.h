@@ -1,0 +1,105 @@
+/* ecw_b200.h — C ABI of the B200-native coupled-cluster residual path.
+ *
+ * Drop-in boundary for the hot path of MilaimKas/ECW_CC.  The reference has no
+ * FFI of its own (it is pure Python/numpy); the boundary is the method surface
+ * of `CCSD.GCC` / `CCS.Gccs` that the unchanged solver loops call
+ * (Solver_GS.py:683-705, Solver_GS.py:172-204, Solver_ES.py:258-368).  Each
+ * entry point below replaces one of those methods and cites it; the Python
+ * classes in ecw_cc_b200/CCSD.py and ecw_cc_b200/CCS.py bind them with ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to FP64 data in C (row-major) order
+ *     unless a parameter says "host";
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered,
+ *     nothing synchronises the device;
+ *   - return value 0 = ok, negative = error (message: ecw_last_error);
+ *   - the library never allocates device memory: the caller binds the constant
+ *     integral layouts and one workspace (sizes: ecw_slot_elems,
+ *     ecw_workspace_bytes);
+ *   - there is no CPU path: without a CUDA device every compute call fails.
+ */
+#ifndef ECW_B200_H
+#define ECW_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ecw_ctx ecw_ctx;
+
+/* mode flags of tupdate/lupdate: mirror `alpha is not None` / `equation=True`
+ * of GCC.tupdate (CCSD.py:248) and GCC.lupdate (CCSD.py:419). */
+#define ECW_HAS_ALPHA 1
+#define ECW_EQUATION 2
+
+/* ---- context ------------------------------------------------------------ */
+/* One context per (device, nocc, nvir); replaces `GCC.__init__` (CCSD.py:186-198)
+ * and `Gccs.__init__`. Touches no CUDA API. */
+int ecw_ctx_create(ecw_ctx** out, int nocc, int nvir);
+void ecw_ctx_destroy(ecw_ctx* ctx);
+const char* ecw_last_error(ecw_ctx* ctx);
+const char* ecw_version(void);
+
+/* ---- integral container (consumed type `Eris.geris`, Eris.py:132-154) ---- */
+/* Constant device layouts, by slot name:
+ *   "oooo" [o,o,o,o]  "ooov" [o,o,o,v]  "oovv" [o,o,v,v]  "ovvv" [o,v,v,v]
+ *   "oovv_ph" [(m,e),(n,f)] = oovv[m,n,e,f]     "ovov_ph" [(i,a),(n,f)] = ovov[n,a,i,f]
+ *   "oooo_p" [ij_p,kl_p]  "oovv_p" [ij_p,ab_p]  "ovvv_p" [m,a,ef_p]  "vvvv_p" [ab_p,cd_p]
+ * with the antisymmetric pair index p(x<y) = y(y-1)/2 + x.  Also bindable:
+ * "scal" (16 doubles of device scratch for scalars). */
+int64_t ecw_slot_elems(ecw_ctx* ctx, const char* slot);
+int ecw_bind(ecw_ctx* ctx, const char* slot, void* device_ptr);
+/* Fill the derived layouts (oovv_ph, ovov_ph, *_p) from dense canonical blocks
+ * already on the device; "oooo","ooov","oovv","ovvv" must be bound to the dense
+ * blocks themselves.  Replaces the block copies of Eris.py:132-150. */
+int ecw_eris_pack_from_dense(ecw_ctx* ctx, const double* ovov_dense, const double* vvvv_dense, void* stream);
+/* Fill every bound integral layout with the function-defined synthetic
+ * integrals (DESIGN.md "Synthetic inputs"); dense vvvv never exists. */
+int ecw_eris_synthetic(ecw_ctx* ctx, double scale, void* stream);
+/* One synthetic tensor (kinds: ecw SynthKind in kernels.h: 10 fock, 11 fsp,
+ * 12 t1, 13 l1, 14 t2, 15 l2, 0..9 integral layouts), rows [row0,row0+nrows). */
+int ecw_synth_tensor(int kind, double* out, int nocc, int nvir, int64_t row0, int64_t nrows, double scale,
+                     void* stream);
+
+/* ---- workspace ------------------------------------------------------------ */
+/* func: "tupdate","lupdate","gamma","energy", or a CCS entry name. */
+int64_t ecw_workspace_bytes(ecw_ctx* ctx, const char* func, int mode_flags);
+int ecw_set_workspace(ecw_ctx* ctx, void* device_ptr, int64_t bytes);
+
+/* ---- CCSD (CCSD.py) --------------------------------------------------------- */
+/* GCC.tupdate(t1,t2,fsp,alpha,equation) — CCSD.py:248-338.  fock = bare Fock (n x n). */
+int ecw_ccsd_tupdate(ecw_ctx* ctx, const double* t1, const double* t2, const double* fsp, const double* fock,
+                     int mode_flags, double alpha, double* t1new, double* t2new, void* stream);
+/* GCC.lupdate(t1,t2,l1,l2,fsp,alpha,equation) — CCSD.py:419-535 (incl. Linter :543-623). */
+int ecw_ccsd_lupdate(ecw_ctx* ctx, const double* t1, const double* t2, const double* l1, const double* l2,
+                     const double* fsp, const double* fock, int mode_flags, double alpha, double* l1new,
+                     double* l2new, void* stream);
+/* GCC.gamma(t1,t2,l1,l2) — CCSD.py:136-182, 204-208.  rdm1: n x n. */
+int ecw_ccsd_gamma(ecw_ctx* ctx, const double* t1, const double* t2, const double* l1, const double* l2,
+                   double* rdm1, void* stream);
+/* GCC.energy(t1,t2,fsp) — CCSD.py:224-242.  e_out: one device double. */
+int ecw_ccsd_energy(ecw_ctx* ctx, const double* t1, const double* t2, const double* fsp, double* e_out,
+                    void* stream);
+/* utilities.subdiff(eq,var,alpha) — utilities.py:26-73 (element-wise, any shape). */
+int ecw_subdiff(const double* eq, const double* var, double alpha, double* out, int64_t n, void* stream);
+
+/* ---- introspection / test hooks ---------------------------------------------- */
+/* JSON dump of the op list a call would launch (host only, no CUDA). */
+int64_t ecw_plan_dump(ecw_ctx* ctx, const char* func, int mode_flags, char* buf, int64_t buflen);
+/* executed GEMM flops (sum of 2MNK) and launches of a plan */
+double ecw_plan_flops(ecw_ctx* ctx, const char* func, int mode_flags);
+int64_t ecw_plan_launches(ecw_ctx* ctx, const char* func, int mode_flags);
+/* Raw FP64 tensor-core GEMM: C = alpha op(A) op(B) + beta C (row-major C);
+ * ta/tb: 0 = A is [M,K] / B is [K,N] row-major, 1 = transposed storage.
+ * cfg < 0 picks the tile configuration automatically. */
+int ecw_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+              const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int cfg, void* stream);
+/* per-op device timing of the last executed plan (ms), written as JSON */
+int ecw_profile_enable(ecw_ctx* ctx, int on);
+int64_t ecw_profile_dump(ecw_ctx* ctx, char* buf, int64_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECW_B200_H */

@@ -1,0 +1,39 @@
+"""Shared test helpers (CPU side)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODES = [("upd", None, False), ("eq", None, True), ("l1upd", 1e-3, False), ("l1eq", 1e-3, True)]
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def plan_json(lib, o, v, func, flags):
+    h = ctypes.c_void_p()
+    assert lib.ecw_ctx_create(ctypes.byref(h), o, v) == 0
+    try:
+        n = 1 << 24
+        buf = ctypes.create_string_buffer(n)
+        r = lib.ecw_plan_dump(h, func.encode(), flags, buf, n)
+        assert r > 0, lib.ecw_last_error(h)
+        return json.loads(buf.value.decode())
+    finally:
+        lib.ecw_ctx_destroy(h)
+
+
+def eris_slots(er):
+    """numpy versions of the constant device layouts (oracle/refactored_np.DeviceErisSpec)."""
+    from oracle import refactored_np as R
+    E = R.DeviceErisSpec(er)
+    return dict(oooo=E.oooo.copy(), ooov=E.ooov.copy(), oovv=E.oovv.copy(), oovv_ph=E.oovv_ph,
+                ovov_ph=E.ovov_ph, ovvv=E.ovvv.copy(), oooo_p=E.oooo_p, oovv_p=E.oovv_p,
+                ovvv_p=E.ovvv_p, vvvv_p=E.vvvv_p)
+
+
+def flags_of(alpha, equation):
+    return (1 if alpha is not None else 0) | (2 if equation else 0)

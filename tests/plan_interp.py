@@ -1,0 +1,194 @@
+"""numpy interpreter for execution plans — TEST INFRASTRUCTURE ONLY.
+
+Replays the op list that `ecw_plan_dump` emits (the same list `exec.cu`
+launches on the GPU) with numpy on host arrays, so the *lowering* — index
+strings, layouts, batch/split-K choices, workspace offsets and lifetimes — can
+be checked against the oracle on a CPU-only box.  It is not a fallback: the
+product has no path that reaches it.
+"""
+import json
+
+import numpy as np
+from numpy.lib.stride_tricks import as_strided
+
+
+def npair(n):
+    return n * (n - 1) // 2
+
+
+def pair_decode(n):
+    hi, lo = np.tril_indices(n, -1)
+    return lo, hi
+
+
+class Interp(object):
+    def __init__(self, plan_json, slots, alpha=0.0):
+        self.plan = json.loads(plan_json) if isinstance(plan_json, str) else plan_json
+        self.slots = dict(slots)
+        self.alpha = alpha
+        ws = int(self.plan["workspace_elems"])
+        # poison the workspace so reads of never-written scratch show up as NaN
+        self.slots["ws"] = np.full(max(ws, 1), np.nan)
+        if "scal" not in self.slots:
+            self.slots["scal"] = np.zeros(16)
+
+    def view(self, t):
+        if t is None:
+            return None
+        base = self.slots[t["slot"]].reshape(-1)
+        dim = tuple(t["dim"])
+        strides = tuple(8 * s for s in t["str"])
+        off = t["off"]
+        # bounds check
+        ext = off + sum((d - 1) * s for d, s in zip(t["dim"], t["str"]) if d > 0)
+        assert 0 <= off and ext < base.size or np.prod(dim) == 0, (t, base.size)
+        return as_strided(base[off:], shape=dim, strides=strides)
+
+    def run(self):
+        for op in self.plan["ops"]:
+            getattr(self, "op_" + op["kind"])(op)
+        return self
+
+    # ---------------------------------------------------------------- ops
+    def _mat(self, t_off_slot, off, rows, cols, rs, cs):
+        base = self.slots[t_off_slot].reshape(-1)
+        return as_strided(base[off:], shape=(rows, cols), strides=(8 * rs, 8 * cs))
+
+    def op_gemm(self, op):
+        M, N, K = op["M"], op["N"], op["K"]
+        S = op["splitk"]
+        kc = op["kchunk"] if S > 1 else K
+        for zb in range(op["batch"]):
+            r, s = divmod(zb, S)
+            k0 = s * kc
+            kn = min(kc, K - k0)
+            assert kn > 0
+            a, b, c = op["a"], op["b"], op["c"]
+            if op["ta"] == 0:
+                A = self._mat(a["slot"], a["off"] + r * op["sA"] + k0, M, kn, op["lda"], 1)
+            else:
+                A = self._mat(a["slot"], a["off"] + r * op["sA"] + k0 * op["lda"], M, kn, 1, op["lda"])
+            if op["tb"] == 0:
+                B = self._mat(b["slot"], b["off"] + r * op["sB"] + k0 * op["ldb"], kn, N, op["ldb"], 1)
+            else:
+                B = self._mat(b["slot"], b["off"] + r * op["sB"] + k0, kn, N, 1, op["ldb"])
+            C = self._mat(c["slot"], c["off"] + zb * op["sC"], M, N, op["ldc"], 1)
+            assert not np.isnan(A).any() and not np.isnan(B).any(), op["note"]
+            res = op["alpha"] * (A @ B)
+            if op["beta"] != 0.0:
+                res = res + op["beta"] * C
+            C[...] = res
+
+    def op_reduce(self, op):
+        M, N = op["M"], op["N"]
+        a, c = op["a"], op["c"]
+        P = self._mat(a["slot"], a["off"], op["i0"], M * N, M * N, 1).reshape(op["i0"], M, N)
+        C = self._mat(c["slot"], c["off"], M, N, op["i1"], op["i2"])
+        res = op["alpha"] * P.sum(axis=0)
+        if op["beta"] != 0.0:
+            res = res + op["beta"] * C
+        C[...] = res
+
+    def op_permute(self, op):
+        A, C = self.view(op["a"]), self.view(op["c"])
+        assert not np.isnan(A).any(), op["note"]
+        res = op["alpha"] * A
+        if op["beta"] != 0.0:
+            res = res + op["beta"] * C
+        C[...] = res
+
+    def op_fill(self, op):
+        self.view(op["c"])[...] = op["alpha"]
+
+    def op_tau(self, op):
+        t2, t1, out = self.view(op["a"]), self.view(op["b"]), self.view(op["c"])
+        x = np.einsum('ia,jb->ijab', t1, t1)
+        out[...] = t2 + op["alpha"] * (x - x.transpose(0, 1, 3, 2))
+
+    def op_pack(self, op):
+        A, C = self.view(op["a"]), self.view(op["c"])
+        fl = op["i0"]
+        x = A
+        if fl & 4:
+            x = x - x.transpose(0, 1, 3, 2)
+        if fl & 2:
+            lo, hi = pair_decode(A.shape[2])
+            x = x[:, :, lo, hi]
+        else:
+            x = x.reshape(A.shape[0], A.shape[1], -1)
+        if fl & 1:
+            lo, hi = pair_decode(A.shape[0])
+            x = x[lo, hi]
+        else:
+            x = x.reshape(A.shape[0] * A.shape[1], -1)
+        res = op["alpha"] * x
+        if op["beta"] != 0.0:
+            res = res + op["beta"] * C
+        C[...] = res
+
+    def op_unpack(self, op):
+        A, C = self.view(op["a"]), self.view(op["c"])
+        fl = op["i0"]
+        d0, d1, d2, d3 = C.shape
+        x = A
+        if fl & 2:
+            lo, hi = pair_decode(d2)
+            y = np.zeros((x.shape[0], d2, d3))
+            y[:, lo, hi] = x
+            y[:, hi, lo] = -x
+        else:
+            y = x.reshape(x.shape[0], d2, d3)
+        if fl & 1:
+            lo, hi = pair_decode(d0)
+            w = np.zeros((d0, d1, d2, d3))
+            w[lo, hi] = y
+            w[hi, lo] = -y
+        else:
+            w = y.reshape(d0, d1, d2, d3)
+        res = op["alpha"] * w
+        if op["beta"] != 0.0:
+            res = res + op["beta"] * C
+        C[...] = res
+
+    def op_finish(self, op):
+        r, amp, fock, out = self.view(op["a"]), self.view(op["b"]), self.view(op["d"]), self.view(op["c"])
+        o, rank, has_alpha, equation = op["i0"], op["i1"], op["i2"], op["i3"]
+        alpha = self.alpha
+        e = np.diagonal(fock)
+        d1 = e[:o, None] - e[None, o:]
+        d = d1 if rank == 2 else d1[:, None, :, None] + d1[None, :, None, :]
+        if has_alpha:
+            if rank == 4:
+                shr = np.where(r < -alpha, r + alpha, np.where(r > alpha, r - alpha, 0.0))
+                w = np.where(amp > 0.0, r + alpha, shr)
+            else:
+                w = r
+            res = w if equation else (w + amp * d) / d
+        else:
+            res = r if equation else r / d
+        out[...] = res
+
+    def op_dot(self, op):
+        A, B = self.view(op["a"]), self.view(op["b"])
+        k = op["i0"]
+        s = self.slots["scal"]
+        s[k] = (op["beta"] * s[k] if op["beta"] != 0.0 else 0.0) + op["alpha"] * float(np.sum(A * B))
+
+    def op_scale_dev(self, op):
+        C = self.view(op["c"])
+        C *= op["d0"] + op["d1"] * self.slots["scal"][op["i0"]]
+
+    def op_diag_add(self, op):
+        C, fock = self.view(op["c"]), self.view(op["d"])
+        m = C.shape[0]
+        idx = np.arange(m)
+        C[idx, idx] += op["alpha"] * np.diagonal(fock)[op["i0"]:op["i0"] + m]
+
+    def op_rdm1(self, op):
+        doo, dvoT, l1, dvv, out = (self.view(op[k]) for k in ("a", "b", "d", "e", "c"))
+        o = doo.shape[0]
+        out[:o, :o] = 0.5 * (doo + doo.T)
+        out[:o, o:] = 0.5 * (l1 + dvoT)
+        out[o:, :o] = out[:o, o:].T
+        out[o:, o:] = 0.5 * (dvv + dvv.T)
+        out[np.arange(o), np.arange(o)] += 1.0

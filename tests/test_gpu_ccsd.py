@@ -1,0 +1,225 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI
+(ecw_cc_b200 -> libecw_b200.so) and is compared with the CPU oracle on the same
+seeded inputs.  Tolerance: 1e-10 absolute in FP64 (BASELINE.json north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, MODES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def ecw(built_lib):
+    import ecw_cc_b200
+    return ecw_cc_b200
+
+
+def _dev(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_dgemm_all_layouts(ecw, cfg, ta, tb):
+    import torch
+    rng = np.random.default_rng(10 * ta + tb + 100)
+    for (M, N, K) in [(1, 1, 1), (7, 5, 3), (33, 17, 129), (130, 131, 67), (256, 128, 64), (45, 300, 1000)]:
+        A = rng.standard_normal((K, M) if ta else (M, K))
+        B = rng.standard_normal((N, K) if tb else (K, N))
+        C0 = rng.standard_normal((M, N))
+        ref = 0.7 * ((A.T if ta else A) @ (B.T if tb else B)) - 0.3 * C0
+        dA, dB, dC = _dev(A), _dev(B), _dev(C0)
+        rc = ecw.lib.ecw_dgemm(ta, tb, M, N, K, 0.7, dA.data_ptr(), A.shape[1], dB.data_ptr(), B.shape[1],
+                               -0.3, dC.data_ptr(), N, cfg, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        err = np.abs(dC.cpu().numpy() - ref).max()
+        assert err < 1e-11 * max(1.0, K ** 0.5), (M, N, K, err)
+
+
+def test_dgemm_strided_views(ecw):
+    """Leading dimensions larger than the extent and odd (8-byte path) alignments."""
+    import torch
+    rng = np.random.default_rng(5)
+    M, N, K = 50, 37, 91
+    Abig, Bbig, Cbig = rng.standard_normal((M, K + 5)), rng.standard_normal((K, N + 3)), rng.standard_normal((M, N + 7))
+    dA, dB, dC = _dev(Abig), _dev(Bbig), _dev(Cbig)
+    ref = Cbig.copy()
+    ref[:, 1:N + 1] = Abig[:, 1:K + 1] @ Bbig[:, 2:N + 2]
+    rc = ecw.lib.ecw_dgemm(0, 0, M, N, K, 1.0, dA.data_ptr() + 8, K + 5, dB.data_ptr() + 16, N + 3, 0.0,
+                           dC.data_ptr() + 8, N + 7, -1, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert np.abs(dC.cpu().numpy() - ref).max() < 1e-11
+
+
+def test_synthetic_tensors_bit_exact(ecw):
+    """Device generators == oracle/synth.py, bit for bit."""
+    from oracle import synth
+    from oracle import refactored_np as R
+    o, v = 5, 9
+    de = ecw.DeviceEris.synthetic(o, v)
+    er = synth.SynthEris(o, v)
+    E = R.DeviceErisSpec(er)
+    host = dict(oooo=E.oooo, ooov=E.ooov, oovv=E.oovv, ovvv=E.ovvv, oovv_ph=E.oovv_ph, ovov_ph=E.ovov_ph,
+                oooo_p=E.oooo_p, oovv_p=E.oovv_p, ovvv_p=E.ovvv_p, vvvv_p=E.vvvv_p)
+    for name, ref in host.items():
+        got = de.buf[name].cpu().numpy()[: ref.size].reshape(ref.shape)
+        assert np.array_equal(got, ref), name
+    assert np.array_equal(de.fock, synth.fock(o, v))
+    n = o + v
+    t1, t2, l1, l2 = synth.amplitudes(o, v)
+    assert np.array_equal(de.synth_tensor("fsp", (n, n)).cpu().numpy(), synth.fsp(o, v))
+    assert np.array_equal(de.synth_tensor("t1", (o, v)).cpu().numpy(), t1)
+    assert np.array_equal(de.synth_tensor("l1", (o, v)).cpu().numpy(), l1)
+    assert np.array_equal(de.synth_tensor("t2", (o, o, v, v)).cpu().numpy(), t2)
+    assert np.array_equal(de.synth_tensor("l2", (o, o, v, v)).cpu().numpy(), l2)
+
+
+@pytest.mark.parametrize("ov", [(2, 3), (4, 6), (5, 7), (6, 11), (8, 20), (10, 33)])
+def test_ccsd_matches_oracle(ecw, ov):
+    from oracle import synth
+    from oracle.ccsd_np import OracleGCC
+    o, v = ov
+    er = synth.SynthEris(o, v)
+    t1, t2, l1, l2 = synth.amplitudes(o, v)
+    fsp = synth.fsp(o, v)
+    orc = OracleGCC(er)
+    cc = ecw.GCC(er)
+    assert (cc.nocc, cc.nvir) == (o, v)
+    for tag, alpha, eq in MODES:
+        a, b = cc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq)
+        c, d = orc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq)
+        assert np.abs(a - c).max() < TOL and np.abs(b - d).max() < TOL, ("tupdate", tag)
+        a, b = cc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq)
+        c, d = orc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq)
+        assert np.abs(a - c).max() < TOL and np.abs(b - d).max() < TOL, ("lupdate", tag)
+    # fsp=None -> bare Fock (CCSD.py:266-267, 440-441)
+    a, b = cc.tupdate(t1, t2)
+    c, d = orc.tupdate(t1, t2)
+    assert np.abs(a - c).max() < TOL and np.abs(b - d).max() < TOL
+    assert np.abs(cc.gamma(t1, t2, l1, l2) - orc.gamma(t1, t2, l1, l2)).max() < TOL
+    assert abs(cc.energy(t1, t2, fsp) - orc.energy(t1, t2, fsp)) < TOL
+    # inputs are never mutated
+    t1c, t2c, l1c, l2c = synth.amplitudes(o, v)
+    assert np.array_equal(t1, t1c) and np.array_equal(t2, t2c) and np.array_equal(l2, l2c)
+
+
+@pytest.mark.parametrize("name", ["ccsd_o4v6.npz", "ccsd_o5v8.npz"])
+def test_ccsd_matches_golden(ecw, name):
+    """Against outputs of the reference itself (tests/golden, made by oracle/make_golden.py)."""
+    from oracle import synth
+    g = load_golden(name)
+    o, v = int(g["nocc"]), int(g["nvir"])
+    er = synth.SynthEris(o, v)
+    t1, t2, l1, l2 = synth.amplitudes(o, v)
+    cc = ecw.GCC(er)
+    for fname, fsp in (("sym", synth.fsp(o, v)), ("ns", g["fsp_ns"])):
+        for tag, alpha, eq in MODES:
+            a, b = cc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq)
+            assert np.abs(a - g["T1_%s_%s" % (fname, tag)]).max() < TOL
+            assert np.abs(b - g["T2_%s_%s" % (fname, tag)]).max() < TOL
+            a, b = cc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq)
+            assert np.abs(a - g["L1_%s_%s" % (fname, tag)]).max() < TOL
+            assert np.abs(b - g["L2_%s_%s" % (fname, tag)]).max() < TOL
+        assert abs(cc.energy(t1, t2, fsp) - float(g["E_%s" % fname])) < TOL
+    assert np.abs(cc.gamma(t1, t2, l1, l2) - g["gamma"]).max() < TOL
+    a, b = cc.tupdate(t1, t2, equation=True)
+    assert np.abs(a - g["rawT1"]).max() < TOL and np.abs(b - g["rawT2"]).max() < TOL
+    a, b = cc.lupdate(t1, t2, l1, l2, equation=True)
+    assert np.abs(a - g["rawL1"]).max() < TOL and np.abs(b - g["rawL2"]).max() < TOL
+
+
+def test_device_resident_and_synthetic_eris(ecw):
+    """torch tensors in -> torch tensors out; synthetic device eris == uploaded eris."""
+    import torch
+    from oracle import synth
+    from oracle.ccsd_np import OracleGCC
+    o, v = 6, 14
+    de = ecw.DeviceEris.synthetic(o, v)
+    cc = ecw.GCC(de)
+    n = o + v
+    t1, t2 = de.synth_tensor("t1", (o, v)), de.synth_tensor("t2", (o, o, v, v))
+    l1, l2 = de.synth_tensor("l1", (o, v)), de.synth_tensor("l2", (o, o, v, v))
+    fsp = de.synth_tensor("fsp", (n, n))
+    a, b = cc.tupdate(t1, t2, fsp=fsp, alpha=1e-3)
+    c, d = cc.lupdate(t1, t2, l1, l2, fsp=fsp)
+    assert isinstance(a, torch.Tensor) and a.is_cuda and isinstance(d, torch.Tensor)
+    orc = OracleGCC(synth.SynthEris(o, v))
+    ht1, ht2, hl1, hl2 = synth.amplitudes(o, v)
+    ra, rb = orc.tupdate(ht1, ht2, fsp=synth.fsp(o, v), alpha=1e-3)
+    rc, rd = orc.lupdate(ht1, ht2, hl1, hl2, fsp=synth.fsp(o, v))
+    assert np.abs(a.cpu().numpy() - ra).max() < TOL and np.abs(b.cpu().numpy() - rb).max() < TOL
+    assert np.abs(c.cpu().numpy() - rc).max() < TOL and np.abs(d.cpu().numpy() - rd).max() < TOL
+    # reference attribute surface used by Solver_GS.py:554-559
+    assert np.array_equal(cc.eris.oovv, synth.SynthEris(o, v).oovv)
+
+
+def test_subdiff_kernel(ecw):
+    from oracle.ccsd_np import soft_threshold
+    rng = np.random.default_rng(3)
+    e, v = rng.standard_normal((9, 4, 5)), rng.standard_normal((9, 4, 5))
+    v[0] = 0.0
+    e[1, 0] = 0.0
+    for al in (0.0, 1e-3, 0.5):
+        assert np.array_equal(ecw.subdiff(e, v, al), soft_threshold(e, v, al))
+    with pytest.raises(ValueError):
+        ecw.subdiff(np.zeros(3), np.zeros(4), 0.1)
+
+
+def test_solver_iterations_track_oracle(ecw):
+    """Body of Solver_CCSD.SCF (Solver_GS.py:683-705) driven by the GPU object vs the oracle:
+    gamma -> energy -> tupdate -> lupdate with warm-started amplitudes, with and without L1."""
+    from oracle import synth
+    from oracle.ccsd_np import OracleGCC
+    o, v = 5, 9
+    er = synth.SynthEris(o, v)
+    fsp = synth.fsp(o, v)
+    e = np.diagonal(er.fock)
+    d1 = e[:o, None] - e[None, o:]
+    d2 = d1[:, None, :, None] + d1[None, :, None, :]
+    for alpha in (None, 5e-4):
+        gs = [ecw.GCC(er), OracleGCC(er)]
+        st = [[np.zeros((o, v)), np.zeros((o, v)), er.oovv / d2, er.oovv / d2] for _ in gs]   # Solver_GS.py:554-559
+        for it in range(4):
+            outs = []
+            for cc, s in zip(gs, st):
+                ts, ls, td, ld = s
+                g = cc.gamma(ts, td, ls, ld)
+                ep = cc.energy(ts, td, fsp)
+                ts, td = cc.tupdate(ts, td, fsp=fsp, alpha=alpha)
+                ls, ld = cc.lupdate(ts, td, ls, ld, fsp=fsp, alpha=alpha)
+                s[:] = [ts, ls, td, ld]
+                outs.append((g, ep, ts, td, ls, ld))
+            for x, y in zip(outs[0], outs[1]):
+                assert np.abs(np.asarray(x) - np.asarray(y)).max() < TOL, (alpha, it)
+
+
+def test_size_independent_properties(ecw):
+    """At a size the oracle would need minutes for: antisymmetry of the doubles residuals,
+    tupdate(alpha=0) == tupdate(alpha=None) (CCSD.py:732-739), tr(gamma)=nocc, gamma symmetric,
+    and the soft-threshold identity  subdiff(eq-mode output) applied by hand == L1-equation mode."""
+    import torch
+    o, v = 12, 64
+    de = ecw.DeviceEris.synthetic(o, v)
+    cc = ecw.GCC(de)
+    n = o + v
+    t1, t2 = de.synth_tensor("t1", (o, v)), de.synth_tensor("t2", (o, o, v, v))
+    l1, l2 = de.synth_tensor("l1", (o, v)), de.synth_tensor("l2", (o, o, v, v))
+    fsp = de.synth_tensor("fsp", (n, n))
+    r1, r2 = cc.tupdate(t1, t2, fsp=fsp, equation=True)
+    assert float((r2 + r2.permute(1, 0, 2, 3)).abs().max()) < 1e-12
+    assert float((r2 + r2.permute(0, 1, 3, 2)).abs().max()) < 1e-12
+    q1, q2 = cc.lupdate(t1, t2, l1, l2, fsp=fsp, equation=True)
+    assert float((q2 + q2.permute(1, 0, 2, 3)).abs().max()) < 1e-12
+    assert float((q2 + q2.permute(0, 1, 3, 2)).abs().max()) < 1e-12
+    a0 = cc.tupdate(t1, t2, fsp=fsp, alpha=0.0)
+    an = cc.tupdate(t1, t2, fsp=fsp, alpha=None)
+    assert float((a0[1] - an[1]).abs().max()) < 1e-12 and float((a0[0] - an[0]).abs().max()) < 1e-12
+    w1, w2 = cc.tupdate(t1, t2, fsp=fsp, alpha=1e-3, equation=True)
+    assert torch.equal(w2, ecw.subdiff(r2, t2, 1e-3)) and torch.equal(w1, r1)
+    g = cc.gamma(t1, t2, l1, l2)
+    assert abs(float(torch.trace(g)) - o) < 1e-10 and float((g - g.T).abs().max()) < 1e-14
