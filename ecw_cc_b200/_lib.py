@@ -9,6 +9,7 @@ _SRC = ["gemm.cu", "ewise.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp
 
 ECW_HAS_ALPHA = 1
 ECW_EQUATION = 2
+ECW_ANTISYM = 4
 
 
 class EcwError(RuntimeError):
@@ -65,6 +66,7 @@ class _Lib(object):
             "ecw_ccsd_gamma": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
             "ecw_ccsd_energy": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p]),
             "ecw_subdiff": (c_i, [c_p, c_p, c_d, c_p, c_l, c_p]),
+            "ecw_antisym_defect": (c_i, [c_p, c_i, c_i, c_p, c_p]),
             "ecw_plan_dump": (c_l, [c_p, c_s, c_i, c_p, c_l]),
             "ecw_plan_flops": (c_d, [c_p, c_s, c_i]),
             "ecw_plan_launches": (c_l, [c_p, c_s, c_i]),

@@ -64,8 +64,9 @@ Plan& get_plan(ecw_ctx* c, const std::string& func, int flags) {
   if (it != c->plans.end()) return *it->second;
   std::unique_ptr<Plan> P(new Plan());
   const int ha = (flags & ECW_HAS_ALPHA) ? 1 : 0, eq = (flags & ECW_EQUATION) ? 1 : 0;
-  if (func == "tupdate") build_ccsd_tupdate(*P, c->z, ha, eq);
-  else if (func == "lupdate") build_ccsd_lupdate(*P, c->z, ha, eq);
+  const bool as = (flags & ECW_ANTISYM) != 0;
+  if (func == "tupdate") (as ? build_ccsd_tupdate : build_ccsd_tupdate_general)(*P, c->z, ha, eq);
+  else if (func == "lupdate") (as ? build_ccsd_lupdate : build_ccsd_lupdate_general)(*P, c->z, ha, eq);
   else if (func == "gamma") build_ccsd_gamma(*P, c->z);
   else if (func == "energy") build_ccsd_energy(*P, c->z);
   else if (!build_ccs_plan(*P, c->z, func, flags)) throw Fail("unknown function '" + func + "'");
@@ -129,7 +130,7 @@ void run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
       }
       case OP_TAU:
         ck(launch_tau(resolve(c, op.a), resolve(c, op.b), resolve(c, op.c), (int)op.b.dim[0], (int)op.b.dim[1],
-                      op.alpha, st), "tau");
+                      op.alpha, op.beta, st), "tau");
         break;
       case OP_PACK: {
         PackArgs a{};
@@ -353,6 +354,13 @@ int ecw_ccsd_energy(ecw_ctx* c, const double* t1, const double* t2, const double
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     run_plan(c, get_plan(c, "energy", 0), 0.0, st);
     ck(cudaMemcpyAsync(e_out, c->ptr[S_SCAL], sizeof(double), cudaMemcpyDeviceToDevice, st), "copy energy");
+  });
+}
+
+int ecw_antisym_defect(const double* x, int nocc, int nvir, double* out, void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    ck(launch_antisym_defect(x, nocc, nvir, out, static_cast<cudaStream_t>(stream)), "antisym_defect");
   });
 }
 

@@ -12,6 +12,9 @@ struct Sizes {
 // (CCSD.py:248, :419): has_alpha <=> `alpha is not None`, equation <=> `equation=True`.
 void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation);
 void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation);
+// general variants: amplitudes not assumed antisymmetric (only the integrals are)
+void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equation);
+void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equation);
 void build_ccsd_gamma(Plan& P, const Sizes& z);
 void build_ccsd_energy(Plan& P, const Sizes& z);
 

@@ -114,16 +114,41 @@ reduce_kernel(const double* __restrict__ part, int64_t nz, int64_t M, int64_t N,
 
 __global__ void __launch_bounds__(EW_THREADS)
 tau_kernel(const double* __restrict__ t2, const double* __restrict__ t1, double* __restrict__ out, int o, int v,
-           double coef) {
+           double c1, double c2) {
   const int64_t vv = (int64_t)v * v, total = (int64_t)o * o * vv;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t ij = idx / vv, ab = idx - ij * vv;
     int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
     int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
-    double x = t1[i * v + a] * t1[j * v + b] - t1[i * v + b] * t1[j * v + a];
-    out[idx] = t2[idx] + coef * x;
+    double x = c1 * (t1[i * v + a] * t1[j * v + b]) - c2 * (t1[i * v + b] * t1[j * v + a]);
+    out[idx] = t2[idx] + x;
   }
+}
+
+// max asymmetry of a doubles amplitude; non-negative doubles order like their bit patterns
+__global__ void __launch_bounds__(EW_THREADS)
+defect_kernel(const double* __restrict__ x, int o, int v, double* out) {
+  __shared__ double sh[EW_THREADS];
+  const int64_t vv = (int64_t)v * v, total = (int64_t)o * o * vv;
+  double m = 0.0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t ij = idx / vv, ab = idx - ij * vv;
+    int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
+    int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
+    double val = x[idx];
+    m = fmax(m, fabs(val + x[((int64_t)j * o + i) * vv + ab]));
+    m = fmax(m, fabs(val + x[ij * vv + (int64_t)b * v + a]));
+  }
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  for (int w = EW_THREADS / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(sh[0]));
 }
 
 // packed pair index k = hi(hi-1)/2 + lo  (lo < hi)
@@ -148,6 +173,12 @@ __global__ void __launch_bounds__(EW_THREADS) pack_kernel(PackArgs p, int64_t ro
     const double* s = p.src + i0 * p.s0 + i1 * p.s1;
     double val = s[i2 * p.s2 + i3 * p.s3];
     if (p.flags & 4) val -= s[i3 * p.s2 + i2 * p.s3];
+    if (p.flags & 8) {
+      const double* s2 = p.src + i1 * p.s0 + i0 * p.s1;
+      double w = s2[i2 * p.s2 + i3 * p.s3];
+      if (p.flags & 4) w -= s2[i3 * p.s2 + i2 * p.s3];
+      val -= w;
+    }
     double* d = p.dst + r * p.ld + c;
     double out = p.alpha * val;
     if (p.beta != 0.0) out += p.beta * *d;
@@ -363,10 +394,20 @@ cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double coef, cudaStream_t st) {
+cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double c1, double c2,
+                       cudaStream_t st) {
   int64_t total = (int64_t)o * o * v * v;
   if (total <= 0) return cudaSuccess;
-  tau_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(t2, t1, out, o, v, coef);
+  tau_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_antisym_defect(const double* x, int o, int v, double* out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  int64_t total = (int64_t)o * o * v * v;
+  if (total <= 0) return cudaSuccess;
+  defect_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(x, o, v, out);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,6 @@ namespace ecw {
 
 namespace {
 
-constexpr int BK = 16;
 constexpr int PAD = 4;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -42,7 +41,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // Load a tile whose contiguous direction is the K direction: smem[r][k], r < ROWS.
-template <int ROWS, int THREADS>
+template <int ROWS, int THREADS, int BK>
 __device__ __forceinline__ void load_kmajor(double* sm, const double* __restrict__ g, int64_t ld,
                                             int64_t row0, int64_t nrows, int64_t k0, int64_t kend,
                                             int vec, int tid) {
@@ -72,7 +71,7 @@ __device__ __forceinline__ void load_kmajor(double* sm, const double* __restrict
 }
 
 // Load a tile whose contiguous direction is the M/N direction: smem[k][c], c < COLS.
-template <int COLS, int THREADS>
+template <int COLS, int THREADS, int BK>
 __device__ __forceinline__ void load_mnmajor(double* sm, const double* __restrict__ g, int64_t ld,
                                              int64_t col0, int64_t ncols, int64_t k0, int64_t kend,
                                              int vec, int tid) {
@@ -102,19 +101,19 @@ __device__ __forceinline__ void load_mnmajor(double* sm, const double* __restric
   }
 }
 
-template <int BM, int BN, int TA, int TB>
+template <int BM, int BN, int BK, int TA, int TB>
 struct SmemLayout {
   static constexpr int A_ELEMS = TA ? BK * (BM + PAD) : BM * (BK + PAD);
   static constexpr int B_ELEMS = TB ? BN * (BK + PAD) : BK * (BN + PAD);
   static constexpr int STAGE = A_ELEMS + B_ELEMS;
 };
 
-template <int BM, int BN, int WM, int WN, int TA, int TB, int STAGES>
+template <int BM, int BN, int WM, int WN, int BK, int TA, int TB, int STAGES, int ILV>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1)
 dgemm_kernel(GemmArgs p) {
   constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
   constexpr int MI = WM / 8, NI = WN / 8;
-  using L = SmemLayout<BM, BN, TA, TB>;
+  using L = SmemLayout<BM, BN, BK, TA, TB>;
   extern __shared__ __align__(16) double smem[];
 
   const int tid = threadIdx.x;
@@ -154,15 +153,16 @@ dgemm_kernel(GemmArgs p) {
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int64_t ktiles = (kend - kbeg + BK - 1) / BK;
+  static_assert(BK % 4 == 0, "BK");
 
   auto load_stage = [&](int stage, int64_t kt) {
     double* sa = smem + stage * L::STAGE;
     double* sb = sa + L::A_ELEMS;
     const int64_t k0 = kbeg + kt * BK;
-    if (TA == 0) load_kmajor<BM, THREADS>(sa, A, p.lda, m0, p.M, k0, kend, p.vecA, tid);
-    else load_mnmajor<BM, THREADS>(sa, A, p.lda, m0, p.M, k0, kend, p.vecA, tid);
-    if (TB == 0) load_mnmajor<BN, THREADS>(sb, B, p.ldb, n0, p.N, k0, kend, p.vecB, tid);
-    else load_kmajor<BN, THREADS>(sb, B, p.ldb, n0, p.N, k0, kend, p.vecB, tid);
+    if (TA == 0) load_kmajor<BM, THREADS, BK>(sa, A, p.lda, m0, p.M, k0, kend, p.vecA, tid);
+    else load_mnmajor<BM, THREADS, BK>(sa, A, p.lda, m0, p.M, k0, kend, p.vecA, tid);
+    if (TB == 0) load_mnmajor<BN, THREADS, BK>(sb, B, p.ldb, n0, p.N, k0, kend, p.vecB, tid);
+    else load_kmajor<BN, THREADS, BK>(sb, B, p.ldb, n0, p.N, k0, kend, p.vecB, tid);
   };
 
 #pragma unroll
@@ -174,7 +174,7 @@ dgemm_kernel(GemmArgs p) {
   for (int64_t kt = 0; kt < ktiles; ++kt) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
+    if (!ILV) {
       int64_t nk = kt + STAGES - 1;
       if (nk < ktiles) load_stage((int)(nk % STAGES), nk);
       cp_async_commit();
@@ -199,6 +199,13 @@ dgemm_kernel(GemmArgs p) {
       for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      if (ILV && k4 == 0) {
+        // issue the next stage's copies in the shadow of the DMMAs just queued: the slot being
+        // refilled was last read in iteration kt-1, i.e. before the barrier above
+        int64_t nk = kt + STAGES - 1;
+        if (nk < ktiles) load_stage((int)(nk % STAGES), nk);
+        cp_async_commit();
+      }
     }
   }
   cp_async_wait<0>();
@@ -235,15 +242,15 @@ dgemm_kernel(GemmArgs p) {
   }
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES>
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, int ILV>
 cudaError_t launch_cfg(const GemmArgs& p, cudaStream_t st) {
   constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
   int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   dim3 grid((unsigned)tiles, (unsigned)p.batch, 1);
 #define ECW_LAUNCH(TA_, TB_)                                                                        \
   {                                                                                                 \
-    auto kern = dgemm_kernel<BM, BN, WM, WN, TA_, TB_, STAGES>;                                      \
-    size_t smem = sizeof(double) * STAGES * SmemLayout<BM, BN, TA_, TB_>::STAGE;                     \
+    auto kern = dgemm_kernel<BM, BN, WM, WN, BK, TA_, TB_, STAGES, ILV>;                                      \
+    size_t smem = sizeof(double) * STAGES * SmemLayout<BM, BN, BK, TA_, TB_>::STAGE;                     \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                 \
     kern<<<grid, THREADS, smem, st>>>(p);                                                           \
@@ -284,12 +291,16 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
   if (p.batch > 65535) return cudaErrorInvalidValue;
   int cfg = force_cfg >= 0 ? force_cfg : gemm_pick_config(p.M, p.N);
   switch (cfg) {
-    case 0: return launch_cfg<128, 128, 32, 32, 4>(p, st);
-    case 1: return launch_cfg<32, 128, 16, 32, 4>(p, st);
-    case 2: return launch_cfg<128, 32, 32, 16, 4>(p, st);
-    case 3: return launch_cfg<128, 8, 16, 8, 4>(p, st);
-    case 4: return launch_cfg<64, 64, 32, 16, 4>(p, st);
-    case 5: return launch_cfg<128, 128, 64, 32, 4>(p, st);
+    case 0: return launch_cfg<128, 128, 32, 32, 16, 4, 0>(p, st);
+    case 1: return launch_cfg<32, 128, 16, 32, 16, 4, 0>(p, st);
+    case 2: return launch_cfg<128, 32, 32, 16, 16, 4, 0>(p, st);
+    case 3: return launch_cfg<128, 8, 16, 8, 16, 4, 0>(p, st);
+    case 4: return launch_cfg<64, 64, 32, 16, 16, 4, 0>(p, st);
+    case 5: return launch_cfg<128, 128, 64, 32, 16, 4, 0>(p, st);
+    case 6: return launch_cfg<128, 128, 64, 32, 16, 4, 1>(p, st);
+    case 7: return launch_cfg<128, 128, 64, 32, 32, 3, 1>(p, st);
+    case 8: return launch_cfg<128, 128, 32, 32, 16, 4, 1>(p, st);
+    case 9: return launch_cfg<128, 128, 32, 32, 32, 3, 1>(p, st);
     default: return cudaErrorInvalidValue;
   }
 }

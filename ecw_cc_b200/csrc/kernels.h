@@ -32,8 +32,11 @@ cudaError_t launch_fill(double* c, int64_t n, double value, cudaStream_t st);
 // partial[z][M*N] -> C[m*sr + n*sc] = alpha*sum + beta*C
 cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, double* C, int64_t sr,
                           int64_t sc, double alpha, double beta, cudaStream_t st);
-// out[ijab] = t2[ijab] + coef*(t1[ia]t1[jb] - t1[ib]t1[ja])
-cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double coef, cudaStream_t st);
+// out[ijab] = t2[ijab] + c1*t1[ia]t1[jb] - c2*t1[ib]t1[ja]
+cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double c1, double c2,
+                       cudaStream_t st);
+// out[0] = max(|x[ijab]+x[jiab]|, |x[ijab]+x[ijba]|)  (0 for exactly antisymmetric doubles amplitudes)
+cudaError_t launch_antisym_defect(const double* x, int o, int v, double* out, cudaStream_t st);
 
 struct PackArgs {
   const double* src;   // 4-index view (pack) / matrix (unpack)

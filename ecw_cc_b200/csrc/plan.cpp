@@ -176,13 +176,14 @@ void Plan::fill(const Tensor& C, double value) {
   ops.push_back(op);
 }
 
-void Plan::tau(const Tensor& t2, const Tensor& t1, double coef, const Tensor& out) {
+void Plan::tau(const Tensor& t2, const Tensor& t1, double c1, double c2, const Tensor& out) {
   Op op;
   op.kind = OP_TAU;
   op.a = t2;
   op.b = t1;
   op.c = out;
-  op.alpha = coef;
+  op.alpha = c1;
+  op.beta = c2;
   ops.push_back(op);
 }
 
@@ -190,7 +191,7 @@ void Plan::pack(double alpha, const Tensor& a4, int flags, double beta, const Te
   if (a4.nd != 4 || c2.nd != 2) throw PlanError("pack: need 4-index source and matrix destination");
   int64_t rows = (flags & 1) ? npair(a4.dim[0]) : a4.dim[0] * a4.dim[1];
   int64_t cols = (flags & 2) ? npair(a4.dim[2]) : a4.dim[2] * a4.dim[3];
-  if ((flags & 1) && a4.dim[0] != a4.dim[1]) throw PlanError("pack: first pair dims differ");
+  if ((flags & 9) && a4.dim[0] != a4.dim[1]) throw PlanError("pack: first pair dims differ");
   if ((flags & 6) && a4.dim[2] != a4.dim[3]) throw PlanError("pack: second pair dims differ");
   if (rows != c2.dim[0] || cols != c2.dim[1]) throw PlanError("pack: destination shape mismatch");
   Op op;

@@ -56,7 +56,7 @@ enum OpKind : int {
   OP_REDUCE,      // C = alpha sum_z P[z] + beta C
   OP_PERMUTE,     // C[..] = alpha A[perm ..] + beta C   (strided N-d copy)
   OP_FILL,        // C = alpha
-  OP_TAU,         // C = t2 + alpha (t1 x t1 antisymmetrised)
+  OP_TAU,         // C = t2 + alpha t1[ia]t1[jb] - beta t1[ib]t1[ja]
   OP_PACK,        // antisymmetric pair packing of a 4-index view
   OP_UNPACK,      // inverse (scatter with signs)
   OP_FINISH,      // residual -> update / subdiff (CCSD.py:316-338)
@@ -112,9 +112,11 @@ class Plan {
                const char* sc, const char* note = "");
   void axpby(double alpha, const Tensor& A, double beta, const Tensor& C, const char* note = "");
   void fill(const Tensor& C, double value);
-  void tau(const Tensor& t2, const Tensor& t1, double coef, const Tensor& out);
+  // out = t2 + c1 t1[ia]t1[jb] - c2 t1[ib]t1[ja]
+  void tau(const Tensor& t2, const Tensor& t1, double c1, double c2, const Tensor& out);
   // pack/unpack: flags bit0 = first pair packed, bit1 = second pair packed,
   //              bit2 = antisymmetrise second pair while packing (x[..rs]-x[..sr])
+  //              bit3 = antisymmetrise first pair while packing  (x[pq..]-x[qp..])
   void pack(double alpha, const Tensor& a4, int flags, double beta, const Tensor& c2);
   void unpack(double alpha, const Tensor& a2, int flags, double beta, const Tensor& c4);
   void finish(const Tensor& resid, const Tensor& amp, const Tensor& fock, int nocc, int rank,

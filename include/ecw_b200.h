@@ -32,6 +32,11 @@ typedef struct ecw_ctx ecw_ctx;
  * of GCC.tupdate (CCSD.py:248) and GCC.lupdate (CCSD.py:419). */
 #define ECW_HAS_ALPHA 1
 #define ECW_EQUATION 2
+/* ECW_ANTISYM: the caller guarantees t2 (and l2) are antisymmetric in (i,j) and (a,b)
+ * (check with ecw_antisym_defect).  Then the ladders also pack the (i,j) rows.  Without
+ * it only the antisymmetry of the integrals is used — required after an L1-regularised
+ * update, which breaks amplitude antisymmetry in the reference (utilities.py:59-67). */
+#define ECW_ANTISYM 4
 
 /* ---- context ------------------------------------------------------------ */
 /* One context per (device, nocc, nvir); replaces `GCC.__init__` (CCSD.py:186-198)
@@ -81,6 +86,8 @@ int ecw_ccsd_gamma(ecw_ctx* ctx, const double* t1, const double* t2, const doubl
 /* GCC.energy(t1,t2,fsp) — CCSD.py:224-242.  e_out: one device double. */
 int ecw_ccsd_energy(ecw_ctx* ctx, const double* t1, const double* t2, const double* fsp, double* e_out,
                     void* stream);
+/* out[0] = max |x[ijab]+x[jiab]|, |x[ijab]+x[ijba]| over a doubles amplitude (device scalar). */
+int ecw_antisym_defect(const double* x, int nocc, int nvir, double* out, void* stream);
 /* utilities.subdiff(eq,var,alpha) — utilities.py:26-73 (element-wise, any shape). */
 int ecw_subdiff(const double* eq, const double* var, double alpha, double* out, int64_t n, void* stream);
 

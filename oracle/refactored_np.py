@@ -305,3 +305,194 @@ def gamma(t1, t2, l1, l2):
     dm[o:, o:] = 0.5 * (dvv + dvv.T)
     dm[np.arange(o), np.arange(o)] += 1.0
     return dm
+
+
+# ======================================================================
+# GENERAL path: amplitudes NOT assumed antisymmetric.
+#
+# The reference's L1 update (utilities.py:53-67: v<=0 is soft-thresholded,
+# v>0 gets e+alpha) destroys the antisymmetry of t2/l2 after the first
+# regularised iteration, and its dense einsums are evaluated on whatever they
+# are given.  The variant below uses only the antisymmetry of the INTEGRALS
+# (Eris.py:128), never that of the amplitudes: contracted integral pairs are
+# still packed (the amplitude is antisymmetrised while packing), but the (i,j)
+# rows of the ladders stay dense (o^2 instead of o(o-1)/2).
+# ======================================================================
+def make_tau2(t1, t2, c1, c2):
+    """t2 + c1 t1[ia]t1[jb] - c2 t1[ib]t1[ja]"""
+    x = es('ia,jb->ijab', t1, t1)
+    return t2 + c1 * x - c2 * x.transpose(0, 1, 3, 2)
+
+
+def tupdate_general(E, fock, t1, t2, fsp=None, alpha=None, equation=False):
+    o, v = t1.shape
+    if fsp is None:
+        fsp = fock
+    foo, fov, fvv = fsp[:o, :o], fsp[:o, o:], fsp[o:, o:]
+    e_o, e_v = np.diagonal(fock)[:o], np.diagonal(fock)[o:]
+    shift = (not equation) and alpha is None
+
+    tau = make_tau2(t1, t2, 1.0, 1.0)
+    ttl = make_tau2(t1, t2, 0.5, 0.5)
+    tau_q = 0.5 * pack_last(tau - tau.transpose(0, 1, 3, 2)).reshape(o * o, -1)   # [(ij), ef_p]
+    tau_r = 0.5 * pack_first(tau - tau.transpose(1, 0, 2, 3)).reshape(-1, v * v)  # [mn_p, (ab)]
+    t2ph = np.ascontiguousarray(t2.transpose(0, 2, 1, 3))          # [(ia),(jb)] = t2[i,j,a,b]
+    t2ph2 = np.ascontiguousarray(t2.transpose(1, 2, 0, 3))         # [(nf),(jb)] = t2[j,n,f,b]
+
+    G = es('menf,nf->me', E.oovv_ph, t1)
+    Fov = fov + G
+    Fvv = fvv - 0.5 * es('me,ma->ae', fov, t1)
+    Fvv = Fvv - es('maef,mf->ae', E.ovvv, t1)
+    Fvv = Fvv + 0.5 * es('mnaf,mnfe->ae', ttl, E.oovv)
+    Foo = foo + 0.5 * es('me,ie->mi', fov, t1)
+    Foo = Foo + es('mnie,ne->mi', E.ooov, t1)
+    Foo = Foo + 0.5 * es('mnef,inef->mi', E.oovv, ttl)
+    if shift:
+        Fvv = Fvv - np.diag(e_v)
+        Foo = Foo - np.diag(e_o)
+
+    r1 = fov + es('ie,ae->ia', t1, Fvv) - es('mi,ma->ia', Foo, t1)
+    r1 += es('iame,me->ia', t2ph, Fov)
+    r1 -= es('ianf,nf->ia', E.ovov_ph, t1)
+    r1 -= 0.5 * es('imef,maef->ia', t2, E.ovvv)
+    r1 -= 0.5 * es('mnae,mnie->ia', t2, E.ooov)
+
+    F1 = Fvv - 0.5 * es('mb,me->be', t1, Fov)
+    x = es('ijae,be->ijab', t2, F1)
+    r2 = E.oovv + x - x.transpose(0, 1, 3, 2)
+    F2 = Foo + 0.5 * es('je,me->mj', t1, Fov)
+    x = es('mj,imab->ijab', F2, t2)
+    r2 -= x - x.transpose(1, 0, 2, 3)
+
+    x = es('mnie,je->mnij', E.ooov, t1)
+    Woo_p = pack_first(E.oooo + x - x.transpose(0, 1, 3, 2)).reshape(-1, o * o)   # [mn_p, (ij)]
+    Woo_p = Woo_p + es('mf,if->mi', E.oovv_p, tau_q)
+    r2 += es('mi,ma->ia', Woo_p, tau_r).reshape(o, o, v, v)       # hh ladder, dense output
+    acc_q = es('if,af->ia', tau_q, E.vvvv_p)                      # [(ij), ab_p]
+    ovvv_p2 = E.ovvv_p.reshape(o * v, -1)
+    Y_q = -2.0 * es('if,qf->iq', tau_q, ovvv_p2).reshape(-1, o, v)
+    Z = es('pma,mb->pab', Y_q, t1)
+    acc_q += -0.5 * pack_last(Z - Z.transpose(0, 2, 1))
+    r2 += unpack_last(acc_q, v).reshape(o, o, v, v)
+
+    Wph = -0.5 * es('menf,nfjb->mejb', E.oovv_ph, t2ph2)
+    Wph += es('mbef,jf->mejb', E.ovvv, t1)
+    Wph += es('nb,mnje->mejb', t1, E.ooov)
+    U = es('mnef,jf->mnej', E.oovv, t1)
+    Wph -= es('nb,mnej->mejb', t1, U)
+    Wph -= E.ovov_ph
+    ring = es('iame,mejb->iajb', t2ph, Wph)
+    Q = es('jbme,ie->jbmi', E.ovov_ph, t1)
+    ring += es('ma,jbmi->iajb', t1, Q)
+    r2 += antisym_ph(ring)
+    x = -es('ie,jeab->ijab', t1, E.ovvv)
+    r2 += x - x.transpose(1, 0, 2, 3)
+    x = es('ma,ijmb->ijab', t1, E.ooov)
+    r2 -= x - x.transpose(0, 1, 3, 2)
+    return finish(r1, r2, t1, t2, e_o, e_v, alpha, equation)
+
+
+def lupdate_general(E, fock, t1, t2, l1, l2, fsp=None, alpha=None, equation=False):
+    o, v = t1.shape
+    if fsp is None:
+        fsp = fock
+    foo, fov, fvo, fvv = fsp[:o, :o], fsp[:o, o:], fsp[o:, :o], fsp[o:, o:]
+    e_o, e_v = np.diagonal(fock)[:o], np.diagonal(fock)[o:]
+    shift = (equation is False) and alpha is None
+
+    tau = make_tau2(t1, t2, 2.0, 0.0)                               # CCSD.py:565 exactly
+    tau_q = 0.5 * pack_last(tau - tau.transpose(0, 1, 3, 2)).reshape(o * o, -1)
+    l2_q = 0.5 * pack_last(l2 - l2.transpose(0, 1, 3, 2)).reshape(o * o, -1)
+    t2ph = np.ascontiguousarray(t2.transpose(0, 2, 1, 3))
+    l2ph = np.ascontiguousarray(l2.transpose(0, 2, 1, 3))          # [(ib),(jc)] = l2[i,j,b,c]
+    l2ph2 = np.ascontiguousarray(l2.transpose(1, 3, 0, 2))         # [(ia),(kc)] = l2[k,i,c,a]
+
+    G = es('menf,nf->me', E.oovv_ph, t1)
+    Fov = fov + G
+    v1 = fvv - es('ja,jb->ba', fov, t1)
+    v1 = v1 - es('jbac,jc->ba', E.ovvv, t1)
+    v1 = v1 + 0.5 * es('jkca,jkbc->ba', E.oovv, tau)
+    v2 = foo + es('ib,jb->ij', fov, t1)
+    v2 = v2 - es('kijb,kb->ij', E.ooov, t1)
+    v2 = v2 + 0.5 * es('ikbc,jkbc->ij', E.oovv, tau)
+
+    v4ph = es('kcld,ldjb->kcjb', t2ph, E.oovv_ph) - E.ovov_ph
+    v5T = fvo.T + es('jbkc,kc->jb', t2ph, fov)
+    q = es('kc,jc->kj', Fov, t1)
+    v5T = v5T + es('kj,kb->jb', q, t1)
+    v5T = v5T - 0.5 * es('kljc,klbc->jb', E.ooov, t2)
+    v5T = v5T - 0.5 * es('jkdc,kbdc->jb', t2, E.ovvv)
+    w3T = v5T + es('kcjb,jb->kc', v4ph, t1)
+    w3T = w3T + es('kb,cb->kc', t1, v1)
+    w3T = w3T - es('jk,jc->kc', v2, t1)
+
+    # woooo packed on its antisymmetric (integral) first pair only: [ij_p, (kl)]
+    y = es('jilc,kc->jilk', E.ooov, t1)
+    woo_p = pack_first(0.5 * E.oooo + y).reshape(-1, o * o)
+    woo_p = woo_p + 0.5 * es('if,kf->ik', E.oovv_p, tau_q)         # 1/4 v3, v3 = 2 oovv_p.tau_q
+    lt = es('ijcd,klcd->ijkl', l2, tau)                            # dense, no symmetry
+
+    S = es('ljbd,kd->ljbk', E.oovv, t1)
+    wph = v4ph + es('lc,ljbk->kcjb', t1, S)
+    wph = wph - es('lc,ljkb->kcjb', t1, E.ooov)
+    wph = wph + es('jcbd,kd->kcjb', E.ovvv, t1)
+
+    ovvv_p2 = E.ovvv_p.reshape(o * v, -1)
+    wovoo = 0.5 * es('qf,kf->qk', ovvv_p2, tau_q).reshape(o, v, o, o)
+    wovoo = wovoo + 0.5 * E.ooov.transpose(2, 3, 0, 1)
+    wovoo = wovoo + es('kcib,jb->icjk', v4ph, t1)
+    wovoo = wovoo - es('kclb,lijb->icjk', t2ph, E.ooov)
+
+    # m3 dense [ij,ab]; pieces with an antisymmetric integral pair are accumulated packed
+    m3 = unpack_first(es('ik,ka->ia', woo_p, l2.reshape(o * o, v * v)), o).reshape(o, o, v, v)
+    ltp = pack_last(lt - lt.transpose(0, 1, 3, 2)).reshape(o * o, -1)     # [(ij), kl_p]
+    acc_q = 0.25 * es('ik,ka->ia', ltp, E.oovv_p)
+    l2t1 = es('ijcd,kd->ijck', l2, t1)
+    a_q = np.ascontiguousarray(l2t1.transpose(0, 1, 3, 2)).reshape(o * o, o * v)
+    acc_q += es('pq,qa->pa', a_q, ovvv_p2)
+    acc_q += es('if,af->ia', l2_q, E.vvvv_p)
+    m3 += unpack_last(acc_q, v).reshape(o, o, v, v)
+
+    m_vv = 0.5 * es('klcb,klca->ba', t2, l2)
+    m_oo = 0.5 * es('kicd,kjcd->ij', l2, t2)
+    x_vv = m_vv + es('ka,kb->ba', l1, t1)
+    x_oo = m_oo + es('ic,kc->ik', l1, t1)
+    if shift:
+        v1s = v1 - np.diag(e_v)
+        v2s = v2 - np.diag(e_o)
+    else:
+        v1s, v2s = v1, v2
+
+    r2 = E.oovv + m3
+    ring = es('iakc,kcjb->iajb', l2ph2, wph) + es('ia,jb->iajb', l1, Fov)
+    r2 += antisym_ph(ring)
+    y = es('ka,ijkb->ijab', l1, E.ooov) + es('ijca,cb->ijab', l2, v1s)
+    y += es('ca,ijcb->ijab', x_vv, E.oovv)
+    r2 -= y - y.transpose(0, 1, 3, 2)
+    y = es('qc,pcrs->pqrs', l1, E.ovvv)
+    y = y + es('qk,kprs->pqrs', v2s, l2) - es('pk,kqrs->pqrs', x_oo, E.oovv)
+    r2 += y - y.transpose(1, 0, 2, 3)
+
+    r1 = fov - es('jbia,jb->ia', E.ovov_ph, l1)
+    r1 += es('ib,ba->ia', l1, v1s) - es('ij,ja->ia', v2s, l1)
+    r1 -= es('icjk,kjca->ia', wovoo, l2)
+    l2t1b = es('ikbc,jb->ikcj', l2, t1)
+    r1 -= es('ikcj,kcja->ia', l2t1b, v4ph)
+    r1 -= 0.25 * es('ikjl,jlka->ia', lt, E.ooov)
+    r1 -= 0.5 * es('ikbc,kabc->ia', l2, E.ovvv)
+    Xph = es('ibjc,jckd->ibkd', l2ph, t2ph)
+    r1 += es('ibkd,kbda->ia', Xph, E.ovvv)
+    r1 += es('ijab,jb->ia', m3, t1)
+    r1 += es('iajb,jb->ia', l2ph2, w3T)
+    z = t1 + es('kcjb,kc->jb', t2ph, l1) - es('bd,jd->jb', x_vv, t1) - es('lj,lb->jb', m_oo, t1)
+    r1 += es('iajb,jb->ia', E.oovv_ph, z)
+    r1 -= es('icba,bc->ia', E.ovvv, x_vv)
+    r1 -= es('jika,kj->ia', E.ooov, x_oo)
+    r1 -= es('ik,ka->ia', m_oo, Fov)
+    r1 -= es('ca,ic->ia', m_vv, Fov)
+
+    if shift:
+        Ecc = energy(E, t1, t2, fsp)
+        r1 = r1 * (1.0 - Ecc)
+        r2 = r2 * (1.0 - Ecc)
+    return finish(r1, r2, l1, l2, e_o, e_v, alpha, equation)

@@ -35,5 +35,5 @@ def eris_slots(er):
                 ovvv_p=E.ovvv_p, vvvv_p=E.vvvv_p)
 
 
-def flags_of(alpha, equation):
-    return (1 if alpha is not None else 0) | (2 if equation else 0)
+def flags_of(alpha, equation, antisym=True):
+    return (1 if alpha is not None else 0) | (2 if equation else 0) | (4 if antisym else 0)

@@ -103,7 +103,7 @@ class Interp(object):
     def op_tau(self, op):
         t2, t1, out = self.view(op["a"]), self.view(op["b"]), self.view(op["c"])
         x = np.einsum('ia,jb->ijab', t1, t1)
-        out[...] = t2 + op["alpha"] * (x - x.transpose(0, 1, 3, 2))
+        out[...] = t2 + (op["alpha"] * x - op["beta"] * x.transpose(0, 1, 3, 2))
 
     def op_pack(self, op):
         A, C = self.view(op["a"]), self.view(op["c"])
@@ -111,6 +111,8 @@ class Interp(object):
         x = A
         if fl & 4:
             x = x - x.transpose(0, 1, 3, 2)
+        if fl & 8:
+            x = x - x.transpose(1, 0, 2, 3)
         if fl & 2:
             lo, hi = pair_decode(A.shape[2])
             x = x[:, :, lo, hi]

@@ -23,7 +23,7 @@ def _dev(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_dgemm_all_layouts(ecw, cfg, ta, tb):
     import torch
@@ -156,6 +156,37 @@ def test_device_resident_and_synthetic_eris(ecw):
     assert np.abs(c.cpu().numpy() - rc).max() < TOL and np.abs(d.cpu().numpy() - rd).max() < TOL
     # reference attribute surface used by Solver_GS.py:554-559
     assert np.array_equal(cc.eris.oovv, synth.SynthEris(o, v).oovv)
+
+
+@pytest.mark.parametrize("ov", [(3, 4), (5, 9), (8, 21)])
+def test_general_path_unsymmetric_amplitudes(ecw, ov):
+    """t2/l2 without permutational symmetry (what the reference's L1 update produces, Q1):
+    the host measures the antisymmetry defect on the device and runs the general path."""
+    from oracle import synth
+    from oracle.ccsd_np import OracleGCC
+    o, v = ov
+    er = synth.SynthEris(o, v)
+    fsp = synth.fsp(o, v)
+    rng = np.random.default_rng(17 * o + v)
+    t1, l1 = 0.05 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, v))
+    t2, l2 = 0.02 * rng.standard_normal((o, o, v, v)), 0.02 * rng.standard_normal((o, o, v, v))
+    orc, cc = OracleGCC(er), ecw.GCC(er)
+    assert cc.antisym_defect(_dev(t2)) > 1e-3
+    assert cc.antisym_defect(_dev(synth.amplitudes(o, v)[1])) == 0.0
+    for tag, alpha, eq in MODES:
+        a, b = cc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq)
+        c, d = orc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq)
+        assert np.abs(a - c).max() < TOL and np.abs(b - d).max() < TOL, ("tupdate", tag)
+        a, b = cc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq)
+        c, d = orc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq)
+        assert np.abs(a - c).max() < TOL and np.abs(b - d).max() < TOL, ("lupdate", tag)
+    assert np.abs(cc.gamma(t1, t2, l1, l2) - orc.gamma(t1, t2, l1, l2)).max() < TOL
+    assert abs(cc.energy(t1, t2, fsp) - orc.energy(t1, t2, fsp)) < TOL
+    # general path on antisymmetric input == packed path
+    t1a, t2a, l1a, l2a = synth.amplitudes(o, v)
+    fast = ecw.GCC(cc.eris, assume_antisym=True).lupdate(t1a, t2a, l1a, l2a, fsp=fsp)
+    gen = ecw.GCC(cc.eris, assume_antisym=False).lupdate(t1a, t2a, l1a, l2a, fsp=fsp)
+    assert np.abs(fast[0] - gen[0]).max() < 1e-13 and np.abs(fast[1] - gen[1]).max() < 1e-13
 
 
 def test_subdiff_kernel(ecw):

@@ -44,6 +44,67 @@ def test_ccsd_plans_match_oracle(built_lib, ov):
     assert abs(it.slots["scal"][0] - orc.energy(t1, t2, fsp)) < TOL
 
 
+@pytest.mark.parametrize("ov", [(3, 4), (4, 6), (5, 9)])
+def test_general_plans_with_unsymmetric_amplitudes(built_lib, ov):
+    """General path (no ECW_ANTISYM flag): t2/l2 without any permutational symmetry, as the
+    reference's dense einsums accept them — the state of the amplitudes after an L1 update."""
+    o, v = ov
+    er = synth.SynthEris(o, v)
+    fsp = synth.fsp(o, v)
+    rng = np.random.default_rng(17 * o + v)
+    t1, l1 = 0.05 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, v))
+    t2, l2 = 0.02 * rng.standard_normal((o, o, v, v)), 0.02 * rng.standard_normal((o, o, v, v))
+    orc = OracleGCC(er)
+    base = eris_slots(er)
+    base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=fsp, fock=er.fock.copy())
+    for tag, alpha, eq in MODES:
+        for fn in ("tupdate", "lupdate"):
+            sl = dict(base)
+            sl["out1"] = np.full((o, v), np.nan)
+            sl["out2"] = np.full((o, o, v, v), np.nan)
+            Interp(plan_json(built_lib, o, v, fn, flags_of(alpha, eq, antisym=False)), sl, alpha=alpha or 0.0).run()
+            if fn == "tupdate":
+                ref = orc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq)
+            else:
+                ref = orc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq)
+            assert np.abs(sl["out1"] - ref[0]).max() < TOL, (fn, tag)
+            assert np.abs(sl["out2"] - ref[1]).max() < TOL, (fn, tag)
+    # gamma / energy never assume antisymmetry
+    sl = dict(base)
+    sl["rdm1"] = np.full((o + v, o + v), np.nan)
+    Interp(plan_json(built_lib, o, v, "gamma", 0), sl).run()
+    assert np.abs(sl["rdm1"] - orc.gamma(t1, t2, l1, l2)).max() < TOL
+    it = Interp(plan_json(built_lib, o, v, "energy", 0), dict(base)).run()
+    assert abs(it.slots["scal"][0] - orc.energy(t1, t2, fsp)) < TOL
+
+
+def test_l1_update_breaks_antisymmetry_and_general_path_tracks_it(built_lib):
+    """Q1 consequence: after one L1-regularised tupdate the reference's t2 is no longer
+    antisymmetric; the packed path would then be wrong at the 1e-8 level, the general path is exact."""
+    o, v = 5, 9
+    er = synth.SynthEris(o, v)
+    fsp = synth.fsp(o, v)
+    orc = OracleGCC(er)
+    e = np.diagonal(er.fock)
+    d1 = e[:o, None] - e[None, o:]
+    d2 = d1[:, None, :, None] + d1[None, :, None, :]
+    ts, ls, td = np.zeros((o, v)), np.zeros((o, v)), er.oovv / d2
+    ld = td.copy()
+    ts, td = orc.tupdate(ts, td, fsp=fsp, alpha=5e-4)
+    assert np.abs(td + td.transpose(1, 0, 2, 3)).max() > 1e-6
+    ref = orc.lupdate(ts, td, ls, ld, fsp=fsp, alpha=5e-4)
+    base = eris_slots(er)
+    base.update(t1=ts, t2=td, l1=ls, l2=ld, fsp=fsp, fock=er.fock.copy())
+    err = {}
+    for anti in (True, False):
+        sl = dict(base)
+        sl["out1"] = np.full((o, v), np.nan)
+        sl["out2"] = np.full((o, o, v, v), np.nan)
+        Interp(plan_json(built_lib, o, v, "lupdate", flags_of(5e-4, False, antisym=anti)), sl, alpha=5e-4).run()
+        err[anti] = max(np.abs(sl["out1"] - ref[0]).max(), np.abs(sl["out2"] - ref[1]).max())
+    assert err[False] < TOL and err[True] > 1e-9
+
+
 def test_ccsd_plan_matches_golden(built_lib):
     g = load_golden("ccsd_o5v8.npz")
     o, v = 5, 8
@@ -67,7 +128,7 @@ def test_north_star_plan_has_no_integral_permutes(built_lib):
     o, v = 40, 400
     total = 0.0
     for fn in ("tupdate", "lupdate"):
-        pl = plan_json(built_lib, o, v, fn, 0)
+        pl = plan_json(built_lib, o, v, fn, 4)
         assert pl["workspace_elems"] * 8 < 40e9
         for op in pl["ops"]:
             if op["kind"] == "permute":

@@ -29,9 +29,8 @@ def main():
     out = []
     st = torch.cuda.current_stream().cuda_stream
     shapes = [("cube8192", 8192, 8192, 8192, 0, 0), ("cube8192_nt", 8192, 8192, 8192, 0, 1),
-              ("ring16000", 16000, 16000, 16000, 0, 0),
-              ("ladder780", 780, 16384, 79800, 0, 1), ("R9_780x16000", 780, 16000, 79800, 0, 1),
-              ("R6_nn", 780, 79800, 16000, 0, 0), ("hh_tn", 780, 79800, 780, 1, 0)]
+              ("ring16000", 16000, 16000, 16000, 0, 0), ("ladder780", 780, 16384, 79800, 0, 1),
+              ("R6_nn", 780, 79800, 16000, 0, 0)]
     for name, M, N, K, ta, tb in shapes:
         A = torch.randn((K, M) if ta else (M, K), dtype=torch.float64, device="cuda")
         B = torch.randn((N, K) if tb else (K, N), dtype=torch.float64, device="cuda")
@@ -42,7 +41,7 @@ def main():
         ms = timeit(lambda: torch.matmul(Aop, Bop, out=C))
         ref = C.clone()
         rec = {"shape": name, "M": M, "N": N, "K": K, "ta": ta, "tb": tb, "cublas_tflops": fl / ms / 1e9}
-        for cfg in (0, 5, 4):
+        for cfg in (0, 5, 6, 7, 8, 9):
             def run():
                 rc = lib.ecw_dgemm(ta, tb, M, N, K, 1.0, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1], 0.0,
                                    C.data_ptr(), N, cfg, st)
