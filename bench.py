@@ -194,7 +194,7 @@ def run_ours(args):
     o, v = args.nocc, args.nvir
     n = o + v
 
-    de = ecw.DeviceEris.synthetic(o, v)
+    de = ecw.DeviceEris.synthetic(o, v, rank=rank, world=world)
     cc = ecw.GCC(de)
     t1, t2 = de.synth_tensor("t1", (o, v)), de.synth_tensor("t2", (o, o, v, v))
     l1, l2 = de.synth_tensor("l1", (o, v)), de.synth_tensor("l2", (o, o, v, v))

@@ -25,14 +25,14 @@ def _flags(alpha, equation, antisym=False):
 
 
 class GCC(object):
-    def __init__(self, eris, fock=None, device=None, assume_antisym=None):
+    def __init__(self, eris, fock=None, device=None, assume_antisym=None, rank=0, world=1, group=None):
         """:param eris: a `DeviceEris`, or any object with the reference's
         `Eris.geris` attribute surface (uploaded once).
         :param assume_antisym: None (default) = measure the antisymmetry of the doubles amplitudes
         on the device at every call and pick the packed or the general path; True/False = force."""
         self.assume_antisym = assume_antisym
         if not isinstance(eris, DeviceEris):
-            eris = DeviceEris.from_geris(eris, device=device)
+            eris = DeviceEris.from_geris(eris, device=device, rank=rank, world=world, group=group)
         self.eris = eris
         self.nocc = eris.nocc
         if fock is None:                       # CCSD.py:196-198
@@ -117,8 +117,8 @@ class GCC(object):
         d_l2, _ = self._to_dev("l2", l2, (o, o, v, v))
         out = torch.empty((o + v, o + v), dtype=torch.float64, device=e.device)
         e.ensure_workspace("gamma", 0)
-        e.check(lib.ecw_ccsd_gamma(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(), d_l2.data_ptr(),
-                                   out.data_ptr(), e.stream()), "ecw_ccsd_gamma")
+        e.run(lib.ecw_ccsd_gamma(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(), d_l2.data_ptr(),
+                                 out.data_ptr(), e.stream()), "ecw_ccsd_gamma")
         return out if dev else self._to_host(out)
 
     # -- energy (CCSD.py:224-242) -------------------------------------------------
@@ -131,8 +131,8 @@ class GCC(object):
         d_f, _ = self._fsp(fsp)
         out = torch.empty(1, dtype=torch.float64, device=e.device)
         e.ensure_workspace("energy", 0)
-        e.check(lib.ecw_ccsd_energy(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(), out.data_ptr(),
-                                    e.stream()), "ecw_ccsd_energy")
+        e.run(lib.ecw_ccsd_energy(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(), out.data_ptr(),
+                                  e.stream()), "ecw_ccsd_energy")
         if dev:
             return out[0]
         self.d2h_bytes += 8
@@ -150,9 +150,9 @@ class GCC(object):
         o2 = torch.empty((o, o, v, v), dtype=torch.float64, device=e.device)
         fl = _flags(alpha, equation, self._is_antisym(d_t2))
         e.ensure_workspace("tupdate", fl)
-        e.check(lib.ecw_ccsd_tupdate(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(), e.fock_dev.data_ptr(),
-                                     fl, float(alpha or 0.0), o1.data_ptr(), o2.data_ptr(), e.stream()),
-                "ecw_ccsd_tupdate")
+        e.run(lib.ecw_ccsd_tupdate(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(), e.fock_dev.data_ptr(),
+                                   fl, float(alpha or 0.0), o1.data_ptr(), o2.data_ptr(), e.stream()),
+              "ecw_ccsd_tupdate")
         if dev:
             return o1, o2
         return self._to_host(o1, o2)
@@ -171,9 +171,9 @@ class GCC(object):
         o2 = torch.empty((o, o, v, v), dtype=torch.float64, device=e.device)
         fl = _flags(alpha, equation, self._is_antisym(d_t2, d_l2))
         e.ensure_workspace("lupdate", fl)
-        e.check(lib.ecw_ccsd_lupdate(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(), d_l2.data_ptr(),
-                                     d_f.data_ptr(), e.fock_dev.data_ptr(), fl, float(alpha or 0.0),
-                                     o1.data_ptr(), o2.data_ptr(), e.stream()), "ecw_ccsd_lupdate")
+        e.run(lib.ecw_ccsd_lupdate(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(), d_l2.data_ptr(),
+                                   d_f.data_ptr(), e.fock_dev.data_ptr(), fl, float(alpha or 0.0),
+                                   o1.data_ptr(), o2.data_ptr(), e.stream()), "ecw_ccsd_lupdate")
         if dev:
             return o1, o2
         return self._to_host(o1, o2)

@@ -54,6 +54,9 @@ class _Lib(object):
             "ecw_ctx_destroy": (None, [c_p]),
             "ecw_last_error": (c_s, [c_p]),
             "ecw_version": (c_s, []),
+            "ecw_ctx_set_shard": (c_i, [c_p, c_i, c_i]),
+            "ecw_resume": (c_i, [c_p, c_p]),
+            "ecw_pending_collective": (c_i, [c_p, ctypes.POINTER(c_l)]),
             "ecw_slot_elems": (c_l, [c_p, c_s]),
             "ecw_bind": (c_i, [c_p, c_s, c_p]),
             "ecw_eris_pack_from_dense": (c_i, [c_p, c_p, c_p, c_p]),

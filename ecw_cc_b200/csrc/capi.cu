@@ -2,6 +2,7 @@
 // declared in include/ecw_b200.h.
 #include "../../include/ecw_b200.h"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -21,6 +22,12 @@ struct ecw_ctx {
   int64_t ws_bytes = 0;
   std::map<std::string, std::unique_ptr<Plan>> plans;
   bool profile = false;
+  // resumable execution (plans with collectives yield to the host)
+  const Plan* run_plan_ptr = nullptr;
+  size_t pc = 0;
+  double run_alpha = 0.0;
+  int64_t pending[6] = {0, 0, 0, 0, 0, 0};
+  double* copy_scal_to = nullptr;
   std::vector<cudaEvent_t> ev;
   const Plan* last_plan = nullptr;
   ecw_ctx() { for (auto& p : ptr) p = nullptr; }
@@ -47,7 +54,11 @@ int64_t slot_elems(const Sizes& z, int s) {
     case S_OOOO_P: return po * po;
     case S_OOVV_P: return po * pv;
     case S_OVVV_P: return o * v * pv;
-    case S_VVVV_P: return pv * pv;
+    case S_VVVV_P: {
+      const int64_t nshmax = (pv + z.world - 1) / z.world;
+      const int64_t n0 = std::min<int64_t>(pv, (int64_t)z.rank * nshmax);
+      return (std::min<int64_t>(pv, n0 + nshmax) - n0) * pv;
+    }
     default: return -1;
   }
 }
@@ -87,19 +98,13 @@ double* resolve(ecw_ctx* c, const Tensor& t, bool required = true) {
 
 void exec_ewise(ecw_ctx* c, const Op& op, cudaStream_t st);   // ccs helpers (ccs_exec.cu)
 
-void run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
-  if (P.workspace_elems() * 8 > c->ws_bytes)
-    throw Fail("workspace too small: need " + std::to_string(P.workspace_elems() * 8) + " bytes, have " +
-               std::to_string(c->ws_bytes));
-  if (c->profile) {
-    for (auto e : c->ev) cudaEventDestroy(e);
-    c->ev.assign(P.ops.size() + 1, nullptr);
-    for (auto& e : c->ev) ck(cudaEventCreate(&e), "cudaEventCreate");
-    ck(cudaEventRecord(c->ev[0], st), "cudaEventRecord");
-    c->last_plan = &P;
-  }
-  size_t iop = 0;
-  for (const Op& op : P.ops) {
+// Runs ops from c->pc until the end (returns 0) or until a collective op (returns 1: the host
+// performs it — torch.distributed over NCCL — and calls ecw_resume).
+int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
+  const Plan& P = *c->run_plan_ptr;
+  const double alpha_rt = c->run_alpha;
+  while (c->pc < P.ops.size()) {
+    const Op& op = P.ops[c->pc];
     switch (op.kind) {
       case OP_GEMM: {
         GemmArgs g{};
@@ -122,12 +127,9 @@ void run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
         ck(launch_permute(a, st), "permute");
         break;
       }
-      case OP_FILL: {
-        PermArgs a{};   // strided fill via permute of itself with alpha=0 is wasteful; fill is only used on dense tensors
+      case OP_FILL:
         ck(launch_fill(resolve(c, op.c), op.c.size(), op.alpha, st), "fill");
-        (void)a;
         break;
-      }
       case OP_TAU:
         ck(launch_tau(resolve(c, op.a), resolve(c, op.b), resolve(c, op.c), (int)op.b.dim[0], (int)op.b.dim[1],
                       op.alpha, op.beta, st), "tau");
@@ -158,9 +160,9 @@ void run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
         break;
       }
       case OP_DOT:
+        if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
         ck(launch_dot(resolve(c, op.a), resolve(c, op.b), op.a.size(), resolve(c, op.c), (int)op.i1,
-                      c->ptr[S_SCAL] ? c->ptr[S_SCAL] + op.i0 : (throw Fail("slot 'scal' is not bound"), nullptr),
-                      op.alpha, op.beta, st), "dot");
+                      c->ptr[S_SCAL] + op.i0, op.alpha, op.beta, st), "dot");
         break;
       case OP_SCALE_DEV:
         if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
@@ -177,11 +179,47 @@ void run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
       case OP_EWISE:
         exec_ewise(c, op, st);
         break;
+      case OP_ALLGATHER: {
+        if (op.a.slot != S_WS || op.c.slot != S_WS) throw Fail("collective operands must live in the workspace");
+        c->pending[0] = 1;                 // kind: all-gather
+        c->pending[1] = op.a.off;          // element offset of this rank's contribution in the workspace
+        c->pending[2] = op.i0;             // elements per rank
+        c->pending[3] = op.c.off;          // element offset of the gathered buffer (world * count elements)
+        c->pending[4] = op.i1;             // world
+        c->pending[5] = op.i2;             // rank
+        ++c->pc;
+        if (c->profile) ck(cudaEventRecord(c->ev[c->pc], st), "cudaEventRecord");
+        return 1;
+      }
       default:
         throw Fail("unknown op kind");
     }
-    if (c->profile) ck(cudaEventRecord(c->ev[++iop], st), "cudaEventRecord");
+    ++c->pc;
+    if (c->profile) ck(cudaEventRecord(c->ev[c->pc], st), "cudaEventRecord");
   }
+  if (c->copy_scal_to) {
+    ck(cudaMemcpyAsync(c->copy_scal_to, c->ptr[S_SCAL], sizeof(double), cudaMemcpyDeviceToDevice, st), "copy scalar");
+    c->copy_scal_to = nullptr;
+  }
+  c->run_plan_ptr = nullptr;
+  return 0;
+}
+
+int run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
+  if (P.workspace_elems() * 8 > c->ws_bytes)
+    throw Fail("workspace too small: need " + std::to_string(P.workspace_elems() * 8) + " bytes, have " +
+               std::to_string(c->ws_bytes));
+  if (c->profile) {
+    for (auto e : c->ev) cudaEventDestroy(e);
+    c->ev.assign(P.ops.size() + 1, nullptr);
+    for (auto& e : c->ev) ck(cudaEventCreate(&e), "cudaEventCreate");
+    ck(cudaEventRecord(c->ev[0], st), "cudaEventRecord");
+    c->last_plan = &P;
+  }
+  c->run_plan_ptr = &P;
+  c->pc = 0;
+  c->run_alpha = alpha_rt;
+  return run_plan_resume(c, st);
 }
 
 template <typename F>
@@ -191,6 +229,16 @@ int guarded(ecw_ctx* c, F&& f) {
     return 0;
   } catch (const std::exception& e) {
     if (c) c->err = e.what();
+    return -1;
+  }
+}
+
+template <typename F>
+int guarded_rc(ecw_ctx* c, F&& f) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    if (c) { c->err = e.what(); c->run_plan_ptr = nullptr; }
     return -1;
   }
 }
@@ -233,6 +281,28 @@ void ecw_ctx_destroy(ecw_ctx* c) {
 
 const char* ecw_last_error(ecw_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
+int ecw_ctx_set_shard(ecw_ctx* c, int rank, int world) {
+  if (!c || world < 1 || rank < 0 || rank >= world) return -1;
+  c->z.rank = rank;
+  c->z.world = world;
+  c->plans.clear();
+  c->run_plan_ptr = nullptr;
+  return 0;
+}
+
+int ecw_resume(ecw_ctx* c, void* stream) {
+  return guarded_rc(c, [&] {
+    if (!c->run_plan_ptr) throw Fail("ecw_resume: no call in flight");
+    return run_plan_resume(c, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int ecw_pending_collective(ecw_ctx* c, int64_t* desc6) {
+  if (!c || !c->run_plan_ptr) return -1;
+  for (int i = 0; i < 6; ++i) desc6[i] = c->pending[i];
+  return 0;
+}
+
 int64_t ecw_slot_elems(ecw_ctx* c, const char* slot) {
   if (!c) return -1;
   int s = slot_by_name(slot);
@@ -264,6 +334,7 @@ int ecw_set_workspace(ecw_ctx* c, void* p, int64_t bytes) {
 int ecw_eris_pack_from_dense(ecw_ctx* c, const double* ovov, const double* vvvv, void* stream) {
   return guarded(c, [&] {
     require_device();
+    if (c->z.world != 1) throw Fail("ecw_eris_pack_from_dense: pack before ecw_ctx_set_shard (vvvv_p must be bound whole)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t o = c->z.nocc, v = c->z.nvir;
     for (int s : {S_OOOO, S_OOOV, S_OOVV, S_OVVV, S_OOVV_PH, S_OVOV_PH, S_OOOO_P, S_OOVV_P, S_OVVV_P, S_VVVV_P})
@@ -297,7 +368,13 @@ int ecw_eris_synthetic(ecw_ctx* c, double scale, void* stream) {
         {S_OVVV_P, SY_OVVV_P, o}, {S_VVVV_P, SY_VVVV_P, pv}};
     for (auto& t : tab) {
       if (!c->ptr[t.slot]) throw Fail(std::string("slot '") + slot_name(t.slot) + "' is not bound");
-      ck(launch_synth(t.kind, c->ptr[t.slot], o, v, 0, t.rows, scale, st), "synth");
+      int64_t r0 = 0, nr = t.rows;
+      if (t.slot == S_VVVV_P) {   // this rank's rows of the packed virtual pair index
+        const int64_t nshmax = (pv + c->z.world - 1) / c->z.world;
+        r0 = std::min<int64_t>(pv, (int64_t)c->z.rank * nshmax);
+        nr = std::min<int64_t>(pv, r0 + nshmax) - r0;
+      }
+      ck(launch_synth(t.kind, c->ptr[t.slot], o, v, r0, nr, scale, st), "synth");
     }
   });
 }
@@ -312,48 +389,47 @@ int ecw_synth_tensor(int kind, double* out, int nocc, int nvir, int64_t row0, in
 
 int ecw_ccsd_tupdate(ecw_ctx* c, const double* t1, const double* t2, const double* fsp, const double* fock,
                      int flags, double alpha, double* t1new, double* t2new, void* stream) {
-  return guarded(c, [&] {
+  return guarded_rc(c, [&] {
     require_device();
     c->ptr[S_T1] = const_cast<double*>(t1); c->ptr[S_T2] = const_cast<double*>(t2);
     c->ptr[S_FSP] = const_cast<double*>(fsp); c->ptr[S_FOCK] = const_cast<double*>(fock);
     c->ptr[S_OUT1] = t1new; c->ptr[S_OUT2] = t2new;
-    run_plan(c, get_plan(c, "tupdate", flags), alpha, static_cast<cudaStream_t>(stream));
+    return run_plan(c, get_plan(c, "tupdate", flags), alpha, static_cast<cudaStream_t>(stream));
   });
 }
 
 int ecw_ccsd_lupdate(ecw_ctx* c, const double* t1, const double* t2, const double* l1, const double* l2,
                      const double* fsp, const double* fock, int flags, double alpha, double* l1new, double* l2new,
                      void* stream) {
-  return guarded(c, [&] {
+  return guarded_rc(c, [&] {
     require_device();
     c->ptr[S_T1] = const_cast<double*>(t1); c->ptr[S_T2] = const_cast<double*>(t2);
     c->ptr[S_L1] = const_cast<double*>(l1); c->ptr[S_L2] = const_cast<double*>(l2);
     c->ptr[S_FSP] = const_cast<double*>(fsp); c->ptr[S_FOCK] = const_cast<double*>(fock);
     c->ptr[S_OUT1] = l1new; c->ptr[S_OUT2] = l2new;
-    run_plan(c, get_plan(c, "lupdate", flags), alpha, static_cast<cudaStream_t>(stream));
+    return run_plan(c, get_plan(c, "lupdate", flags), alpha, static_cast<cudaStream_t>(stream));
   });
 }
 
 int ecw_ccsd_gamma(ecw_ctx* c, const double* t1, const double* t2, const double* l1, const double* l2, double* rdm1,
                    void* stream) {
-  return guarded(c, [&] {
+  return guarded_rc(c, [&] {
     require_device();
     c->ptr[S_T1] = const_cast<double*>(t1); c->ptr[S_T2] = const_cast<double*>(t2);
     c->ptr[S_L1] = const_cast<double*>(l1); c->ptr[S_L2] = const_cast<double*>(l2);
     c->ptr[S_RDM1] = rdm1;
-    run_plan(c, get_plan(c, "gamma", 0), 0.0, static_cast<cudaStream_t>(stream));
+    return run_plan(c, get_plan(c, "gamma", 0), 0.0, static_cast<cudaStream_t>(stream));
   });
 }
 
 int ecw_ccsd_energy(ecw_ctx* c, const double* t1, const double* t2, const double* fsp, double* e_out, void* stream) {
-  return guarded(c, [&] {
+  return guarded_rc(c, [&] {
     require_device();
     c->ptr[S_T1] = const_cast<double*>(t1); c->ptr[S_T2] = const_cast<double*>(t2);
     c->ptr[S_FSP] = const_cast<double*>(fsp);
     if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    run_plan(c, get_plan(c, "energy", 0), 0.0, st);
-    ck(cudaMemcpyAsync(e_out, c->ptr[S_SCAL], sizeof(double), cudaMemcpyDeviceToDevice, st), "copy energy");
+    c->copy_scal_to = e_out;
+    return run_plan(c, get_plan(c, "energy", 0), 0.0, static_cast<cudaStream_t>(stream));
   });
 }
 
@@ -422,7 +498,7 @@ int64_t ecw_profile_dump(ecw_ctx* c, char* buf, int64_t buflen) {
     if (!c->last_plan || c->ev.empty()) throw Fail("no profiled run");
     ck(cudaEventSynchronize(c->ev.back()), "cudaEventSynchronize");
     static const char* kn[] = {"gemm", "reduce", "permute", "fill", "tau", "pack", "unpack", "finish",
-                               "dot", "scale_dev", "diag_add", "rdm1", "ewise"};
+                               "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather"};
     std::ostringstream o;
     o << "[";
     for (size_t i = 0; i < c->last_plan->ops.size(); ++i) {

@@ -16,6 +16,8 @@
 //   * ring terms run in the particle-hole layout X[(ia),(jb)].
 #include "ccsd_plan.h"
 
+#include <algorithm>
+
 namespace ecw {
 
 namespace {
@@ -25,7 +27,10 @@ struct Slots {
   Tensor t1, t2, l1, l2, fsp, fock, out1, out2, rdm1;
   Tensor foo, fov, fvo, fvv;
   Tensor oooo, ooov, oovv, oovv_ph, ovov_ph, ovvv, oooo_p, oovv_p, ovvv_p, ovvv_p2, vvvv_p;
+  int rank, world;
+  int64_t nshmax, n0, nsh;   // this rank's rows [n0, n0+nsh) of vvvv_p (packed virtual pair index)
   explicit Slots(const Sizes& z) {
+    rank = z.rank; world = z.world;
     o = z.nocc; v = z.nvir; n = o + v; po = npair(o); pv = npair(v);
     t1 = make_tensor(S_T1, 0, {o, v});
     t2 = make_tensor(S_T2, 0, {o, o, v, v});
@@ -50,7 +55,10 @@ struct Slots {
     oovv_p = make_tensor(S_OOVV_P, 0, {po, pv});
     ovvv_p = make_tensor(S_OVVV_P, 0, {o, v, pv});
     ovvv_p2 = make_tensor(S_OVVV_P, 0, {o * v, pv});
-    vvvv_p = make_tensor(S_VVVV_P, 0, {pv, pv});
+    nshmax = (pv + world - 1) / world;
+    n0 = std::min<int64_t>(pv, (int64_t)rank * nshmax);
+    nsh = std::min<int64_t>(pv, n0 + nshmax) - n0;
+    vvvv_p = make_tensor(S_VVVV_P, 0, {nsh, pv});   // local shard (all of it when world == 1)
   }
 };
 
@@ -72,9 +80,43 @@ void emit_energy(Plan& P, const Slots& s, const Tensor& fov_dense, int k) {
   P.release(G);
 }
 
+// acc[rows, ab_p] = X[rows, cd_p] . vvvv_p[ab_p, cd_p]^T + beta * acc   (particle-particle ladder).
+// With world > 1 every rank multiplies by its row shard of vvvv_p (columns [n0, n0+nsh) of the result);
+// the column blocks are all-gathered and assembled.  CCSD.py:305 (K1) and :470 (K2).
+void ladder_dist(Plan& P, const Slots& s, const Tensor& X, const Tensor& acc, double beta, const char* note) {
+  if (s.world == 1) {
+    P.contract(1.0, X, "if", s.vvvv_p, "af", beta, acc, "ia", note);
+    return;
+  }
+  const int64_t rows = X.dim[0];
+  Tensor accL = P.tmp({rows, s.nshmax});
+  Tensor G = P.tmp({(int64_t)s.world, rows, s.nshmax});
+  if (s.nsh > 0) {
+    Tensor accv = accL;
+    accv.dim[1] = s.nsh;
+    P.contract(1.0, X, "if", s.vvvv_p, "af", 0.0, accv, "ia", note);
+  }
+  P.allgather(accL, rows * s.nshmax, G, note);
+  for (int r = 0; r < s.world; ++r) {
+    const int64_t c0 = std::min<int64_t>(s.pv, (int64_t)r * s.nshmax);
+    const int64_t nc = std::min<int64_t>(s.pv, c0 + s.nshmax) - c0;
+    if (nc <= 0) continue;
+    Tensor src = make_tensor(G.slot, G.off + (int64_t)r * rows * s.nshmax, {rows, nc});
+    src.str[0] = s.nshmax;
+    Tensor dst = acc;
+    dst.off = acc.off + c0;
+    dst.dim[1] = nc;
+    P.permute(1.0, src, "ia", beta, dst, "ia", "ladder shard -> accumulator");
+  }
+  P.release(G);
+  P.release(accL);
+}
+
 }  // namespace
 
 void build_ccsd_energy(Plan& P, const Sizes& z) {
+  P.rank = z.rank;
+  P.world = z.world;
   Slots s(z);
   Tensor f = P.tmp({s.o, s.v});
   P.axpby(1.0, s.fov, 0.0, f);
@@ -83,6 +125,8 @@ void build_ccsd_energy(Plan& P, const Sizes& z) {
 }
 
 void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
+  P.rank = z.rank;
+  P.world = z.world;
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv;
   const bool shift = !equation && !has_alpha;  // CCSD.py:283-285
@@ -156,21 +200,28 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   Tensor acc_p = P.tmp({po, pv});
   P.contract(1.0, Woo_p, "mi", tau_p, "ma", 0.0, acc_p, "ia", "hh ladder");
   P.release(Woo_p);
-  P.contract(1.0, tau_p, "if", s.vvvv_p, "af", 1.0, acc_p, "ia", "K1 pp ladder");
-  Tensor Y_p = P.tmp({po, o * v});
-  P.contract(-2.0, tau_p, "if", s.ovvv_p2, "qf", 0.0, Y_p, "iq", "R9 Y[ijma]");
-  P.release(tau_p);
+  ladder_dist(P, s, tau_p, acc_p, 1.0, "K1 pp ladder");
   Tensor Z = P.tmp({po, v, v});
-  P.contract(1.0, reshape(Y_p, {po, o, v}), "pma", t1, "mb", 0.0, Z, "pab");
-  P.release(Y_p);
+  if (P.world == 1) {
+    Tensor Y_p = P.tmp({po, o * v});
+    P.contract(-2.0, tau_p, "if", s.ovvv_p2, "qf", 0.0, Y_p, "iq", "R9 Y[ijma]");
+    P.contract(1.0, reshape(Y_p, {po, o, v}), "pma", t1, "mb", 0.0, Z, "pab");
+    P.release(Y_p);
+  } else {
+    Tensor YT = P.tmp_lead_padded({o, v, po});      // Y[ij,m,a] stored [m,a,ij], distributed over m
+    P.contract_lead_dist(-2.0, s.ovvv_p, "maf", tau_p, "if", YT, "mai", "R9 Y[ijma]");
+    P.contract(1.0, YT, "map", t1, "mb", 0.0, Z, "pab");
+    P.release(YT);
+  }
+  P.release(tau_p);
   P.pack(-0.5, reshape(Z, {po, 1, v, v}), 2 | 4, 1.0, acc_p);
   P.release(Z);
   P.unpack(1.0, acc_p, 3, 1.0, r2);
   P.release(acc_p);
 
   // ring, CCSD.py:306-310 with Wovvo (CCSD.py:404-413) as W'[(me),(jb)]
-  Tensor Wph = P.tmp({o, v, o, v});
-  P.contract(0.5, s.oovv_ph, "menf", t2ph, "nfjb", 0.0, Wph, "mejb", "R1 Wovvo");
+  Tensor Wph = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(0.5, s.oovv_ph, "menf", t2ph, "nfjb", Wph, "mejb", "R1 Wovvo");
   P.contract(1.0, s.ovvv, "mbef", t1, "jf", 1.0, Wph, "mejb");
   P.contract(1.0, t1, "nb", s.ooov, "mnje", 1.0, Wph, "mejb");
   Tensor U = P.tmp({o, o, v, o});
@@ -178,8 +229,8 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(-1.0, t1, "nb", U, "mnej", 1.0, Wph, "mejb");
   P.release(U);
   P.axpby(-1.0, s.ovov_ph, 1.0, Wph);
-  Tensor ring = P.tmp({o, v, o, v});
-  P.contract(1.0, t2ph, "iame", Wph, "mejb", 0.0, ring, "iajb", "R2 ring");
+  Tensor ring = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(1.0, t2ph, "iame", Wph, "mejb", ring, "iajb", "R2 ring");
   P.release(Wph);
   Tensor Q = P.tmp({o, v, o, o});
   P.contract(1.0, s.ovov_ph, "jbme", t1, "ie", 0.0, Q, "jbmi");
@@ -205,6 +256,8 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
 }
 
 void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
+  P.rank = z.rank;
+  P.world = z.world;
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv;
   const bool shift = !equation && !has_alpha;  // CCSD.py:449-456 (Q2)
@@ -237,8 +290,8 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(0.5, s.oovv, "ikbc", tau, "jkbc", 1.0, v2, "ij");
   P.release(tau);
 
-  Tensor v4ph = P.tmp({o, v, o, v});   // [(kc),(jb)] = v4[j,c,b,k]
-  P.contract(1.0, t2ph, "kcld", s.oovv_ph, "ldjb", 0.0, v4ph, "kcjb", "R3 v4");
+  Tensor v4ph = P.tmp_lead_padded({o, v, o, v});   // [(kc),(jb)] = v4[j,c,b,k]
+  P.contract_lead_dist(1.0, t2ph, "kcld", s.oovv_ph, "ldjb", v4ph, "kcjb", "R3 v4");
   P.axpby(-1.0, s.ovov_ph, 1.0, v4ph);
 
   Tensor v5T = P.tmp({o, v});          // v5T[j,b] = v5[b,j]
@@ -278,11 +331,11 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(-1.0, t1, "lc", s.ooov, "ljkb", 1.0, wph, "kcjb");
   P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
 
-  Tensor wo_p = P.tmp({o * v, po});
-  P.contract(0.5, s.ovvv_p2, "qf", tau_p, "kf", 0.0, wo_p, "qk", "R4 wovoo");
+  Tensor wo_p = P.tmp_lead_padded({o, v, po});
+  P.contract_lead_dist(0.5, s.ovvv_p, "icf", tau_p, "kf", wo_p, "ick", "R4 wovoo");
   P.release(tau_p);
   Tensor wovoo = P.tmp({o, v, o, o});
-  P.unpack(1.0, wo_p, 2, 0.0, wovoo);
+  P.unpack(1.0, reshape(wo_p, {o * v, po}), 2, 0.0, wovoo);
   P.release(wo_p);
   P.permute(0.5, s.ooov, "jkic", 1.0, wovoo, "icjk");
   P.contract(1.0, v4ph, "kcib", t1, "jb", 1.0, wovoo, "icjk");
@@ -300,9 +353,16 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   Tensor a_p = P.tmp({po, o * v});
   P.pack(1.0, reshape(a_full, {o, o, o * v, 1}), 1, 0.0, a_p);
   P.release(a_full);
-  P.contract(1.0, a_p, "pq", s.ovvv_p2, "qa", 1.0, m3_p, "pa", "R6 ovvv.(l2 t1)");
+  if (P.world == 1) {
+    P.contract(1.0, a_p, "pq", s.ovvv_p2, "qa", 1.0, m3_p, "pa", "R6 ovvv.(l2 t1)");
+  } else {
+    Tensor r6 = P.tmp_lead_padded({po, pv});
+    P.contract_lead_dist(1.0, a_p, "pq", s.ovvv_p2, "qa", r6, "pa", "R6 ovvv.(l2 t1)");
+    P.axpby(1.0, r6, 1.0, m3_p);
+    P.release(r6);
+  }
   P.release(a_p);
-  P.contract(1.0, l2_p, "if", s.vvvv_p, "af", 1.0, m3_p, "ia", "K2 pp ladder");
+  ladder_dist(P, s, l2_p, m3_p, 1.0, "K2 pp ladder");
   P.release(l2_p);
   Tensor m3 = P.tmp({o, o, v, v});
   P.unpack(1.0, m3_p, 3, 0.0, m3);
@@ -326,8 +386,8 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   // ---- L2 residual, CCSD.py:472-488
   P.axpby(1.0, s.oovv, 0.0, r2);
   P.axpby(1.0, m3, 1.0, r2);
-  Tensor ring = P.tmp({o, v, o, v});
-  P.contract(1.0, l2ph, "iakc", wph, "kcjb", 0.0, ring, "iajb", "R7 ring");
+  Tensor ring = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(1.0, l2ph, "iakc", wph, "kcjb", ring, "iajb", "R7 ring");
   P.release(wph);
   P.contract(1.0, l1, "ia", Fov, "jb", 1.0, ring, "iajb");
   Tensor y = P.tmp({o, o, v, v});
@@ -362,8 +422,8 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(-0.25, lt, "ikjl", s.ooov, "jlka", 1.0, r1, "ia", "wvvvo: ooov.tau");
   P.release(lt);
   P.contract(-0.5, l2, "ikbc", s.ovvv, "kabc", 1.0, r1, "ia", "wvvvo: ovvv");
-  Tensor Xph = P.tmp({o, v, o, v});
-  P.contract(1.0, l2ph, "ibjc", t2ph, "jckd", 0.0, Xph, "ibkd", "R8 l2.t2");
+  Tensor Xph = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(1.0, l2ph, "ibjc", t2ph, "jckd", Xph, "ibkd", "R8 l2.t2");
   P.contract(1.0, Xph, "ibkd", s.ovvv, "kbda", 1.0, r1, "ia", "wvvvo: ovvv.t2 (K4 refactored)");
   P.release(Xph);
   P.contract(1.0, m3, "ijab", t1, "jb", 1.0, r1, "ia");
@@ -408,6 +468,8 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
 // rows of the ladders stay dense.  Spec: oracle/refactored_np.py *_general.
 // ======================================================================
 void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equation) {
+  P.rank = z.rank;
+  P.world = z.world;
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv, oo = o * o, vv = v * v;
   const bool shift = !equation && !has_alpha;
@@ -486,13 +548,20 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.release(tau_r);
   // particle-particle ladder + t1.ovvv part of Wvvvv: [(ij), ab_p]
   Tensor acc_q = P.tmp({oo, pv});
-  P.contract(1.0, tau_q, "if", s.vvvv_p, "af", 0.0, acc_q, "ia", "K1 pp ladder (general)");
-  Tensor Y_q = P.tmp({oo, o * v});
-  P.contract(-2.0, tau_q, "if", s.ovvv_p2, "qf", 0.0, Y_q, "iq", "R9 Y[ijma]");
-  P.release(tau_q);
+  ladder_dist(P, s, tau_q, acc_q, 0.0, "K1 pp ladder (general)");
   Tensor Z = P.tmp({oo, v, v});
-  P.contract(1.0, reshape(Y_q, {oo, o, v}), "pma", t1, "mb", 0.0, Z, "pab");
-  P.release(Y_q);
+  if (P.world == 1) {
+    Tensor Y_q = P.tmp({oo, o * v});
+    P.contract(-2.0, tau_q, "if", s.ovvv_p2, "qf", 0.0, Y_q, "iq", "R9 Y[ijma]");
+    P.contract(1.0, reshape(Y_q, {oo, o, v}), "pma", t1, "mb", 0.0, Z, "pab");
+    P.release(Y_q);
+  } else {
+    Tensor YT = P.tmp_lead_padded({o, v, oo});
+    P.contract_lead_dist(-2.0, s.ovvv_p, "maf", tau_q, "if", YT, "mai", "R9 Y[ijma]");
+    P.contract(1.0, YT, "map", t1, "mb", 0.0, Z, "pab");
+    P.release(YT);
+  }
+  P.release(tau_q);
   P.pack(-0.5, reshape(Z, {oo, 1, v, v}), 2 | 4, 1.0, acc_q);
   P.release(Z);
   P.unpack(1.0, acc_q, 2, 1.0, r2);
@@ -501,8 +570,8 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   // ring; t2ph2[(nf),(jb)] = t2[j,n,f,b]
   Tensor t2ph2 = P.tmp({o, v, o, v});
   P.permute(1.0, t2, "jnfb", 0.0, t2ph2, "nfjb", "t2 ph2 layout");
-  Tensor Wph = P.tmp({o, v, o, v});
-  P.contract(-0.5, s.oovv_ph, "menf", t2ph2, "nfjb", 0.0, Wph, "mejb", "R1 Wovvo");
+  Tensor Wph = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(-0.5, s.oovv_ph, "menf", t2ph2, "nfjb", Wph, "mejb", "R1 Wovvo");
   P.release(t2ph2);
   P.contract(1.0, s.ovvv, "mbef", t1, "jf", 1.0, Wph, "mejb");
   P.contract(1.0, t1, "nb", s.ooov, "mnje", 1.0, Wph, "mejb");
@@ -511,8 +580,8 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(-1.0, t1, "nb", U, "mnej", 1.0, Wph, "mejb");
   P.release(U);
   P.axpby(-1.0, s.ovov_ph, 1.0, Wph);
-  Tensor ring = P.tmp({o, v, o, v});
-  P.contract(1.0, t2ph, "iame", Wph, "mejb", 0.0, ring, "iajb", "R2 ring");
+  Tensor ring = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(1.0, t2ph, "iame", Wph, "mejb", ring, "iajb", "R2 ring");
   P.release(Wph);
   Tensor Q = P.tmp({o, v, o, o});
   P.contract(1.0, s.ovov_ph, "jbme", t1, "ie", 0.0, Q, "jbmi");
@@ -538,6 +607,8 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
 }
 
 void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equation) {
+  P.rank = z.rank;
+  P.world = z.world;
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv, oo = o * o, vv = v * v;
   const bool shift = !equation && !has_alpha;
@@ -570,8 +641,8 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(1.0, l2, "ijcd", tau, "klcd", 0.0, lt, "ijkl", "l2.tau (dense)");
   P.release(tau);
 
-  Tensor v4ph = P.tmp({o, v, o, v});
-  P.contract(1.0, t2ph, "kcld", s.oovv_ph, "ldjb", 0.0, v4ph, "kcjb", "R3 v4");
+  Tensor v4ph = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(1.0, t2ph, "kcld", s.oovv_ph, "ldjb", v4ph, "kcjb", "R3 v4");
   P.axpby(-1.0, s.ovov_ph, 1.0, v4ph);
 
   Tensor v5T = P.tmp({o, v});
@@ -609,8 +680,14 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(-1.0, t1, "lc", s.ooov, "ljkb", 1.0, wph, "kcjb");
   P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
 
-  Tensor wovoo = P.tmp({o, v, o, o});
-  P.contract(0.5, s.ovvv_p2, "qf", tau_q, "kf", 0.0, reshape(wovoo, {o * v, oo}), "qk", "R4 wovoo");
+  Tensor wovoo = P.tmp_lead_padded({o, v, o, o});
+  {
+    Tensor w3d = wovoo;           // [i, c, (jk)]
+    w3d.nd = 3;
+    w3d.dim[2] = oo;
+    w3d.str[2] = 1;
+    P.contract_lead_dist(0.5, s.ovvv_p, "icf", tau_q, "kf", w3d, "ick", "R4 wovoo");
+  }
   P.release(tau_q);
   P.permute(0.5, s.ooov, "jkic", 1.0, wovoo, "icjk");
   P.contract(1.0, v4ph, "kcib", t1, "jb", 1.0, wovoo, "icjk");
@@ -633,9 +710,16 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   Tensor a_q = P.tmp({o, o, o, v});
   P.permute(1.0, l2t1, "ijck", 0.0, a_q, "ijkc");
   P.release(l2t1);
-  P.contract(1.0, reshape(a_q, {oo, o * v}), "pq", s.ovvv_p2, "qa", 1.0, acc_q, "pa", "R6 ovvv.(l2 t1)");
+  if (P.world == 1) {
+    P.contract(1.0, reshape(a_q, {oo, o * v}), "pq", s.ovvv_p2, "qa", 1.0, acc_q, "pa", "R6 ovvv.(l2 t1)");
+  } else {
+    Tensor r6 = P.tmp_lead_padded({oo, pv});
+    P.contract_lead_dist(1.0, reshape(a_q, {oo, o * v}), "pq", s.ovvv_p2, "qa", r6, "pa", "R6 ovvv.(l2 t1)");
+    P.axpby(1.0, r6, 1.0, acc_q);
+    P.release(r6);
+  }
   P.release(a_q);
-  P.contract(1.0, l2_q, "if", s.vvvv_p, "af", 1.0, acc_q, "ia", "K2 pp ladder (general)");
+  ladder_dist(P, s, l2_q, acc_q, 1.0, "K2 pp ladder (general)");
   P.release(l2_q);
   P.unpack(1.0, acc_q, 2, 1.0, m3);
   P.release(acc_q);
@@ -660,8 +744,8 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.axpby(1.0, m3, 1.0, r2);
   Tensor l2ph2 = P.tmp({o, v, o, v});      // [(ia),(kc)] = l2[k,i,c,a]
   P.permute(1.0, l2, "kica", 0.0, l2ph2, "iakc", "l2 ph2 layout");
-  Tensor ring = P.tmp({o, v, o, v});
-  P.contract(1.0, l2ph2, "iakc", wph, "kcjb", 0.0, ring, "iajb", "R7 ring");
+  Tensor ring = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(1.0, l2ph2, "iakc", wph, "kcjb", ring, "iajb", "R7 ring");
   P.release(wph);
   P.contract(1.0, l1, "ia", Fov, "jb", 1.0, ring, "iajb");
   Tensor y = P.tmp({o, o, v, v});
@@ -696,8 +780,8 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(-0.5, l2, "ikbc", s.ovvv, "kabc", 1.0, r1, "ia", "wvvvo: ovvv");
   Tensor l2ph = P.tmp({o, v, o, v});
   P.permute(1.0, l2, "ijab", 0.0, l2ph, "iajb", "l2 ph layout");
-  Tensor Xph = P.tmp({o, v, o, v});
-  P.contract(1.0, l2ph, "ibjc", t2ph, "jckd", 0.0, Xph, "ibkd", "R8 l2.t2");
+  Tensor Xph = P.tmp_lead_padded({o, v, o, v});
+  P.contract_lead_dist(1.0, l2ph, "ibjc", t2ph, "jckd", Xph, "ibkd", "R8 l2.t2");
   P.release(l2ph);
   P.contract(1.0, Xph, "ibkd", s.ovvv, "kbda", 1.0, r1, "ia", "wvvvo: ovvv.t2 (K4 refactored)");
   P.release(Xph);
@@ -734,6 +818,8 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
 }
 
 void build_ccsd_gamma(Plan& P, const Sizes& z) {
+  P.rank = z.rank;
+  P.world = z.world;
   Slots s(z);
   const int64_t o = s.o, v = s.v;
   const Tensor &t1 = s.t1, &t2 = s.t2, &l1 = s.l1, &l2 = s.l2;

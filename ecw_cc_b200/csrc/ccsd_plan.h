@@ -6,6 +6,7 @@ namespace ecw {
 
 struct Sizes {
   int64_t nocc = 0, nvir = 0;
+  int rank = 0, world = 1;   // vvvv_p is row-sharded over the packed virtual pair index; heavy GEMMs owner-computes
 };
 
 // mode flags mirror the reference keyword arguments of GCC.tupdate/lupdate

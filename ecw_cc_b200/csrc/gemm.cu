@@ -266,17 +266,20 @@ cudaError_t launch_cfg(const GemmArgs& p, cudaStream_t st) {
 }  // namespace
 
 int gemm_pick_config(int64_t M, int64_t N) {
-  // 0: 128x128 (16 warps)  1: 32x128  2: 128x32  3: 128x8  4: 64x64  5: 128x128 (8 warps, 64x32 warp tiles)
+  // 1: 32x128  2: 128x32  3: 128x8  4: 64x64  8: 128x128 (16 warps, interleaved loads)
+  // 10: 112x128  11: 96x128 (8 warps) — chosen when they cut the padded-row waste of the M dimension
   if (N <= 8) return 3;
   if (M <= 48) return 1;
   if (N <= 48) return 2;
   if (M <= 96 || N <= 96) return 4;
-  // mid-size problems: prefer the tile that wastes less padded work
   auto padded = [](int64_t x, int64_t b) { return (x + b - 1) / b * b; };
   double w128 = (double)padded(M, 128) * padded(N, 128);
   double w64 = (double)padded(M, 64) * padded(N, 64);
   if (w64 * 1.15 < w128) return 4;
-  return 0;
+  double p128 = (double)padded(M, 128), p112 = (double)padded(M, 112), p96 = (double)padded(M, 96);
+  if (p112 * 1.04 < p128 && p112 <= p96) return 10;
+  if (p96 * 1.06 < p128 && p96 < p112) return 11;
+  return 8;
 }
 
 cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
@@ -301,6 +304,8 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
     case 7: return launch_cfg<128, 128, 64, 32, 32, 3, 1>(p, st);
     case 8: return launch_cfg<128, 128, 32, 32, 16, 4, 1>(p, st);
     case 9: return launch_cfg<128, 128, 32, 32, 32, 3, 1>(p, st);
+    case 10: return launch_cfg<112, 128, 56, 32, 16, 4, 1>(p, st);
+    case 11: return launch_cfg<96, 128, 48, 32, 16, 4, 1>(p, st);
     default: return cudaErrorInvalidValue;
   }
 }

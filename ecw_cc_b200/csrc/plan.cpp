@@ -132,6 +132,45 @@ Tensor Plan::tmpv(const std::vector<int64_t>& dims) {
 
 Tensor Plan::tmp(std::initializer_list<int64_t> dims) { return tmpv(std::vector<int64_t>(dims)); }
 
+Tensor Plan::tmp_lead_padded(std::initializer_list<int64_t> dims) {
+  std::vector<int64_t> d(dims);
+  const int64_t lead = d[0];
+  d[0] = lead_chunk(lead) * world;
+  Tensor t = tmpv(d);
+  t.dim[0] = lead;
+  return t;
+}
+
+void Plan::allgather(const Tensor& chunk, int64_t count, const Tensor& full, const char* note) {
+  Op op;
+  op.kind = OP_ALLGATHER;
+  op.a = chunk;
+  op.c = full;
+  op.i0 = count;
+  op.i1 = world;
+  op.i2 = rank;
+  op.note = note;
+  ops.push_back(op);
+}
+
+void Plan::contract_lead_dist(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
+                              const Tensor& C, const char* sc, const char* note) {
+  if (world == 1) {
+    contract(alpha, A, sa, B, sb, 0.0, C, sc, note);
+    return;
+  }
+  if (sa[0] != sc[0]) throw PlanError(std::string("contract_lead_dist: leading labels differ in ") + sa + "->" + sc);
+  const int64_t L = C.dim[0], chunk = lead_chunk(L);
+  const int64_t l0 = std::min<int64_t>(L, rank * chunk), nl = std::min<int64_t>(L, l0 + chunk) - l0;
+  if (nl > 0) contract(alpha, slice0(A, l0, nl), sa, B, sb, 0.0, slice0(C, l0, nl), sc, note);
+  Tensor mine = C;
+  mine.off = C.off + rank * chunk * C.str[0];
+  mine.dim[0] = chunk;
+  Tensor full = C;
+  full.dim[0] = chunk * world;
+  allgather(mine, chunk * C.str[0], full, note);
+}
+
 void Plan::release(const Tensor& t) {
   if (t.slot != S_WS) throw PlanError("release of non-workspace tensor");
   arena.release(t.off);
@@ -611,7 +650,7 @@ static void dump_tensor(std::ostringstream& o, const char* key, const Tensor& t)
 
 std::string Plan::dump_json() const {
   static const char* kn[] = {"gemm", "reduce", "permute", "fill", "tau", "pack", "unpack", "finish",
-                             "dot", "scale_dev", "diag_add", "rdm1", "ewise"};
+                             "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather"};
   std::ostringstream o;
   o.precision(17);
   o << "{\"workspace_elems\":" << arena.peak << ",\"gemm_flops\":" << gemm_flops

@@ -65,6 +65,7 @@ enum OpKind : int {
   OP_DIAG_ADD,    // C[i,i] += alpha * fock[off+i, off+i]
   OP_RDM1,        // assemble the symmetrised rdm1 (CCSD.py:154-160)
   OP_EWISE,       // small CCS element-wise helpers (sub-kind in i0)
+  OP_ALLGATHER,   // collective: every rank contributes `a` (i0 elements); `c` receives world*i0 (host runs it)
 };
 
 struct Op {
@@ -97,11 +98,19 @@ class Plan {
   std::vector<Op> ops;
   Arena arena;
   int sm_count = 148;
+  int rank = 0, world = 1;     // owner-computes distribution of the heavy contractions
   double gemm_flops = 0.0;     // sum of 2MNK over GEMM ops (executed flops)
   double perm_bytes = 0.0;     // bytes moved by engine-inserted permutes
 
   Tensor tmp(std::initializer_list<int64_t> dims);
   Tensor tmpv(const std::vector<int64_t>& dims);
+  // dense temp whose leading extent is padded to a multiple of `world` chunks (for in-place allgather)
+  Tensor tmp_lead_padded(std::initializer_list<int64_t> dims);
+  int64_t lead_chunk(int64_t extent) const { return (extent + world - 1) / world; }
+  // C (leading index distributed) = alpha * A (same leading label) . B ; then allgather of C
+  void contract_lead_dist(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
+                          const Tensor& C, const char* sc, const char* note = "");
+  void allgather(const Tensor& chunk, int64_t count, const Tensor& full, const char* note = "");
   void release(const Tensor& t);
 
   // C[sc] = alpha * sum_K A[sa] B[sb] + beta * C[sc]

@@ -27,14 +27,19 @@ def _torch():
 class DeviceEris(object):
     """Owns the C context, the bound integral layouts and the workspace."""
 
-    def __init__(self, nocc, nvir, device=None):
+    def __init__(self, nocc, nvir, device=None, rank=0, world=1, group=None):
+        """rank/world/group: one process per GPU; `vvvv_p` is then row-sharded over the packed
+        virtual pair index and the heavy contractions are distributed (include/ecw_b200.h)."""
         torch = _torch()
         self.nocc = int(nocc)
         self.nvir = int(nvir)
+        self.rank, self.world, self.group = int(rank), int(world), group
         self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
         self._h = ctypes.c_void_p()
         if lib.ecw_ctx_create(ctypes.byref(self._h), self.nocc, self.nvir) != 0:
             raise EcwError("ecw_ctx_create failed")
+        if self.world > 1 and lib.ecw_ctx_set_shard(self._h, self.rank, self.world) != 0:
+            raise EcwError("ecw_ctx_set_shard failed")
         self.buf = {}
         self._ws = None
         self._scal = torch.zeros(16, dtype=torch.float64, device=self.device)
@@ -84,6 +89,23 @@ class DeviceEris(object):
             self._ws = torch.empty(max(int(need), 256), dtype=torch.uint8, device=self.device)
             self.check(lib.ecw_set_workspace(self._h, self._ws.data_ptr(), self._ws.numel()), "ecw_set_workspace")
 
+    def run(self, rc, what):
+        """Drive a (possibly distributed) call to completion: while the library reports a pending
+        collective, perform it with torch.distributed (NCCL) on the workspace and resume."""
+        torch = _torch()
+        while rc == 1:
+            desc = (ctypes.c_int64 * 6)()
+            if lib.ecw_pending_collective(self._h, desc) != 0:
+                raise EcwError("%s: no pending collective" % what)
+            kind, soff, count, roff, world, rank = [int(x) for x in desc]
+            if kind != 1 or world != self.world:
+                raise EcwError("%s: unexpected collective %r" % (what, list(desc)))
+            import torch.distributed as dist
+            ws = self._ws.view(torch.float64)
+            dist.all_gather_into_tensor(ws[roff: roff + world * count], ws[soff: soff + count], group=self.group)
+            rc = lib.ecw_resume(self._h, self.stream())
+        self.check(rc, what)
+
     def set_fock(self, fock):
         torch = _torch()
         self.fock = np.ascontiguousarray(fock, dtype=np.float64)
@@ -91,12 +113,12 @@ class DeviceEris(object):
 
     # -- constructors ----------------------------------------------------------
     @classmethod
-    def from_geris(cls, eris, device=None):
+    def from_geris(cls, eris, device=None, rank=0, world=1, group=None):
         """Upload a reference-style container (numpy blocks, Eris.py:132-150)."""
         torch = _torch()
         fock = np.asarray(eris.fock)
         nocc = int(eris.nocc)
-        self = cls(nocc, fock.shape[0] - nocc, device)
+        self = cls(nocc, fock.shape[0] - nocc, device)          # packed whole first, sharded below
         self.set_fock(fock)
         for name in ("oooo", "ooov", "oovv", "ovvv"):
             t = torch.from_numpy(np.ascontiguousarray(getattr(eris, name), dtype=np.float64)).to(self.device)
@@ -109,16 +131,29 @@ class DeviceEris(object):
         self.check(lib.ecw_eris_pack_from_dense(self._h, ovov.data_ptr(), vvvv.data_ptr(), self.stream()),
                    "ecw_eris_pack_from_dense")
         torch.cuda.current_stream(self.device).synchronize()
+        if world > 1:
+            self.rank, self.world, self.group = int(rank), int(world), group
+            if lib.ecw_ctx_set_shard(self._h, self.rank, self.world) != 0:
+                raise EcwError("ecw_ctx_set_shard failed")
+            pv = self.nvir * (self.nvir - 1) // 2
+            nshmax = (pv + world - 1) // world
+            n0 = min(pv, rank * nshmax)
+            n1 = min(pv, n0 + nshmax)
+            shard = self.buf["vvvv_p"][n0 * pv: n1 * pv].clone() if n1 > n0 else torch.zeros(
+                1, dtype=torch.float64, device=self.device)
+            self.buf["vvvv_p"] = shard
+            self._bind("vvvv_p", shard)
         for attr in ("mo_occ", "EHF", "orbspin"):
             if hasattr(eris, attr):
                 setattr(self, attr, getattr(eris, attr))
         return self
 
     @classmethod
-    def synthetic(cls, nocc, nvir, device=None, scale=0.01):
-        """Function-defined synthetic integrals generated in place on the device."""
+    def synthetic(cls, nocc, nvir, device=None, scale=0.01, rank=0, world=1, group=None):
+        """Function-defined synthetic integrals generated in place on the device (each rank
+        generates only its own rows of the packed vvvv)."""
         torch = _torch()
-        self = cls(nocc, nvir, device)
+        self = cls(nocc, nvir, device, rank=rank, world=world, group=group)
         for name in _LAYOUTS:
             self._alloc_layout(name)
         self.check(lib.ecw_eris_synthetic(self._h, float(scale), self.stream()), "ecw_eris_synthetic")

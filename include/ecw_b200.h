@@ -13,7 +13,8 @@
  *     unless a parameter says "host";
  *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered,
  *     nothing synchronises the device;
- *   - return value 0 = ok, negative = error (message: ecw_last_error);
+ *   - return value 0 = ok, negative = error (message: ecw_last_error), 1 = collective pending
+ *     (multi-GPU contexts only, see ecw_ctx_set_shard);
  *   - the library never allocates device memory: the caller binds the constant
  *     integral layouts and one workspace (sizes: ecw_slot_elems,
  *     ecw_workspace_bytes);
@@ -45,6 +46,15 @@ int ecw_ctx_create(ecw_ctx** out, int nocc, int nvir);
 void ecw_ctx_destroy(ecw_ctx* ctx);
 const char* ecw_last_error(ecw_ctx* ctx);
 const char* ecw_version(void);
+/* Multi-GPU (one process per GPU): rank r of `world` keeps rows [r*ceil(P_v/world), ...) of "vvvv_p"
+ * (the packed virtual pair index) and computes its share of the heavy contractions.  Calls then
+ * return 1 whenever a collective is due: the host reads it with ecw_pending_collective
+ * (desc = {kind 1=all-gather, send offset, elements per rank, recv offset, world, rank}; offsets
+ * are FP64-element offsets into the workspace), performs it (torch.distributed / NCCL) and calls
+ * ecw_resume until it returns 0. */
+int ecw_ctx_set_shard(ecw_ctx* ctx, int rank, int world);
+int ecw_resume(ecw_ctx* ctx, void* stream);
+int ecw_pending_collective(ecw_ctx* ctx, int64_t* desc6);
 
 /* ---- integral container (consumed type `Eris.geris`, Eris.py:132-154) ---- */
 /* Constant device layouts, by slot name:

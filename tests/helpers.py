@@ -13,9 +13,11 @@ def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name)))
 
 
-def plan_json(lib, o, v, func, flags):
+def plan_json(lib, o, v, func, flags, rank=0, world=1):
     h = ctypes.c_void_p()
     assert lib.ecw_ctx_create(ctypes.byref(h), o, v) == 0
+    if world > 1:
+        assert lib.ecw_ctx_set_shard(h, rank, world) == 0
     try:
         n = 1 << 24
         buf = ctypes.create_string_buffer(n)

@@ -22,7 +22,8 @@ def pair_decode(n):
 
 
 class Interp(object):
-    def __init__(self, plan_json, slots, alpha=0.0):
+    def __init__(self, plan_json, slots, alpha=0.0, allgather=None):
+        self.allgather = allgather      # callable(send ndarray, recv ndarray) for multi-rank plans
         self.plan = json.loads(plan_json) if isinstance(plan_json, str) else plan_json
         self.slots = dict(slots)
         self.alpha = alpha
@@ -96,6 +97,14 @@ class Interp(object):
         if op["beta"] != 0.0:
             res = res + op["beta"] * C
         C[...] = res
+
+    def op_allgather(self, op):
+        ws = self.slots["ws"]
+        count, world = op["i0"], op["i1"]
+        send = ws[op["a"]["off"]: op["a"]["off"] + count]
+        recv = ws[op["c"]["off"]: op["c"]["off"] + world * count]
+        assert self.allgather is not None, "multi-rank plan needs an allgather callable"
+        self.allgather(send, recv)
 
     def op_fill(self, op):
         self.view(op["c"])[...] = op["alpha"]
