@@ -246,9 +246,9 @@ def run_ours(args):
         buf = ctypes.create_string_buffer(1 << 22)
         lib.ecw_profile_dump(de._h, buf, 1 << 22)
         ops = json.loads(buf.value.decode())
-        ladder_ms += [x["ms"] for x in ops if "K1 pp ladder" in x["note"]]
+        ladder_ms += [x["ms"] for x in ops if x["kind"] == "gemm" and "K1 pp ladder" in x["note"]]
     lib.ecw_profile_enable(de._h, 0)
-    ladder = [x for x in ops if "K1 pp ladder" in x["note"]][0]
+    ladder = [x for x in ops if x["kind"] == "gemm" and "K1 pp ladder" in x["note"]][0]
     ladder_flops = 2.0 * ladder["M"] * ladder["N"] * ladder["K"]
     ladder_ms = sum(ladder_ms) / len(ladder_ms)
     t_ms = sum(x["ms"] for x in ops)
@@ -298,7 +298,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_per_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches * args.steps),
-        "roofline": {"bound": "tensor", "kernel": "dgemm_kernel<128,128,..> (packed pp-ladder, CCSD.py:305)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "ecw::dgemm_kernel (FP64 DMMA), launch = packed pp-ladder %dx%dx%d (CCSD.py:305)"
+                               % (ladder["M"], ladder["N"], ladder["K"]),
                      "achieved": ladder_flops / ladder_ms / 1e9, "peak": peak, "unit": "TFLOP/s",
                      "frac": ladder_flops / ladder_ms / 1e9 / peak, "traffic": None,
                      "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run, burst; "
