@@ -8,6 +8,8 @@ every compute call needs a CUDA device and the built library.
 from ._lib import lib, build, LIB_PATH, EcwError  # noqa: F401
 from .eris import DeviceEris  # noqa: F401
 from .CCSD import GCC, gamma_CCSD  # noqa: F401
+from .CCS import Gccs  # noqa: F401
+from .devops import DevOps  # noqa: F401
 from .utilities import subdiff  # noqa: F401
 
-__all__ = ["GCC", "DeviceEris", "subdiff", "gamma_CCSD", "build", "lib", "EcwError"]
+__all__ = ["GCC", "Gccs", "DevOps", "DeviceEris", "subdiff", "gamma_CCSD", "build", "lib", "EcwError"]

@@ -10,6 +10,7 @@ _SRC = ["gemm.cu", "ewise.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp
 ECW_HAS_ALPHA = 1
 ECW_EQUATION = 2
 ECW_ANTISYM = 4
+ECW_SUBDIFF_SINGLES = 8
 
 
 class EcwError(RuntimeError):
@@ -74,6 +75,13 @@ class _Lib(object):
             "ecw_plan_flops": (c_d, [c_p, c_s, c_i]),
             "ecw_plan_launches": (c_l, [c_p, c_s, c_i]),
             "ecw_dgemm": (c_i, [c_i, c_i, c_l, c_l, c_l, c_d, c_p, c_l, c_p, c_l, c_d, c_p, c_l, c_i, c_p]),
+            "ecw_op_contract": (c_i, [c_p, c_d, c_p, c_s, c_p, c_s, c_d, c_p, c_s, c_p]),
+            "ecw_op_axpby": (c_i, [c_p, c_d, c_p, c_s, c_d, c_p, c_s, c_p]),
+            "ecw_op_mul": (c_i, [c_p, c_d, c_p, c_p, c_d, c_p, c_p]),
+            "ecw_op_diag_shift": (c_i, [c_p, c_p, c_d, c_p, c_l, c_p]),
+            "ecw_op_denom": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_p, c_p]),
+            "ecw_op_dot": (c_i, [c_p, c_d, c_p, c_p, c_d, c_p, c_p]),
+            "ecw_op_workspace_needed": (c_l, [c_p]),
             "ecw_profile_enable": (c_i, [c_p, c_i]),
             "ecw_profile_dump": (c_l, [c_p, c_p, c_l]),
         }

@@ -28,6 +28,8 @@ struct ecw_ctx {
   double run_alpha = 0.0;
   int64_t pending[6] = {0, 0, 0, 0, 0, 0};
   double* copy_scal_to = nullptr;
+  Plan op_plan;            // plan of the last primitive op
+  int64_t need_ws = 0;
   std::vector<cudaEvent_t> ev;
   const Plan* last_plan = nullptr;
   ecw_ctx() { for (auto& p : ptr) p = nullptr; }
@@ -156,7 +158,7 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
         int o = (int)op.i0;
         int v = (int)(op.d.dim[0] - o);
         ck(launch_finish(resolve(c, op.a), resolve(c, op.b), resolve(c, op.d), op.d.str[0], resolve(c, op.c), o, v,
-                         (int)op.i1, (int)op.i2, (int)op.i3, alpha_rt, st), "finish");
+                         (int)op.i1, (int)op.i2, (int)op.i3, alpha_rt, op.d0, (int)op.d1, st), "finish");
         break;
       }
       case OP_DOT:
@@ -255,8 +257,21 @@ void require_device() {
 // small CCS element-wise helpers live in ccs_plan.cpp / ccs_exec (none needed yet)
 namespace {
 void exec_ewise(ecw_ctx* c, const Op& op, cudaStream_t st) {
-  (void)c; (void)op; (void)st;
-  throw Fail("ewise op not implemented");
+  // i0 = 0: out = alpha * a * b + beta * out (strided; a and/or b may be absent)
+  Ew2Args e{};
+  e.a = op.a.valid() ? resolve(c, op.a) : nullptr;
+  e.b = op.b.valid() ? resolve(c, op.b) : nullptr;
+  e.out = resolve(c, op.c);
+  e.nd = op.c.nd;
+  for (int d = 0; d < op.c.nd; ++d) {
+    e.dim[d] = op.c.dim[d];
+    e.so[d] = op.c.str[d];
+    e.sa[d] = op.a.valid() ? op.a.str[d] : 0;
+    e.sb[d] = op.b.valid() ? op.b.str[d] : 0;
+  }
+  e.alpha = op.alpha;
+  e.beta = op.beta;
+  ck(launch_ew2(e, st), "ew2");
 }
 }  // namespace
 
@@ -483,6 +498,128 @@ int ecw_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, con
     g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
     g.batch = 1; g.splitk = 1; g.kchunk = K; g.ta = ta; g.tb = tb; g.alpha = alpha; g.beta = beta;
     ck(launch_gemm(g, static_cast<cudaStream_t>(stream), cfg), "dgemm");
+  });
+}
+
+// ---- primitive device ops (the CCS host class and the GCC intermediate getters are sequences of these)
+namespace {
+
+Tensor from_desc(const ecw_tensor* t, int slot) {
+  Tensor r;
+  if (!t || !t->ptr) return r;
+  if (t->nd < 0 || t->nd > MAXD) throw Fail("ecw_tensor: rank out of range");
+  r.slot = slot;
+  r.off = 0;
+  r.nd = t->nd;
+  for (int i = 0; i < t->nd; ++i) { r.dim[i] = t->dim[i]; r.str[i] = t->str[i]; }
+  if (r.nd == 0) { r.nd = 1; r.dim[0] = 1; r.str[0] = 1; }
+  return r;
+}
+
+int run_op_plan(ecw_ctx* c, Plan& P, double alpha_rt, void* stream) {
+  if (P.workspace_elems() * 8 > c->ws_bytes) {
+    c->need_ws = P.workspace_elems() * 8;
+    c->err = "workspace too small for this op (ecw_op_workspace_needed)";
+    return -2;
+  }
+  return run_plan(c, P, alpha_rt, static_cast<cudaStream_t>(stream));
+}
+
+}  // namespace
+
+int64_t ecw_op_workspace_needed(ecw_ctx* c) { return c ? c->need_ws : -1; }
+
+int ecw_op_contract(ecw_ctx* c, double alpha, const ecw_tensor* A, const char* sa, const ecw_tensor* B, const char* sb,
+                    double beta, const ecw_tensor* C, const char* sc, void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    Plan P;
+    c->ptr[S_A0] = (double*)A->ptr; c->ptr[S_A1] = (double*)B->ptr; c->ptr[S_B0] = (double*)C->ptr;
+    P.contract(alpha, from_desc(A, S_A0), sa, from_desc(B, S_A1), sb, beta, from_desc(C, S_B0), sc, "op");
+    c->op_plan = std::move(P);
+    return run_op_plan(c, c->op_plan, 0.0, stream);
+  });
+}
+
+int ecw_op_axpby(ecw_ctx* c, double alpha, const ecw_tensor* A, const char* sa, double beta, const ecw_tensor* C,
+                 const char* sc, void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    Plan P;
+    c->ptr[S_A0] = (double*)A->ptr; c->ptr[S_B0] = (double*)C->ptr;
+    P.permute(alpha, from_desc(A, S_A0), sa, beta, from_desc(C, S_B0), sc, "op");
+    c->op_plan = std::move(P);
+    return run_op_plan(c, c->op_plan, 0.0, stream);
+  });
+}
+
+int ecw_op_mul(ecw_ctx* c, double alpha, const ecw_tensor* A, const ecw_tensor* B, double beta, const ecw_tensor* C,
+               void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    Plan P;
+    Tensor a = from_desc(A, S_A0), b = from_desc(B, S_A1), cc = from_desc(C, S_B0);
+    if (A && A->ptr) c->ptr[S_A0] = (double*)A->ptr;
+    if (B && B->ptr) c->ptr[S_A1] = (double*)B->ptr;
+    c->ptr[S_B0] = (double*)C->ptr;
+    for (const Tensor* t : {&a, &b})
+      if (t->valid()) {
+        if (t->nd != cc.nd) throw Fail("ecw_op_mul: rank mismatch");
+        for (int i = 0; i < cc.nd; ++i) if (t->dim[i] != cc.dim[i]) throw Fail("ecw_op_mul: shape mismatch");
+      }
+    P.ewise(0, a, b, cc, alpha, beta);
+    c->op_plan = std::move(P);
+    return run_op_plan(c, c->op_plan, 0.0, stream);
+  });
+}
+
+int ecw_op_diag_shift(ecw_ctx* c, const ecw_tensor* Cm, double alpha, const ecw_tensor* fock, int64_t offset,
+                      void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    Plan P;
+    c->ptr[S_B0] = (double*)Cm->ptr; c->ptr[S_FOCK] = (double*)fock->ptr;
+    P.diag_add(from_desc(Cm, S_B0), alpha, from_desc(fock, S_FOCK), offset);
+    c->op_plan = std::move(P);
+    return run_op_plan(c, c->op_plan, 0.0, stream);
+  });
+}
+
+int ecw_op_denom(ecw_ctx* c, const ecw_tensor* resid, const ecw_tensor* amp, const ecw_tensor* fock, int nocc,
+                 int mode_flags, double alpha, double shift, const ecw_tensor* out, void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    Plan P;
+    c->ptr[S_A0] = (double*)resid->ptr; c->ptr[S_A1] = (double*)amp->ptr; c->ptr[S_FOCK] = (double*)fock->ptr;
+    c->ptr[S_B0] = (double*)out->ptr;
+    Tensor r = from_desc(resid, S_A0);
+    const int rank = r.nd == 4 ? 4 : 2;
+    P.finish(r, from_desc(amp, S_A1), from_desc(fock, S_FOCK), nocc, rank, (mode_flags & ECW_HAS_ALPHA) ? 1 : 0,
+             (mode_flags & ECW_EQUATION) ? 1 : 0, alpha, from_desc(out, S_B0), shift,
+             (mode_flags & ECW_SUBDIFF_SINGLES) ? 1 : 0);
+    c->op_plan = std::move(P);
+    return run_op_plan(c, c->op_plan, alpha, stream);
+  });
+}
+
+int ecw_op_dot(ecw_ctx* c, double alpha, const ecw_tensor* A, const ecw_tensor* B, double beta, double* out_dev,
+               void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
+    Plan P;
+    c->ptr[S_A0] = (double*)A->ptr; c->ptr[S_A1] = (double*)B->ptr;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (beta != 0.0) ck(cudaMemcpyAsync(c->ptr[S_SCAL] + 1, out_dev, sizeof(double), cudaMemcpyDeviceToDevice, st), "dot in");
+    Tensor a = from_desc(A, S_A0), b = from_desc(B, S_A1);
+    Tensor ad = P.tmpv(std::vector<int64_t>(a.dim, a.dim + a.nd)), bd = P.tmpv(std::vector<int64_t>(b.dim, b.dim + b.nd));
+    P.axpby(1.0, a, 0.0, ad);
+    P.axpby(1.0, b, 0.0, bd);
+    P.dot(alpha, ad, bd, beta, 1);
+    c->op_plan = std::move(P);
+    int rc = run_op_plan(c, c->op_plan, 0.0, stream);
+    if (rc == 0) ck(cudaMemcpyAsync(out_dev, c->ptr[S_SCAL] + 1, sizeof(double), cudaMemcpyDeviceToDevice, st), "dot out");
+    return rc;
   });
 }
 

@@ -92,6 +92,29 @@ __global__ void __launch_bounds__(256) permute_tiled_kernel(PermK p) {
   }
 }
 
+__global__ void __launch_bounds__(EW_THREADS) ew2_kernel(Ew2Args p, int64_t total) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = idx, oa = 0, ob = 0, oo = 0;
+#pragma unroll
+    for (int d = KMAXD - 1; d >= 0; --d) {
+      if (d < p.nd) {
+        int64_t q = rem / p.dim[d];
+        int64_t c = rem - q * p.dim[d];
+        rem = q;
+        oa += c * p.sa[d];
+        ob += c * p.sb[d];
+        oo += c * p.so[d];
+      }
+    }
+    double v = p.alpha;
+    if (p.a) v *= p.a[oa];
+    if (p.b) v *= p.b[ob];
+    if (p.beta != 0.0) v += p.beta * p.out[oo];
+    p.out[oo] = v;
+  }
+}
+
 __global__ void __launch_bounds__(EW_THREADS) fill_kernel(double* c, int64_t n, double v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     c[i] = v;
@@ -233,7 +256,8 @@ subdiff_kernel(const double* __restrict__ e, const double* __restrict__ v, doubl
 
 __global__ void __launch_bounds__(EW_THREADS)
 finish_kernel(const double* r, const double* __restrict__ amp, const double* __restrict__ fock, int64_t ldf,
-              double* out, int o, int v, int rank, int has_alpha, int equation, double alpha) {
+              double* out, int o, int v, int rank, int has_alpha, int equation, double alpha, double shift,
+              int sub_singles) {
   extern __shared__ double eps[];
   const int n = o + v;
   for (int i = threadIdx.x; i < n; i += blockDim.x) eps[i] = fock[(int64_t)i * ldf + i];
@@ -245,17 +269,18 @@ finish_kernel(const double* r, const double* __restrict__ amp, const double* __r
     double d;
     if (rank == 2) {
       int i = (int)(idx / v), a = (int)(idx - (int64_t)i * v);
-      d = eps[i] - eps[o + a];
+      d = shift + (eps[i] - eps[o + a]);
     } else {
       int64_t ij = idx / vv, ab = idx - ij * vv;
       int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
       int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
       d = (eps[i] - eps[o + a]) + (eps[j] - eps[o + b]);
+      if (shift != 0.0) d += shift;
     }
     double e = r[idx], res;
     if (has_alpha) {
       double t = amp[idx];
-      double w = rank == 4 ? subdiff(e, t, alpha) : e;   // L1 only on doubles (Q3)
+      double w = (rank == 4 || sub_singles) ? subdiff(e, t, alpha) : e;   // CCSD: L1 only on doubles (Q3)
       res = equation ? w : (w + t * d) / d;
     } else {
       res = equation ? e : e / d;
@@ -381,6 +406,14 @@ cudaError_t launch_permute(const PermArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_ew2(const Ew2Args& a, cudaStream_t st) {
+  int64_t total = 1;
+  for (int d = 0; d < a.nd; ++d) total *= a.dim[d];
+  if (total <= 0) return cudaSuccess;
+  ew2_kernel<<<grid_for(total, EW_THREADS * 2), EW_THREADS, 0, st>>>(a, total);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fill(double* c, int64_t n, double value, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   fill_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, st>>>(c, n, value);
@@ -427,12 +460,14 @@ cudaError_t launch_unpack(const PackArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_finish(const double* r, const double* amp, const double* fock, int64_t ldf, double* out, int o,
-                          int v, int rank, int has_alpha, int equation, double alpha, cudaStream_t st) {
+                          int v, int rank, int has_alpha, int equation, double alpha, double shift, int sub_singles,
+                          cudaStream_t st) {
   int64_t total = rank == 2 ? (int64_t)o * v : (int64_t)o * o * v * v;
   if (total <= 0) return cudaSuccess;
   size_t sm = sizeof(double) * (size_t)(o + v);
   finish_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, sm, st>>>(r, amp, fock, ldf, out, o, v, rank,
-                                                                        has_alpha, equation, alpha);
+                                                                        has_alpha, equation, alpha, shift,
+                                                                        sub_singles);
   return cudaGetLastError();
 }
 

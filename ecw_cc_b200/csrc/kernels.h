@@ -29,6 +29,16 @@ struct PermArgs {
 cudaError_t launch_permute(const PermArgs& a, cudaStream_t st);
 
 cudaError_t launch_fill(double* c, int64_t n, double value, cudaStream_t st);
+// strided element-wise: out = alpha * a * b + beta * out  (b == nullptr: alpha*a; a == nullptr: fill alpha)
+struct Ew2Args {
+  const double* a;
+  const double* b;
+  double* out;
+  int nd;
+  int64_t dim[KMAXD], sa[KMAXD], sb[KMAXD], so[KMAXD];
+  double alpha, beta;
+};
+cudaError_t launch_ew2(const Ew2Args& a, cudaStream_t st);
 // partial[z][M*N] -> C[m*sr + n*sc] = alpha*sum + beta*C
 cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, double* C, int64_t sr,
                           int64_t sc, double alpha, double beta, cudaStream_t st);
@@ -51,8 +61,11 @@ cudaError_t launch_pack(const PackArgs& a, cudaStream_t st);
 cudaError_t launch_unpack(const PackArgs& a, cudaStream_t st);
 
 // residual -> update (CCSD.py:316-338); fock is the bare n x n Fock matrix
+// shift is added to every denominator (EOM-like updates divide by Em + e_i - e_a, CCS.py:938);
+// sub_singles applies the soft threshold to rank-2 amplitudes too (CCS.py:377, 610)
 cudaError_t launch_finish(const double* r, const double* amp, const double* fock, int64_t ldf, double* out,
-                          int o, int v, int rank, int has_alpha, int equation, double alpha, cudaStream_t st);
+                          int o, int v, int rank, int has_alpha, int equation, double alpha, double shift,
+                          int sub_singles, cudaStream_t st);
 cudaError_t launch_subdiff(const double* e, const double* v, double alpha, double* out, int64_t n, cudaStream_t st);
 cudaError_t launch_dot(const double* a, const double* b, int64_t n, double* partial, int nblocks, double* scal,
                        double alpha, double beta, cudaStream_t st);

@@ -259,7 +259,7 @@ void Plan::unpack(double alpha, const Tensor& a2, int flags, double beta, const 
 }
 
 void Plan::finish(const Tensor& resid, const Tensor& amp, const Tensor& fock, int nocc, int rank,
-                  int has_alpha, int equation, double alpha, const Tensor& out) {
+                  int has_alpha, int equation, double alpha, const Tensor& out, double shift, int sub_singles) {
   Op op;
   op.kind = OP_FINISH;
   op.a = resid;
@@ -271,6 +271,8 @@ void Plan::finish(const Tensor& resid, const Tensor& amp, const Tensor& fock, in
   op.i2 = has_alpha;
   op.i3 = equation;
   op.alpha = alpha;
+  op.d0 = shift;
+  op.d1 = sub_singles;
   ops.push_back(op);
 }
 

@@ -129,7 +129,8 @@ class Plan {
   void pack(double alpha, const Tensor& a4, int flags, double beta, const Tensor& c2);
   void unpack(double alpha, const Tensor& a2, int flags, double beta, const Tensor& c4);
   void finish(const Tensor& resid, const Tensor& amp, const Tensor& fock, int nocc, int rank,
-              int has_alpha, int equation, double alpha, const Tensor& out);
+              int has_alpha, int equation, double alpha, const Tensor& out, double shift = 0.0,
+              int sub_singles = 0);
   void dot(double alpha, const Tensor& A, const Tensor& B, double beta, int k);
   void scale_dev(const Tensor& C, double d0, double d1, int k);
   void diag_add(const Tensor& Cmat, double alpha, const Tensor& fock, int64_t foff);

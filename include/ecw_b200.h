@@ -101,6 +101,42 @@ int ecw_antisym_defect(const double* x, int nocc, int nvir, double* out, void* s
 /* utilities.subdiff(eq,var,alpha) — utilities.py:26-73 (element-wise, any shape). */
 int ecw_subdiff(const double* eq, const double* var, double alpha, double* out, int64_t n, void* stream);
 
+/* ---- primitive device ops ---------------------------------------------------------
+ * The CCS class (CCS.py:197-1518: T1inter/tsupdate/L1inter/lsupdate/R1inter/rsupdate/es_L1inter/
+ * es_lsupdate/R0inter/L0inter/*_fromE/gamma_*) and the GCC intermediate getters (cc_Fvv, cc_Woooo,
+ * cc_Wovvo, Linter, ...) are short sequences of o x v / o^2 v^2 contractions; the host states them
+ * with the same index strings as the reference and each one runs through the contraction engine
+ * (permutes + FP64 tensor-core GEMM).  Tensors are described by pointer, rank, extents and
+ * element strides.  A return value of -2 means the bound workspace is too small:
+ * ecw_op_workspace_needed() gives the bytes, rebind with ecw_set_workspace and retry. */
+typedef struct ecw_tensor {
+  void* ptr;
+  int32_t nd;
+  int64_t dim[6];
+  int64_t str[6];
+} ecw_tensor;
+#define ECW_SUBDIFF_SINGLES 8
+/* C[sc] = alpha * sum_contracted A[sa] B[sb] + beta * C[sc]   (numpy.einsum / pyscf.lib.einsum) */
+int ecw_op_contract(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const char* sa, const ecw_tensor* B,
+                    const char* sb, double beta, const ecw_tensor* C, const char* sc, void* stream);
+/* C[sc] = alpha * A[sa] + beta * C[sc]   (sa a permutation of sc: transposes, block copies, axpy) */
+int ecw_op_axpby(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const char* sa, double beta, const ecw_tensor* C,
+                 const char* sc, void* stream);
+/* C = alpha * A * B + beta * C element-wise (A and/or B may be NULL: scaling / fill) */
+int ecw_op_mul(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const ecw_tensor* B, double beta, const ecw_tensor* C,
+               void* stream);
+/* C[i,i] += alpha * fock[offset+i, offset+i]   (CCS.py:307-308, 529-530, 927-928, 1384-1385) */
+int ecw_op_diag_shift(ecw_ctx* ctx, const ecw_tensor* C, double alpha, const ecw_tensor* fock, int64_t offset,
+                      void* stream);
+/* residual -> update: out = resid / (shift + e_i - e_a), or with ECW_HAS_ALPHA the L1 form
+ * (subdiff(resid, amp, alpha) + amp * d) / d   (CCS.py:349, 377-382, 938; CCSD.py:316-336) */
+int ecw_op_denom(ecw_ctx* ctx, const ecw_tensor* resid, const ecw_tensor* amp, const ecw_tensor* fock, int nocc,
+                 int mode_flags, double alpha, double shift, const ecw_tensor* out, void* stream);
+/* out_dev[0] = beta * out_dev[0] + alpha * <A, B> */
+int ecw_op_dot(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const ecw_tensor* B, double beta, double* out_dev,
+               void* stream);
+int64_t ecw_op_workspace_needed(ecw_ctx* ctx);
+
 /* ---- introspection / test hooks ---------------------------------------------- */
 /* JSON dump of the op list a call would launch (host only, no CUDA). */
 int64_t ecw_plan_dump(ecw_ctx* ctx, const char* func, int mode_flags, char* buf, int64_t buflen);

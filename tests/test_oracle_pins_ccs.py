@@ -1,0 +1,56 @@
+"""Pin the CCS oracle (oracle/ccs_np.py) to reference-generated vectors, and to the live reference
+when it is present."""
+import types
+
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle import synth, ref_loader, ccs_np
+from oracle.make_golden import ccs_calls, ccs_inputs
+
+TOL = 1e-13
+_MOD = types.SimpleNamespace(gamma_CCS=ccs_np.gamma_CCS, gamma_unsym_CCS=ccs_np.gamma_unsym_CCS,
+                             gamma_es_CCS=ccs_np.gamma_es_CCS, gamma_tr_CCS=ccs_np.gamma_tr_CCS)
+
+
+def inputs_from_golden(g):
+    d = {k[3:]: g[k] for k in g if k.startswith("in_")}
+    for k in ("r0", "l0", "Em"):
+        d[k] = float(d[k])
+    return d
+
+
+@pytest.mark.parametrize("name", ["ccs_o4v6.npz", "ccs_o6v9.npz"])
+def test_ccs_oracle_matches_golden(name):
+    g = load_golden(name)
+    o, v = int(g["nocc"]), int(g["nvir"])
+    out = ccs_calls(ccs_np.OracleGccs(synth.SynthEris(o, v)), _MOD, inputs_from_golden(g))
+    assert len(out) > 60
+    for k, val in out.items():
+        assert np.abs(val - g[k]).max() < TOL, k
+
+
+def test_inplace_shift_quirk():
+    """Q6: tsupdate/lsupdate/rsupdate/es_lsupdate shift the passed intermediates in place."""
+    o, v = 4, 6
+    cc = ccs_np.OracleGccs(synth.SynthEris(o, v))
+    d = ccs_inputs(o, v)
+    inter = cc.T1inter(d["ts"], d["fsp"])
+    before = inter[0].copy()
+    cc.tsupdate(d["ts"], inter)
+    assert np.abs(np.diagonal(inter[0] - before) + np.diagonal(cc.fock)[o:]).max() < 1e-14
+    new = cc.rsupdate(d["rs"], 0.3, cc.R1inter(d["ts"], d["fsp"], d["vm"]), 0.7)
+    assert np.all(new[0::2] == 0.0) and np.any(new[1::2] != 0.0)      # Q9 force_alpha
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_ccs_oracle_matches_live_reference():
+    CCS = ref_loader.load("CCS")
+    o, v = 5, 8
+    er = synth.SynthEris(o, v)
+    d = ccs_inputs(o, v)
+    a = ccs_calls(CCS.Gccs(er), CCS, d)
+    b = ccs_calls(ccs_np.OracleGccs(er), _MOD, d)
+    for k in a:
+        assert np.abs(a[k] - b[k]).max() < TOL, k
