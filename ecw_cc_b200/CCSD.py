@@ -178,6 +178,188 @@ class GCC(object):
             return o1, o2
         return self._to_host(o1, o2)
 
+    # -- intermediates of the reference API (CCSD.py:207-208, 346-413, 543-623) ------------------
+    # Not used by the fused tupdate/lupdate plans (which never form Wvvvv / wvvvo); provided so
+    # that every public GCC method exists.  numpy in -> numpy out, arithmetic on the device
+    # through the primitive ops (same index strings as the reference, canonical integral blocks).
+    def _dev_ops(self):
+        if getattr(self, "_ops", None) is None:
+            from .devops import DevOps
+            o, v = self.nocc, self.nvir
+            b = self.eris.buf
+            self._ops = DevOps(self.eris)
+            self._oooo = b["oooo"][: o ** 4].view(o, o, o, o)
+            self._ooov = b["ooov"][: o * o * o * v].view(o, o, o, v)
+            self._oovv = b["oovv"][: o * o * v * v].view(o, o, v, v)
+            self._ovvv = b["ovvv"][: o * v ** 3].view(o, v, v, v)
+            self._ovov_ph = b["ovov_ph"][: o * v * o * v].view(o, v, o, v)
+        return self._ops
+
+    def _fblocks(self, fsp):
+        ops = self._dev_ops()
+        o = self.nocc
+        F = self.eris.fock_dev if fsp is None else ops.to_dev(fsp)
+        return F[:o, :o], F[:o, o:], F[o:, :o], F[o:, o:]
+
+    def _tau_dev(self, t2, t1a, t1b, fac=1.):
+        ops = self._dev_ops()
+        x = ops.contract('ia,jb->ijab', t1a, t1b, alpha=0.5 * fac)          # CCSD.py:348
+        y = ops.copy(x)
+        ops.axpby(-1.0, x, 'jiab', 1.0, y, 'ijab')                          # :349
+        tau = ops.copy(y)
+        ops.axpby(-1.0, y, 'ijba', 1.0, tau, 'ijab')                        # :350
+        ops.add(tau, t2)                                                    # :351
+        return tau
+
+    def make_tau(self, t2, t1a, t1b, fac=1.):
+        ops = self._dev_ops()
+        return ops.to_host(self._tau_dev(ops.to_dev(t2), ops.to_dev(t1a), ops.to_dev(t1b), fac))
+
+    def gamma_inter(self, t1, t2, l1, l2):                                  # CCSD.py:165-182
+        ops = self._dev_ops()
+        t1, t2, l1, l2 = (ops.to_dev(x) for x in (t1, t2, l1, l2))
+        doo = ops.contract('ie,je->ij', l1, t1, alpha=-1.0)
+        ops.contract('imef,jmef->ij', l2, t2, alpha=-0.5, out=doo, beta=1.0)
+        dvv = ops.contract('ma,mb->ab', t1, l1)
+        ops.contract('mnea,mneb->ab', t2, l2, alpha=0.5, out=dvv, beta=1.0)
+        xt1 = ops.contract('mnef,inef->mi', l2, t2, alpha=0.5)
+        xt2 = ops.contract('mnfa,mnfe->ae', t2, l2, alpha=0.5)
+        ops.contract('ma,me->ae', t1, l1, out=xt2, beta=1.0)
+        dvo = ops.contract('imae,me->ai', t2, l1)
+        ops.contract('mi,ma->ai', xt1, t1, alpha=-1.0, out=dvo, beta=1.0)
+        ops.contract('ie,ae->ai', t1, xt2, alpha=-1.0, out=dvo, beta=1.0)
+        ops.add(dvo, t1, 1.0, 'ia->ai')
+        return ops.to_host(doo), ops.to_host(l1), ops.to_host(dvo), ops.to_host(dvv)
+
+    def cc_Fvv(self, t1, t2, fsp):                                          # CCSD.py:355-368
+        ops = self._dev_ops()
+        t1, t2 = ops.to_dev(t1), ops.to_dev(t2)
+        foo, fov, fvo, fvv = self._fblocks(fsp)
+        tt = self._tau_dev(t2, t1, t1, fac=0.5)
+        Fae = ops.copy(fvv)
+        ops.contract('me,ma->ae', fov, t1, alpha=-0.5, out=Fae, beta=1.0)
+        ops.contract('mf,maef->ae', t1, self._ovvv, alpha=-1.0, out=Fae, beta=1.0)     # vovv[amef] = -ovvv[maef]
+        ops.contract('mnaf,mnef->ae', tt, self._oovv, alpha=-0.5, out=Fae, beta=1.0)
+        return ops.to_host(Fae)
+
+    def cc_Foo(self, t1, t2, fsp):                                          # CCSD.py:370-381
+        ops = self._dev_ops()
+        t1, t2 = ops.to_dev(t1), ops.to_dev(t2)
+        foo, fov, fvo, fvv = self._fblocks(fsp)
+        tt = self._tau_dev(t2, t1, t1, fac=0.5)
+        Fmi = ops.copy(foo)
+        ops.contract('me,ie->mi', fov, t1, alpha=0.5, out=Fmi, beta=1.0)
+        ops.contract('ne,mnie->mi', t1, self._ooov, out=Fmi, beta=1.0)
+        ops.contract('inef,mnef->mi', tt, self._oovv, alpha=0.5, out=Fmi, beta=1.0)
+        return ops.to_host(Fmi)
+
+    def cc_Fov(self, t1, t2, fsp):                                          # CCSD.py:383-387
+        ops = self._dev_ops()
+        t1 = ops.to_dev(t1)
+        foo, fov, fvo, fvv = self._fblocks(fsp)
+        Fme = ops.copy(fov)
+        ops.contract('nf,mnef->me', t1, self._oovv, out=Fme, beta=1.0)
+        return ops.to_host(Fme)
+
+    def cc_Woooo(self, t1, t2):                                             # CCSD.py:389-394
+        ops = self._dev_ops()
+        t1, t2 = ops.to_dev(t1), ops.to_dev(t2)
+        tau = self._tau_dev(t2, t1, t1)
+        tmp = ops.contract('je,mnie->mnij', t1, self._ooov)
+        W = ops.copy(self._oooo)
+        ops.add(W, tmp)
+        ops.axpby(-1.0, tmp, 'mnji', 1.0, W, 'mnij')
+        ops.contract('ijef,mnef->mnij', tau, self._oovv, alpha=0.25, out=W, beta=1.0)
+        return ops.to_host(W)
+
+    def _vvvv_dense(self):
+        ops = self._dev_ops()
+        v = self.nvir
+        if self.eris.world != 1:
+            raise EcwError("dense vvvv is not available on a sharded context")
+        pv = v * (v - 1) // 2
+        return ops.unpack(self.eris.buf["vvvv_p"][: pv * pv].view(pv, pv), 3, ops.empty(v, v, v, v))
+
+    def cc_Wvvvv(self, t1, t2):                                             # CCSD.py:396-402 (small sizes only: v^4)
+        ops = self._dev_ops()
+        t1, t2 = ops.to_dev(t1), ops.to_dev(t2)
+        tau = self._tau_dev(t2, t1, t1)
+        tmp = ops.contract('mb,mafe->bafe', t1, self._ovvv)
+        W = self._vvvv_dense()
+        ops.add(W, tmp, -1.0)
+        ops.axpby(1.0, tmp, 'bafe', 1.0, W, 'abfe')
+        ops.contract('mnab,mnef->abef', tau, self._oovv, alpha=0.25, out=W, beta=1.0)
+        return ops.to_host(W)
+
+    def _wovvo_dev(self, t1, t2):
+        ops = self._dev_ops()
+        W = ops.contract('jf,mbef->mbej', t1, self._ovvv)                                   # CCSD.py:408
+        ops.contract('nb,mnje->mbej', t1, self._ooov, out=W, beta=1.0)                      # -(oovo = -ooov)
+        ops.contract('jnfb,mnef->mbej', t2, self._oovv, alpha=-0.5, out=W, beta=1.0)
+        x = ops.contract('jf,mnef->mnej', t1, self._oovv)
+        ops.contract('nb,mnej->mbej', t1, x, alpha=-1.0, out=W, beta=1.0)
+        ops.axpby(-1.0, self._ovov_ph, 'jbme', 1.0, W, 'mbej')                              # ovvo[mbej] = -ovov[mbje]
+        return W
+
+    def cc_Wovvo(self, t1, t2):                                             # CCSD.py:404-413
+        ops = self._dev_ops()
+        return ops.to_host(self._wovvo_dev(ops.to_dev(t1), ops.to_dev(t2)))
+
+    def Linter(self, t1, t2, fsp=None):                                     # CCSD.py:543-623
+        ops = self._dev_ops()
+        t1, t2 = ops.to_dev(t1), ops.to_dev(t2)
+        foo, fov, fvo, fvv = self._fblocks(fsp)
+        tau = ops.contract('ia,jb->ijab', t1, t1, alpha=2.0)
+        ops.add(tau, t2)
+        v1 = ops.copy(fvv)
+        ops.contract('ja,jb->ba', fov, t1, alpha=-1.0, out=v1, beta=1.0)
+        ops.contract('jbac,jc->ba', self._ovvv, t1, alpha=-1.0, out=v1, beta=1.0)
+        ops.contract('jkca,jkbc->ba', self._oovv, tau, alpha=0.5, out=v1, beta=1.0)
+        v2 = ops.copy(foo)
+        ops.contract('ib,jb->ij', fov, t1, out=v2, beta=1.0)
+        ops.contract('kijb,kb->ij', self._ooov, t1, alpha=-1.0, out=v2, beta=1.0)
+        ops.contract('ikbc,jkbc->ij', self._oovv, tau, alpha=0.5, out=v2, beta=1.0)
+        v3 = ops.contract('ijcd,klcd->ijkl', self._oovv, tau)
+        v4 = ops.contract('ljdb,klcd->jcbk', self._oovv, t2)
+        ops.axpby(-1.0, self._ovov_ph, 'kcjb', 1.0, v4, 'jcbk')                             # ovvo[jcbk] = -ovov[jckb]
+        v5 = ops.copy(fvo)
+        ops.contract('kc,jkbc->bj', fov, t2, out=v5, beta=1.0)
+        tmp = ops.copy(fov)
+        ops.contract('kldc,ld->kc', self._oovv, t1, alpha=-1.0, out=tmp, beta=1.0)
+        q = ops.contract('kc,jc->kj', tmp, t1)                                              # 'kc,kb,jc->bj'
+        ops.contract('kb,kj->bj', t1, q, out=v5, beta=1.0)
+        ops.contract('kljc,klbc->bj', self._ooov, t2, alpha=-0.5, out=v5, beta=1.0)
+        ops.contract('kbdc,jkcd->bj', self._ovvv, t2, alpha=0.5, out=v5, beta=1.0)
+        w3 = ops.copy(v5)
+        ops.contract('jcbk,jb->ck', v4, t1, out=w3, beta=1.0)
+        ops.contract('cb,jb->cj', v1, t1, out=w3, beta=1.0)
+        ops.contract('jk,jb->bk', v2, t1, alpha=-1.0, out=w3, beta=1.0)
+        woooo = ops.copy(self._oooo, alpha=0.5)
+        ops.add(woooo, v3, 0.25)
+        ops.contract('jilc,kc->jilk', self._ooov, t1, out=woooo, beta=1.0)
+        wovvo = ops.copy(v4)
+        s1 = ops.contract('ljdb,kd->ljbk', self._oovv, t1)                                  # 'ljdb,lc,kd->jcbk'
+        ops.contract('ljbk,lc->jcbk', s1, t1, alpha=-1.0, out=wovvo, beta=1.0)
+        ops.contract('ljkb,lc->jcbk', self._ooov, t1, alpha=-1.0, out=wovvo, beta=1.0)
+        ops.contract('jcbd,kd->jcbk', self._ovvv, t1, out=wovvo, beta=1.0)
+        wovoo = ops.contract('icdb,jkdb->icjk', self._ovvv, tau, alpha=0.25)
+        ops.axpby(0.5, self._ooov, 'jkic', 1.0, wovoo, 'icjk')
+        ops.contract('icbk,jb->icjk', v4, t1, out=wovoo, beta=1.0)
+        ops.contract('lijb,klcb->icjk', self._ooov, t2, alpha=-1.0, out=wovoo, beta=1.0)
+        wvvvo = ops.contract('jcak,jb->bcak', v4, t1)
+        ops.contract('jlka,jlbc->bcak', self._ooov, tau, alpha=0.25, out=wvvvo, beta=1.0)
+        ops.axpby(-0.5, self._ovvv, 'jacb', 1.0, wvvvo, 'bcaj')
+        ops.contract('kbad,jkcd->bcaj', self._ovvv, t2, out=wvvvo, beta=1.0)
+        G = ops.contract('menf,nf->me', self.eris.buf["oovv_ph"][: t1.numel() ** 2].view(*t1.shape, *t1.shape), t1)
+        E = ops.dot(fov, t1) + 0.25 * ops.dot(t2, self._oovv) + 0.5 * ops.dot(t1, G)
+
+        class _IMDS:
+            pass
+        imds = _IMDS()
+        imds.woooo, imds.wovvo, imds.wovoo, imds.wvvvo = (ops.to_host(x) for x in (woooo, wovvo, wovoo, wvvvo))
+        imds.v1, imds.v2, imds.w3, imds.E = ops.to_host(v1), ops.to_host(v2), ops.to_host(w3), E
+        return imds
+
     # -- introspection ---------------------------------------------------------------
     def plan_json(self, func, alpha=None, equation=False, antisym=True):
         import ctypes

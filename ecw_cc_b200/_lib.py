@@ -78,6 +78,7 @@ class _Lib(object):
             "ecw_op_contract": (c_i, [c_p, c_d, c_p, c_s, c_p, c_s, c_d, c_p, c_s, c_p]),
             "ecw_op_axpby": (c_i, [c_p, c_d, c_p, c_s, c_d, c_p, c_s, c_p]),
             "ecw_op_mul": (c_i, [c_p, c_d, c_p, c_p, c_d, c_p, c_p]),
+            "ecw_op_unpack": (c_i, [c_p, c_d, c_p, c_i, c_d, c_p, c_p]),
             "ecw_op_diag_shift": (c_i, [c_p, c_p, c_d, c_p, c_l, c_p]),
             "ecw_op_denom": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_p, c_p]),
             "ecw_op_dot": (c_i, [c_p, c_d, c_p, c_p, c_d, c_p, c_p]),

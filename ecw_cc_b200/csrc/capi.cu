@@ -573,6 +573,18 @@ int ecw_op_mul(ecw_ctx* c, double alpha, const ecw_tensor* A, const ecw_tensor* 
   });
 }
 
+int ecw_op_unpack(ecw_ctx* c, double alpha, const ecw_tensor* A2, int flags, double beta, const ecw_tensor* C4,
+                  void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    Plan P;
+    c->ptr[S_A0] = (double*)A2->ptr; c->ptr[S_B0] = (double*)C4->ptr;
+    P.unpack(alpha, from_desc(A2, S_A0), flags, beta, from_desc(C4, S_B0));
+    c->op_plan = std::move(P);
+    return run_op_plan(c, c->op_plan, 0.0, stream);
+  });
+}
+
 int ecw_op_diag_shift(ecw_ctx* c, const ecw_tensor* Cm, double alpha, const ecw_tensor* fock, int64_t offset,
                       void* stream) {
   return guarded_rc(c, [&] {

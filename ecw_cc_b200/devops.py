@@ -122,6 +122,11 @@ class DevOps(object):
         """C += alpha * A (same shape, any strides)."""
         return self.mul(alpha, A, None, 1.0, C)
 
+    def unpack(self, A2, flags, C4, alpha=1.0, beta=0.0):
+        da, dc = _desc(A2), _desc(C4)
+        self._call(lib.ecw_op_unpack, float(alpha), _ref(da), int(flags), float(beta), _ref(dc))
+        return C4
+
     def diag_shift(self, C, alpha, offset):
         dc, df = _desc(C), _desc(self.e.fock_dev)
         self._call(lib.ecw_op_diag_shift, _ref(dc), float(alpha), _ref(df), int(offset))

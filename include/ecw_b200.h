@@ -125,6 +125,10 @@ int ecw_op_axpby(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const char* sa
 /* C = alpha * A * B + beta * C element-wise (A and/or B may be NULL: scaling / fill) */
 int ecw_op_mul(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const ecw_tensor* B, double beta, const ecw_tensor* C,
                void* stream);
+/* C4[p,q,r,s] = alpha * sign * A2[pair(p,q), pair(r,s)] + beta * C4 — expand antisymmetry-packed pairs
+ * (flags bit0: first pair packed, bit1: second pair packed); used by GCC.cc_Wvvvv at small sizes. */
+int ecw_op_unpack(ecw_ctx* ctx, double alpha, const ecw_tensor* A2, int flags, double beta, const ecw_tensor* C4,
+                  void* stream);
 /* C[i,i] += alpha * fock[offset+i, offset+i]   (CCS.py:307-308, 529-530, 927-928, 1384-1385) */
 int ecw_op_diag_shift(ecw_ctx* ctx, const ecw_tensor* C, double alpha, const ecw_tensor* fock, int64_t offset,
                       void* stream);

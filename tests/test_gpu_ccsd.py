@@ -189,6 +189,29 @@ def test_general_path_unsymmetric_amplitudes(ecw, ov):
     assert np.abs(fast[0] - gen[0]).max() < 1e-13 and np.abs(fast[1] - gen[1]).max() < 1e-13
 
 
+@pytest.mark.parametrize("ov", [(4, 6), (6, 11)])
+def test_gcc_intermediate_getters(ecw, ov):
+    """make_tau, cc_Fvv/Foo/Fov, cc_Woooo/Wvvvv/Wovvo, Linter, gamma_inter (CCSD.py:165-182, 346-413, 543-623)."""
+    from oracle import synth
+    from oracle.ccsd_np import OracleGCC
+    o, v = ov
+    er = synth.SynthEris(o, v)
+    t1, t2, l1, l2 = synth.amplitudes(o, v)
+    fsp = synth.fsp(o, v)
+    orc, cc = OracleGCC(er), ecw.GCC(er)
+    assert np.abs(cc.make_tau(t2, t1, l1, fac=0.5) - orc.make_tau(t2, t1, l1, fac=0.5)).max() < TOL
+    for name in ("cc_Fvv", "cc_Foo", "cc_Fov"):
+        assert np.abs(getattr(cc, name)(t1, t2, fsp) - getattr(orc, name)(t1, t2, fsp)).max() < TOL, name
+    for name in ("cc_Woooo", "cc_Wvvvv", "cc_Wovvo"):
+        assert np.abs(getattr(cc, name)(t1, t2) - getattr(orc, name)(t1, t2)).max() < TOL, name
+    a, b = cc.Linter(t1, t2, fsp=fsp), orc.Linter(t1, t2, fsp=fsp)
+    for name in ("woooo", "wovvo", "wovoo", "wvvvo", "v1", "v2", "w3"):
+        assert np.abs(getattr(a, name) - getattr(b, name)).max() < TOL, name
+    assert abs(a.E - b.E) < TOL
+    for x, y in zip(cc.gamma_inter(t1, t2, l1, l2), orc.gamma_inter(t1, t2, l1, l2)):
+        assert np.abs(x - y).max() < TOL
+
+
 def test_subdiff_kernel(ecw):
     from oracle.ccsd_np import soft_threshold
     rng = np.random.default_rng(3)
