@@ -5,7 +5,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libecw_b200.so")
-_SRC = ["gemm.cu", "ewise.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp", "ccs_plan.cpp"]
+_SRC = ["gemm.cu", "gemm_tma.cu", "ewise.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp", "ccs_plan.cpp"]
 
 ECW_HAS_ALPHA = 1
 ECW_EQUATION = 2

@@ -16,6 +16,8 @@
 // C = alpha * op(A) op(B) + beta * C, row-major C.
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace ecw {
 
 namespace {
@@ -293,6 +295,17 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
   p.vecC = aligned(p.C) && (p.ldc % 2 == 0) && (p.sC % 2 == 0);
   if (p.batch > 65535) return cudaErrorInvalidValue;
   int cfg = force_cfg >= 0 ? force_cfg : gemm_pick_config(p.M, p.N);
+  // large aligned problems: TMA producer + mbarrier ring + DMMA consumers (gemm_tma.cu)
+  static const bool no_tma = getenv("ECW_NO_TMA") != nullptr;
+  if (cfg >= 20 || (force_cfg < 0 && !no_tma && (cfg == 8 || cfg == 10 || cfg == 11))) {
+    if (gemm_tma_eligible(p)) {
+      int tcfg = cfg >= 20 ? cfg : ((cfg != 8 && p.ta == 0) ? 21 : 20);
+      cudaError_t e = launch_gemm_tma(p, st, tcfg);
+      if (e != cudaErrorNotSupported) return e;
+      cudaGetLastError();
+    }
+    if (cfg >= 20) cfg = 8;
+  }
   switch (cfg) {
     case 0: return launch_cfg<128, 128, 32, 32, 16, 4, 0>(p, st);
     case 1: return launch_cfg<32, 128, 16, 32, 16, 4, 0>(p, st);

@@ -17,6 +17,9 @@ struct GemmArgs {
 
 int gemm_pick_config(int64_t M, int64_t N);
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st, int force_cfg = -1);
+// warp-specialised TMA + mbarrier variant (gemm_tma.cu); cfg 20: 128x128, 21: 112x128
+bool gemm_tma_eligible(const GemmArgs& a);
+cudaError_t launch_gemm_tma(const GemmArgs& a, cudaStream_t st, int cfg);
 
 constexpr int KMAXD = 6;
 struct PermArgs {

@@ -23,12 +23,13 @@ def _dev(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 20, 21])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_dgemm_all_layouts(ecw, cfg, ta, tb):
     import torch
     rng = np.random.default_rng(10 * ta + tb + 100)
-    for (M, N, K) in [(1, 1, 1), (7, 5, 3), (33, 17, 129), (130, 131, 67), (256, 128, 64), (45, 300, 1000)]:
+    for (M, N, K) in [(1, 1, 1), (7, 5, 3), (33, 17, 129), (130, 131, 67), (256, 128, 64), (45, 300, 1000),
+                      (300, 258, 520), (112, 128, 48)]:
         A = rng.standard_normal((K, M) if ta else (M, K))
         B = rng.standard_normal((N, K) if tb else (K, N))
         C0 = rng.standard_normal((M, N))
