@@ -80,6 +80,54 @@ void emit_energy(Plan& P, const Slots& s, const Tensor& fov_dense, int k) {
   P.release(G);
 }
 
+// Wph[(me),(jb)] = Wovvo[m,b,e,j] (CCSD.py:404-413) for the rows m in [m0, m0+nm); `t2x`/`c2` give the
+// t2 operand of the o^3v^3 term: (t2ph, +1/2) on the packed path, (t2ph2, -1/2) on the general path.
+void emit_wovvo_rows(Plan& P, const Slots& s, const Tensor& t1, const Tensor& t2x, double c2, const Tensor& Wph,
+                     int64_t m0, int64_t nm) {
+  const int64_t o = s.o, v = s.v;
+  Tensor Wl = slice0(Wph, m0, nm);
+  P.contract(c2, slice0(s.oovv_ph, m0, nm), "menf", t2x, "nfjb", 0.0, Wl, "mejb", "R1 Wovvo");
+  P.contract(1.0, slice0(s.ovvv, m0, nm), "mbef", t1, "jf", 1.0, Wl, "mejb");
+  P.contract(1.0, t1, "nb", slice0(s.ooov, m0, nm), "mnje", 1.0, Wl, "mejb");
+  Tensor U = P.tmp({nm, o, v, o});
+  P.contract(1.0, slice0(s.oovv, m0, nm), "mnef", t1, "jf", 0.0, U, "mnej");
+  P.contract(-1.0, t1, "nb", U, "mnej", 1.0, Wl, "mejb");
+  P.release(U);
+  P.axpby(-1.0, slice0(s.ovov_ph, m0, nm), 1.0, Wl);
+}
+
+// whole Wph, rows distributed over the ranks and all-gathered once
+void emit_wovvo(Plan& P, const Slots& s, const Tensor& t1, const Tensor& t2x, double c2, const Tensor& Wph) {
+  const int64_t L = s.o, chunk = P.lead_chunk(L);
+  const int64_t m0 = std::min<int64_t>(L, (int64_t)P.rank * chunk), nm = std::min<int64_t>(L, m0 + chunk) - m0;
+  if (P.world == 1) {
+    emit_wovvo_rows(P, s, t1, t2x, c2, Wph, 0, L);
+    return;
+  }
+  if (nm > 0) emit_wovvo_rows(P, s, t1, t2x, c2, Wph, m0, nm);
+  Tensor mine = Wph;
+  mine.off = Wph.off + (int64_t)P.rank * chunk * Wph.str[0];
+  mine.dim[0] = chunk;
+  Tensor full = Wph;
+  full.dim[0] = chunk * P.world;
+  P.allgather(mine, chunk * Wph.str[0], full, "Wovvo rows");
+}
+
+// r2[ijab] += x[ijab] - x[jiab] with x[ijab] = -sum_e t1[ie] ovvv[jeab] (CCSD.py:311-312), distributed over j
+void emit_t1_ovvv_term(Plan& P, const Slots& s, const Tensor& t1, const Tensor& x, const Tensor& r2) {
+  if (P.world == 1) {
+    P.contract(-1.0, t1, "ie", s.ovvv, "jeab", 0.0, x, "ijab");
+    P.axpby(1.0, x, 1.0, r2);
+    P.permute(-1.0, x, "jiab", 1.0, r2, "ijab");
+    return;
+  }
+  Tensor xj = P.tmp_lead_padded({s.o, s.o, s.v, s.v});   // xj[j,i,a,b] = x[i,j,a,b]
+  P.contract_lead_dist(-1.0, s.ovvv, "jeab", t1, "ie", xj, "jiab", "t1.ovvv (distributed over j)");
+  P.permute(1.0, xj, "jiab", 1.0, r2, "ijab");
+  P.axpby(-1.0, xj, 1.0, r2);
+  P.release(xj);
+}
+
 // acc[rows, ab_p] = X[rows, cd_p] . vvvv_p[ab_p, cd_p]^T + beta * acc   (particle-particle ladder).
 // With world > 1 every rank multiplies by its row shard of vvvv_p (columns [n0, n0+nsh) of the result);
 // the column blocks are all-gathered and assembled.  CCSD.py:305 (K1) and :470 (K2).
@@ -149,7 +197,7 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   Tensor Fvv = P.tmp({v, v});
   P.axpby(1.0, s.fvv, 0.0, Fvv);
   P.contract(-0.5, s.fov, "me", t1, "ma", 1.0, Fvv, "ae", "cc_Fvv");
-  P.contract(-1.0, s.ovvv, "maef", t1, "mf", 1.0, Fvv, "ae", "cc_Fvv vovv");
+  P.contract_split(-1.0, s.ovvv, "maef", t1, "mf", Fvv, "ae", 'm', "cc_Fvv vovv");
   P.contract(-0.5, ttl, "mnfa", s.oovv, "mnfe", 1.0, Fvv, "ae", "cc_Fvv tau~");
   Tensor Foo = P.tmp({o, o});
   P.axpby(1.0, s.foo, 0.0, Foo);
@@ -168,7 +216,7 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(-1.0, Foo, "mi", t1, "ma", 1.0, r1, "ia");
   P.contract(1.0, t2ph, "iame", Fov, "me", 1.0, r1, "ia");
   P.contract(-1.0, s.ovov_ph, "ianf", t1, "nf", 1.0, r1, "ia");
-  P.contract(-0.5, t2, "imef", s.ovvv, "maef", 1.0, r1, "ia", "T1 ovvv");
+  P.contract_split(-0.5, t2, "imef", s.ovvv, "maef", r1, "ia", 'm', "T1 ovvv");
   P.contract(0.5, t2, "mnea", s.ooov, "mnie", 1.0, r1, "ia");
 
   // T2 residual, CCSD.py:297-314
@@ -221,14 +269,7 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
 
   // ring, CCSD.py:306-310 with Wovvo (CCSD.py:404-413) as W'[(me),(jb)]
   Tensor Wph = P.tmp_lead_padded({o, v, o, v});
-  P.contract_lead_dist(0.5, s.oovv_ph, "menf", t2ph, "nfjb", Wph, "mejb", "R1 Wovvo");
-  P.contract(1.0, s.ovvv, "mbef", t1, "jf", 1.0, Wph, "mejb");
-  P.contract(1.0, t1, "nb", s.ooov, "mnje", 1.0, Wph, "mejb");
-  Tensor U = P.tmp({o, o, v, o});
-  P.contract(1.0, s.oovv, "mnef", t1, "jf", 0.0, U, "mnej");
-  P.contract(-1.0, t1, "nb", U, "mnej", 1.0, Wph, "mejb");
-  P.release(U);
-  P.axpby(-1.0, s.ovov_ph, 1.0, Wph);
+  emit_wovvo(P, s, t1, t2ph, 0.5, Wph);
   Tensor ring = P.tmp_lead_padded({o, v, o, v});
   P.contract_lead_dist(1.0, t2ph, "iame", Wph, "mejb", ring, "iajb", "R2 ring");
   P.release(Wph);
@@ -240,9 +281,7 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.release(ring);
   P.release(t2ph);
 
-  P.contract(-1.0, t1, "ie", s.ovvv, "jeab", 0.0, x, "ijab");
-  P.axpby(1.0, x, 1.0, r2);
-  P.permute(-1.0, x, "jiab", 1.0, r2, "ijab");
+  emit_t1_ovvv_term(P, s, t1, x, r2);
   P.contract(1.0, t1, "ma", s.ooov, "ijmb", 0.0, x, "ijab");
   P.axpby(-1.0, x, 1.0, r2);
   P.permute(1.0, x, "ijba", 1.0, r2, "ijab");
@@ -281,7 +320,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   Tensor v1 = P.tmp({v, v});
   P.axpby(1.0, s.fvv, 0.0, v1);
   P.contract(-1.0, s.fov, "ja", t1, "jb", 1.0, v1, "ba");
-  P.contract(-1.0, s.ovvv, "jbac", t1, "jc", 1.0, v1, "ba", "v1 ovvv");
+  P.contract_split(-1.0, s.ovvv, "jbac", t1, "jc", v1, "ba", 'j', "v1 ovvv");
   P.contract(-0.5, tau, "jkcb", s.oovv, "jkca", 1.0, v1, "ba");
   Tensor v2 = P.tmp({o, o});
   P.axpby(1.0, s.foo, 0.0, v2);
@@ -302,7 +341,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(1.0, q, "kj", t1, "kb", 1.0, v5T, "jb");
   P.release(q);
   P.contract(0.5, s.ooov, "kljc", t2, "klcb", 1.0, v5T, "jb");
-  P.contract(-0.5, t2, "jkdc", s.ovvv, "kbdc", 1.0, v5T, "jb", "v5 ovvv");
+  P.contract_split(-0.5, t2, "jkdc", s.ovvv, "kbdc", v5T, "jb", 'k', "v5 ovvv");
 
   Tensor w3T = P.tmp({o, v});          // w3T[k,c] = w3[c,k]
   P.axpby(1.0, v5T, 0.0, w3T);
@@ -329,7 +368,14 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(1.0, t1, "lc", S, "ljbk", 1.0, wph, "kcjb");
   P.release(S);
   P.contract(-1.0, t1, "lc", s.ooov, "ljkb", 1.0, wph, "kcjb");
-  P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
+  if (P.world == 1) {
+    P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
+  } else {
+    Tensor wj = P.tmp_lead_padded({o, v, v, o});
+    P.contract_lead_dist(1.0, s.ovvv, "jcbd", t1, "kd", wj, "jcbk", "wovvo ovvv.t1 (distributed over j)");
+    P.permute(1.0, wj, "jcbk", 1.0, wph, "kcjb");
+    P.release(wj);
+  }
 
   Tensor wo_p = P.tmp_lead_padded({o, v, po});
   P.contract_lead_dist(0.5, s.ovvv_p, "icf", tau_p, "kf", wo_p, "ick", "R4 wovoo");
@@ -398,7 +444,14 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(1.0, x_vv, "ca", s.oovv, "ijcb", 1.0, y, "ijab");
   P.axpby(-1.0, y, 1.0, r2);
   P.permute(1.0, y, "ijba", 1.0, r2, "ijab");
-  P.contract(1.0, l1, "qc", s.ovvv, "pcrs", 0.0, y, "pqrs");
+  if (P.world == 1) {
+    P.contract(1.0, l1, "qc", s.ovvv, "pcrs", 0.0, y, "pqrs");
+  } else {
+    Tensor yp = P.tmp_lead_padded({o, o, v, v});
+    P.contract_lead_dist(1.0, s.ovvv, "pcrs", l1, "qc", yp, "pqrs", "l1.ovvv (distributed over p)");
+    P.axpby(1.0, yp, 0.0, y);
+    P.release(yp);
+  }
   P.contract(1.0, v2, "qk", l2, "kprs", 1.0, y, "pqrs");
   P.contract(-1.0, x_oo, "pk", s.oovv, "kqrs", 1.0, y, "pqrs");
   P.axpby(1.0, y, 1.0, r2);
@@ -421,10 +474,10 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.release(lt_p);
   P.contract(-0.25, lt, "ikjl", s.ooov, "jlka", 1.0, r1, "ia", "wvvvo: ooov.tau");
   P.release(lt);
-  P.contract(-0.5, l2, "ikbc", s.ovvv, "kabc", 1.0, r1, "ia", "wvvvo: ovvv");
+  P.contract_split(-0.5, l2, "ikbc", s.ovvv, "kabc", r1, "ia", 'k', "wvvvo: ovvv");
   Tensor Xph = P.tmp_lead_padded({o, v, o, v});
   P.contract_lead_dist(1.0, l2ph, "ibjc", t2ph, "jckd", Xph, "ibkd", "R8 l2.t2");
-  P.contract(1.0, Xph, "ibkd", s.ovvv, "kbda", 1.0, r1, "ia", "wvvvo: ovvv.t2 (K4 refactored)");
+  P.contract_split(1.0, Xph, "ibkd", s.ovvv, "kbda", r1, "ia", 'k', "wvvvo: ovvv.t2 (K4 refactored)");
   P.release(Xph);
   P.contract(1.0, m3, "ijab", t1, "jb", 1.0, r1, "ia");
   P.release(m3);
@@ -438,7 +491,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(-1.0, m_oo, "lj", t1, "lb", 1.0, zz, "jb");
   P.contract(1.0, s.oovv_ph, "iajb", zz, "jb", 1.0, r1, "ia");
   P.release(zz);
-  P.contract(-1.0, s.ovvv, "icba", x_vv, "bc", 1.0, r1, "ia", "L1 ovvv.x_vv");
+  P.contract_split(-1.0, s.ovvv, "icba", x_vv, "bc", r1, "ia", 'c', "L1 ovvv.x_vv");
   P.contract(-1.0, s.ooov, "jika", x_oo, "kj", 1.0, r1, "ia");
   P.contract(-1.0, m_oo, "ik", Fov, "ka", 1.0, r1, "ia");
   P.contract(-1.0, m_vv, "ca", Fov, "ic", 1.0, r1, "ia");
@@ -493,7 +546,7 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   Tensor Fvv = P.tmp({v, v});
   P.axpby(1.0, s.fvv, 0.0, Fvv);
   P.contract(-0.5, s.fov, "me", t1, "ma", 1.0, Fvv, "ae", "cc_Fvv");
-  P.contract(-1.0, s.ovvv, "maef", t1, "mf", 1.0, Fvv, "ae", "cc_Fvv vovv");
+  P.contract_split(-1.0, s.ovvv, "maef", t1, "mf", Fvv, "ae", 'm', "cc_Fvv vovv");
   P.contract(0.5, ttl, "mnaf", s.oovv, "mnfe", 1.0, Fvv, "ae", "cc_Fvv tau~");
   Tensor Foo = P.tmp({o, o});
   P.axpby(1.0, s.foo, 0.0, Foo);
@@ -511,7 +564,7 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(-1.0, Foo, "mi", t1, "ma", 1.0, r1, "ia");
   P.contract(1.0, t2ph, "iame", Fov, "me", 1.0, r1, "ia");
   P.contract(-1.0, s.ovov_ph, "ianf", t1, "nf", 1.0, r1, "ia");
-  P.contract(-0.5, t2, "imef", s.ovvv, "maef", 1.0, r1, "ia", "T1 ovvv");
+  P.contract_split(-0.5, t2, "imef", s.ovvv, "maef", r1, "ia", 'm', "T1 ovvv");
   P.contract(-0.5, t2, "mnae", s.ooov, "mnie", 1.0, r1, "ia");
 
   Tensor x = P.tmp({o, o, v, v});
@@ -571,15 +624,8 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   Tensor t2ph2 = P.tmp({o, v, o, v});
   P.permute(1.0, t2, "jnfb", 0.0, t2ph2, "nfjb", "t2 ph2 layout");
   Tensor Wph = P.tmp_lead_padded({o, v, o, v});
-  P.contract_lead_dist(-0.5, s.oovv_ph, "menf", t2ph2, "nfjb", Wph, "mejb", "R1 Wovvo");
+  emit_wovvo(P, s, t1, t2ph2, -0.5, Wph);
   P.release(t2ph2);
-  P.contract(1.0, s.ovvv, "mbef", t1, "jf", 1.0, Wph, "mejb");
-  P.contract(1.0, t1, "nb", s.ooov, "mnje", 1.0, Wph, "mejb");
-  Tensor U = P.tmp({o, o, v, o});
-  P.contract(1.0, s.oovv, "mnef", t1, "jf", 0.0, U, "mnej");
-  P.contract(-1.0, t1, "nb", U, "mnej", 1.0, Wph, "mejb");
-  P.release(U);
-  P.axpby(-1.0, s.ovov_ph, 1.0, Wph);
   Tensor ring = P.tmp_lead_padded({o, v, o, v});
   P.contract_lead_dist(1.0, t2ph, "iame", Wph, "mejb", ring, "iajb", "R2 ring");
   P.release(Wph);
@@ -591,9 +637,7 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.release(ring);
   P.release(t2ph);
 
-  P.contract(-1.0, t1, "ie", s.ovvv, "jeab", 0.0, x, "ijab");
-  P.axpby(1.0, x, 1.0, r2);
-  P.permute(-1.0, x, "jiab", 1.0, r2, "ijab");
+  emit_t1_ovvv_term(P, s, t1, x, r2);
   P.contract(1.0, t1, "ma", s.ooov, "ijmb", 0.0, x, "ijab");
   P.axpby(-1.0, x, 1.0, r2);
   P.permute(1.0, x, "ijba", 1.0, r2, "ijab");
@@ -629,7 +673,7 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   Tensor v1 = P.tmp({v, v});
   P.axpby(1.0, s.fvv, 0.0, v1);
   P.contract(-1.0, s.fov, "ja", t1, "jb", 1.0, v1, "ba");
-  P.contract(-1.0, s.ovvv, "jbac", t1, "jc", 1.0, v1, "ba", "v1 ovvv");
+  P.contract_split(-1.0, s.ovvv, "jbac", t1, "jc", v1, "ba", 'j', "v1 ovvv");
   P.contract(0.5, s.oovv, "jkca", tau, "jkbc", 1.0, v1, "ba");
   Tensor v2 = P.tmp({o, o});
   P.axpby(1.0, s.foo, 0.0, v2);
@@ -653,7 +697,7 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(1.0, q, "kj", t1, "kb", 1.0, v5T, "jb");
   P.release(q);
   P.contract(-0.5, s.ooov, "kljc", t2, "klbc", 1.0, v5T, "jb");
-  P.contract(-0.5, t2, "jkdc", s.ovvv, "kbdc", 1.0, v5T, "jb", "v5 ovvv");
+  P.contract_split(-0.5, t2, "jkdc", s.ovvv, "kbdc", v5T, "jb", 'k', "v5 ovvv");
 
   Tensor w3T = P.tmp({o, v});
   P.axpby(1.0, v5T, 0.0, w3T);
@@ -678,7 +722,14 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(1.0, t1, "lc", S, "ljbk", 1.0, wph, "kcjb");
   P.release(S);
   P.contract(-1.0, t1, "lc", s.ooov, "ljkb", 1.0, wph, "kcjb");
-  P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
+  if (P.world == 1) {
+    P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
+  } else {
+    Tensor wj = P.tmp_lead_padded({o, v, v, o});
+    P.contract_lead_dist(1.0, s.ovvv, "jcbd", t1, "kd", wj, "jcbk", "wovvo ovvv.t1 (distributed over j)");
+    P.permute(1.0, wj, "jcbk", 1.0, wph, "kcjb");
+    P.release(wj);
+  }
 
   Tensor wovoo = P.tmp_lead_padded({o, v, o, o});
   {
@@ -756,7 +807,14 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(1.0, x_vv, "ca", s.oovv, "ijcb", 1.0, y, "ijab");
   P.axpby(-1.0, y, 1.0, r2);
   P.permute(1.0, y, "ijba", 1.0, r2, "ijab");
-  P.contract(1.0, l1, "qc", s.ovvv, "pcrs", 0.0, y, "pqrs");
+  if (P.world == 1) {
+    P.contract(1.0, l1, "qc", s.ovvv, "pcrs", 0.0, y, "pqrs");
+  } else {
+    Tensor yp = P.tmp_lead_padded({o, o, v, v});
+    P.contract_lead_dist(1.0, s.ovvv, "pcrs", l1, "qc", yp, "pqrs", "l1.ovvv (distributed over p)");
+    P.axpby(1.0, yp, 0.0, y);
+    P.release(yp);
+  }
   P.contract(1.0, v2, "qk", l2, "kprs", 1.0, y, "pqrs");
   P.contract(-1.0, x_oo, "pk", s.oovv, "kqrs", 1.0, y, "pqrs");
   P.axpby(1.0, y, 1.0, r2);
@@ -777,13 +835,13 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.release(v4ph);
   P.contract(-0.25, lt, "ikjl", s.ooov, "jlka", 1.0, r1, "ia", "wvvvo: ooov.tau");
   P.release(lt);
-  P.contract(-0.5, l2, "ikbc", s.ovvv, "kabc", 1.0, r1, "ia", "wvvvo: ovvv");
+  P.contract_split(-0.5, l2, "ikbc", s.ovvv, "kabc", r1, "ia", 'k', "wvvvo: ovvv");
   Tensor l2ph = P.tmp({o, v, o, v});
   P.permute(1.0, l2, "ijab", 0.0, l2ph, "iajb", "l2 ph layout");
   Tensor Xph = P.tmp_lead_padded({o, v, o, v});
   P.contract_lead_dist(1.0, l2ph, "ibjc", t2ph, "jckd", Xph, "ibkd", "R8 l2.t2");
   P.release(l2ph);
-  P.contract(1.0, Xph, "ibkd", s.ovvv, "kbda", 1.0, r1, "ia", "wvvvo: ovvv.t2 (K4 refactored)");
+  P.contract_split(1.0, Xph, "ibkd", s.ovvv, "kbda", r1, "ia", 'k', "wvvvo: ovvv.t2 (K4 refactored)");
   P.release(Xph);
   P.contract(1.0, m3, "ijab", t1, "jb", 1.0, r1, "ia");
   P.release(m3);
@@ -797,7 +855,7 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(-1.0, m_oo, "lj", t1, "lb", 1.0, zz, "jb");
   P.contract(1.0, s.oovv_ph, "iajb", zz, "jb", 1.0, r1, "ia");
   P.release(zz);
-  P.contract(-1.0, s.ovvv, "icba", x_vv, "bc", 1.0, r1, "ia", "L1 ovvv.x_vv");
+  P.contract_split(-1.0, s.ovvv, "icba", x_vv, "bc", r1, "ia", 'c', "L1 ovvv.x_vv");
   P.contract(-1.0, s.ooov, "jika", x_oo, "kj", 1.0, r1, "ia");
   P.contract(-1.0, m_oo, "ik", Fov, "ka", 1.0, r1, "ia");
   P.contract(-1.0, m_vv, "ca", Fov, "ic", 1.0, r1, "ia");

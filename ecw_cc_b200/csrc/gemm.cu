@@ -111,7 +111,7 @@ struct SmemLayout {
 };
 
 template <int BM, int BN, int WM, int WN, int BK, int TA, int TB, int STAGES, int ILV>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1)
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 128 * 48) ? 2 : 1)
 dgemm_kernel(GemmArgs p) {
   constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
   constexpr int MI = WM / 8, NI = WN / 8;
@@ -270,9 +270,12 @@ cudaError_t launch_cfg(const GemmArgs& p, cudaStream_t st) {
 int gemm_pick_config(int64_t M, int64_t N) {
   // 1: 32x128  2: 128x32  3: 128x8  4: 64x64  8: 128x128 (16 warps, interleaved loads)
   // 10: 112x128  11: 96x128 (8 warps) — chosen when they cut the padded-row waste of the M dimension
+  // 12: 48x128  13: 128x48 — one tile covers a whole occupied index of up to 48 (no operand re-read)
   if (N <= 8) return 3;
-  if (M <= 48) return 1;
-  if (N <= 48) return 2;
+  if (M <= 32) return 1;
+  if (M <= 48) return 12;
+  if (N <= 32) return 2;
+  if (N <= 48) return 13;
   if (M <= 96 || N <= 96) return 4;
   auto padded = [](int64_t x, int64_t b) { return (x + b - 1) / b * b; };
   double w128 = (double)padded(M, 128) * padded(N, 128);
@@ -318,6 +321,8 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
     case 8: return launch_cfg<128, 128, 32, 32, 16, 4, 1>(p, st);
     case 9: return launch_cfg<128, 128, 32, 32, 32, 3, 1>(p, st);
     case 10: return launch_cfg<112, 128, 56, 32, 16, 4, 1>(p, st);
+    case 12: return launch_cfg<48, 128, 48, 16, 16, 4, 1>(p, st);
+    case 13: return launch_cfg<128, 48, 32, 24, 16, 4, 1>(p, st);
     case 11: return launch_cfg<96, 128, 48, 32, 16, 4, 1>(p, st);
     default: return cudaErrorInvalidValue;
   }

@@ -74,6 +74,13 @@ Tensor slice0(const Tensor& t, int64_t i0, int64_t n) {
   return r;
 }
 
+Tensor slice_dim(const Tensor& t, int d, int64_t i0, int64_t n) {
+  Tensor r = t;
+  r.off = t.off + i0 * t.str[d];
+  r.dim[d] = n;
+  return r;
+}
+
 // ---------------------------------------------------------------- arena
 int64_t Arena::alloc(int64_t n) {
   n = (n + 31) / 32 * 32;  // 256-byte granularity
@@ -151,6 +158,39 @@ void Plan::allgather(const Tensor& chunk, int64_t count, const Tensor& full, con
   op.i2 = rank;
   op.note = note;
   ops.push_back(op);
+}
+
+void Plan::contract_split(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
+                          const Tensor& C, const char* sc, char lab, const char* note) {
+  if (world == 1) {
+    contract(alpha, A, sa, B, sb, 1.0, C, sc, note);
+    return;
+  }
+  const char* qa = strchr(sa, lab);
+  const char* qb = strchr(sb, lab);
+  if (!qa || !qb || strchr(sc, lab)) throw PlanError(std::string("contract_split: label must be contracted in ") + sa + "," + sb);
+  const int pa = (int)(qa - sa), pb = (int)(qb - sb);
+  const int64_t L = A.dim[pa], chunk = lead_chunk(L);
+  const int64_t l0 = std::min<int64_t>(L, rank * chunk), nl = std::min<int64_t>(L, l0 + chunk) - l0;
+  const int64_t n = C.size();
+  std::vector<int64_t> cd(C.dim, C.dim + C.nd);
+  Tensor part = tmpv(cd);
+  Tensor G = tmp({(int64_t)world, n});
+  if (nl > 0) contract(alpha, slice_dim(A, pa, l0, nl), sa, slice_dim(B, pb, l0, nl), sb, 0.0, part, sc, note);
+  else fill(part, 0.0);
+  allgather(part, n, G, note);
+  Op r;
+  r.kind = OP_REDUCE;
+  r.a = G;
+  r.i0 = world;
+  r.M = n; r.N = 1;
+  r.c = C;
+  r.i1 = 1; r.i2 = 0;
+  r.alpha = 1.0; r.beta = 1.0;
+  r.note = std::string(note) + " [sum over ranks]";
+  ops.push_back(r);
+  release(G);
+  release(part);
 }
 
 void Plan::contract_lead_dist(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,

@@ -50,6 +50,7 @@ Tensor reshape(const Tensor& t, std::initializer_list<int64_t> dims);   // conti
 Tensor block2(const Tensor& m, int64_t r0, int64_t nr, int64_t c0, int64_t nc);  // 2-D sub-block
 Tensor transpose2(const Tensor& m);
 Tensor slice0(const Tensor& t, int64_t i0, int64_t n);                   // leading-dim range
+Tensor slice_dim(const Tensor& t, int d, int64_t i0, int64_t n);         // range of dimension d
 
 enum OpKind : int {
   OP_GEMM = 0,    // C = alpha op(A) op(B) + beta C   (batched / split-K)
@@ -111,6 +112,10 @@ class Plan {
   void contract_lead_dist(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
                           const Tensor& C, const char* sc, const char* note = "");
   void allgather(const Tensor& chunk, int64_t count, const Tensor& full, const char* note = "");
+  // C (contiguous) += alpha * sum_K A.B with the range of the contracted label `lab` split across ranks
+  // (partial sums are all-gathered and added in rank order on every rank: bit-identical replicas)
+  void contract_split(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
+                      const Tensor& C, const char* sc, char lab, const char* note = "");
   void release(const Tensor& t);
 
   // C[sc] = alpha * sum_K A[sa] B[sb] + beta * C[sc]
