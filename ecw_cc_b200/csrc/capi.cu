@@ -501,6 +501,29 @@ int ecw_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, con
   });
 }
 
+// ---- FP64 GEMM on the INT8 tcgen05 pipe (ozaki.cu): raw entry points for tools/ and tests/
+int64_t ecw_ozaki_plane_bytes(int64_t R, int64_t K, int ns) { return ozaki_plane_bytes(R, K, ns); }
+int64_t ecw_ozaki_padded_rows(int64_t R) { return ozaki_padded_rows(R); }
+
+int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes, double* scale,
+                    void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    ck(launch_ozaki_split(X, R, K, rs, ks, ns, static_cast<int8_t*>(planes), scale, static_cast<cudaStream_t>(stream)),
+       "ozaki_split");
+  });
+}
+
+int ecw_ozaki_gemm(const void* pa, const double* sa, const void* pb, const double* sb, int64_t M, int64_t N, int64_t K,
+                   double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns, void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    ck(launch_ozaki_gemm(static_cast<const int8_t*>(pa), sa, static_cast<const int8_t*>(pb), sb, M, N, K, C, crs, ccs,
+                         alpha, beta, ns, static_cast<cudaStream_t>(stream), 0),
+       "ozaki_gemm");
+  });
+}
+
 // ---- primitive device ops (the CCS host class and the GCC intermediate getters are sequences of these)
 namespace {
 

@@ -21,6 +21,18 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st, int force_cfg = -1);
 bool gemm_tma_eligible(const GemmArgs& a);
 cudaError_t launch_gemm_tma(const GemmArgs& a, cudaStream_t st, int cfg);
 
+// FP64 GEMM by error-free splitting on the INT8 tcgen05 tensor pipe (ozaki.cu).
+// An operand X[R,K] (element (r,k) at X[r*rs + k*ks], one of rs/ks == 1) is cut into `ns` int8 digit
+// planes (ozaki_plane_bytes) plus one FP64 scale per padded row (ozaki_padded_rows doubles).
+int64_t ozaki_padded_rows(int64_t R);
+int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns);
+cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, int8_t* planes,
+                               double* scale, cudaStream_t st);
+// C[m*crs + n*ccs] = alpha * sum_k A[m,k] B[n,k] + beta * C  from the digit planes of A (M rows) and B (N rows)
+cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* pb, const double* sb, int64_t M, int64_t N,
+                              int64_t K, double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns,
+                              cudaStream_t st, int sm_count);
+
 constexpr int KMAXD = 6;
 struct PermArgs {
   const double* in;

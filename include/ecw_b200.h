@@ -152,6 +152,19 @@ int64_t ecw_plan_launches(ecw_ctx* ctx, const char* func, int mode_flags);
  * cfg < 0 picks the tile configuration automatically. */
 int ecw_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
               const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int cfg, void* stream);
+/* FP64 GEMM by error-free splitting on the INT8 tcgen05 tensor pipe (csrc/ozaki.cu).
+ * ecw_ozaki_split cuts X[R,K] (element (r,k) at X[r*rs + k*ks], one of rs/ks == 1) into `ns` int8
+ * digit planes (ecw_ozaki_plane_bytes bytes) and one FP64 scale per padded row
+ * (ecw_ozaki_padded_rows doubles); ecw_ozaki_gemm forms C[m*crs + n*ccs] = alpha * sum_k A[m,k] B[n,k]
+ * + beta * C from two plane sets.  Replaces the numpy einsum of the large contractions
+ * (CCSD.py:305, 411, 484, 602) together with ecw_dgemm. */
+int64_t ecw_ozaki_plane_bytes(int64_t R, int64_t K, int ns);
+int64_t ecw_ozaki_padded_rows(int64_t R);
+int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes, double* scale,
+                    void* stream);
+int ecw_ozaki_gemm(const void* planes_a, const double* scale_a, const void* planes_b, const double* scale_b, int64_t M,
+                   int64_t N, int64_t K, double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns,
+                   void* stream);
 /* per-op device timing of the last executed plan (ms), written as JSON */
 int ecw_profile_enable(ecw_ctx* ctx, int on);
 int64_t ecw_profile_dump(ecw_ctx* ctx, char* buf, int64_t buflen);
