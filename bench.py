@@ -194,8 +194,9 @@ def run_ours(args):
     o, v = args.nocc, args.nvir
     n = o + v
 
-    de = ecw.DeviceEris.synthetic(o, v, rank=rank, world=world)
+    de = ecw.DeviceEris.synthetic(o, v, rank=rank, world=world, gemm=args.gemm, int8_digits=args.int8_digits)
     cc = ecw.GCC(de)
+    ns = de.int8_digits
     t1, t2 = de.synth_tensor("t1", (o, v)), de.synth_tensor("t2", (o, o, v, v))
     l1, l2 = de.synth_tensor("l1", (o, v)), de.synth_tensor("l2", (o, o, v, v))
     fsp = de.synth_tensor("fsp", (n, n))
@@ -246,13 +247,14 @@ def run_ours(args):
         buf = ctypes.create_string_buffer(1 << 22)
         lib.ecw_profile_dump(de._h, buf, 1 << 22)
         ops = json.loads(buf.value.decode())
-        ladder_ms += [x["ms"] for x in ops if x["kind"] == "gemm" and "K1 pp ladder" in x["note"]]
+        ladder_ms += [x["ms"] for x in ops if x["kind"] in ("gemm", "oz_gemm") and "K1 pp ladder" in x["note"]]
     lib.ecw_profile_enable(de._h, 0)
-    ladder = [x for x in ops if x["kind"] == "gemm" and "K1 pp ladder" in x["note"]][0]
+    ladder = [x for x in ops if x["kind"] in ("gemm", "oz_gemm") and "K1 pp ladder" in x["note"]][0]
     ladder_flops = 2.0 * ladder["M"] * ladder["N"] * ladder["K"]
     ladder_ms = sum(ladder_ms) / len(ladder_ms)
     t_ms = sum(x["ms"] for x in ops)
-    gemm_ms = sum(x["ms"] for x in ops if x["kind"] == "gemm")
+    gemm_ms = sum(x["ms"] for x in ops if x["kind"] in ("gemm", "oz_gemm", "oz_split"))
+    int8_ms = sum(x["ms"] for x in ops if x["kind"] in ("oz_gemm", "oz_split"))
 
     # ---- end-to-end leg: host (pinned numpy) buffers through the reference-facing API
     cc.h2d_bytes = cc.d2h_bytes = 0
@@ -285,6 +287,41 @@ def run_ours(args):
     peak = measure_fp64_peak(torch)
     evals_per_s = args.steps * world / (ms_dev / 1e3) if world == 1 else args.steps / (ms_dev / 1e3)
     e2e_per_s = e2e_steps / (ms_e2e / 1e3)
+    fp64_equiv = ladder_flops / ladder_ms / 1e9
+    if ladder["kind"] == "oz_gemm":
+        # the dominant launch runs on the INT8 tensor pipe: ns(ns+1)/2 int8 products per FP64 product
+        nprod = ns * (ns + 1) // 2
+        mp = {}
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16 = float(mp.get("bf16_tflops", 0.0))
+        int8_peak = 2.0 * bf16 if bf16 > 0 else 4500.0
+        roofline = {"bound": "tensor",
+                    "kernel": "ecw::ozaki_gemm_kernel<%d> (tcgen05.mma kind::i8, TMEM accumulators), launch = packed "
+                              "pp-ladder %dx%dx%d (CCSD.py:305)" % (ns, ladder["M"], ladder["N"], ladder["K"]),
+                    "achieved": fp64_equiv * nprod, "peak": int8_peak, "unit": "TOP/s (int8 dense)",
+                    "frac": fp64_equiv * nprod / int8_peak, "traffic": None,
+                    "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst %.1f): the INT8 dense rate of the "
+                                    "tcgen05 pipe is twice the bf16 rate (nominal 4500 vs 2250)" % bf16) if bf16 > 0
+                    else "nominal INT8 dense 4500 TOP/s (B200_PROFILING.md fallback)",
+                    "int8_products_per_fp64_product": nprod,
+                    "fp64_equivalent_tflops": fp64_equiv, "cublas_dgemm_tflops_measured": peak,
+                    "fp64_equivalent_over_fp64_tensor_peak": fp64_equiv / peak,
+                    "launch_ms": ladder_ms, "launch_flops": ladder_flops,
+                    "gemm_share_of_tupdate": gemm_ms / t_ms, "int8_share_of_tupdate": int8_ms / t_ms}
+    else:
+        roofline = {"bound": "tensor",
+                    "kernel": "ecw::dgemm_tma_kernel (FP64 DMMA), launch = packed pp-ladder %dx%dx%d (CCSD.py:305)"
+                              % (ladder["M"], ladder["N"], ladder["K"]),
+                    "achieved": fp64_equiv, "peak": peak, "unit": "TFLOP/s",
+                    "frac": fp64_equiv / peak, "traffic": None,
+                    "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run, burst; "
+                                   "MEASURED_PEAKS.json has no FP64 entry; nominal FP64 tensor peak %.0f TFLOP/s"
+                                   % NOMINAL_FP64_TFLOPS,
+                    "launch_ms": ladder_ms, "launch_flops": ladder_flops,
+                    "gemm_share_of_tupdate": gemm_ms / t_ms}
     line = {
         "metric": METRIC, "value": evals_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -292,22 +329,18 @@ def run_ours(args):
         "config": {"workload": "synthetic spin-orbital CCSD T+Lambda residual (gamma+energy+tupdate+lupdate), "
                                "nocc=%d nvir=%d FP64" % (o, v),
                    "nocc": o, "nvir": v, "alpha": alpha, "parallelism": "1 GPU" if world == 1 else "vshard%d" % world,
-                   "l2_policy": "inputs larger than L2 (packed vvvv 50.9 GB is streamed every step)",
+                   "gemm_engine": ("int8 tcgen05 (%d digits) for the large GEMMs, FP64 DMMA for the rest" % ns) if ns
+                   else "FP64 DMMA",
+                   "l2_policy": "inputs larger than L2 (the packed vvvv, %.1f GB, is streamed every step)"
+                                % ((ns if ns else 8) * (v * (v - 1) // 2) ** 2 / 1e9),
+                   "fp64_tensor_peak_measured_tflops": peak,
+                   "tflops_alg_over_fp64_tensor_peak": f_alg(o, v) * evals_per_s / 1e12 / peak,
                    "f_alg_flops_per_eval": f_alg(o, v), "executed_gemm_flops_per_eval": exec_flops,
                    "tflops_alg": f_alg(o, v) * evals_per_s / 1e12, "tflops_executed": exec_flops * evals_per_s / 1e12},
         "clocks": clocks,
         "e2e": {"value": e2e_per_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches * args.steps),
-        "roofline": {"bound": "tensor",
-                     "kernel": "ecw::dgemm_kernel (FP64 DMMA), launch = packed pp-ladder %dx%dx%d (CCSD.py:305)"
-                               % (ladder["M"], ladder["N"], ladder["K"]),
-                     "achieved": ladder_flops / ladder_ms / 1e9, "peak": peak, "unit": "TFLOP/s",
-                     "frac": ladder_flops / ladder_ms / 1e9 / peak, "traffic": None,
-                     "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run, burst; "
-                                    "MEASURED_PEAKS.json has no FP64 entry; nominal FP64 tensor peak %.0f TFLOP/s"
-                                    % NOMINAL_FP64_TFLOPS,
-                     "launch_ms": ladder_ms, "launch_flops": ladder_flops,
-                     "gemm_share_of_tupdate": gemm_ms / t_ms},
+        "roofline": roofline,
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(o, v)
@@ -326,6 +359,8 @@ def main():
     ap.add_argument("--nvir", type=int, default=400)
     ap.add_argument("--alpha", type=float, default=None, help="L1 coefficient (default: none, as Main.CCSD_GS)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gemm", default=None, choices=["int8", "dmma"], help="GEMM engine (default: int8)")
+    ap.add_argument("--int8-digits", type=int, default=None, help="7-bit digits of the INT8 engine (default 7)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

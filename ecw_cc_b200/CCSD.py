@@ -278,6 +278,9 @@ class GCC(object):
         if self.eris.world != 1:
             raise EcwError("dense vvvv is not available on a sharded context")
         pv = v * (v - 1) // 2
+        if "vvvv_p" not in self.eris.buf:
+            raise EcwError("dense vvvv is not available: the packed vvvv is held as INT8 digit planes only "
+                           "(DeviceEris.synthetic(..., keep_fp64_vvvv=True) keeps the FP64 layout)")
         return ops.unpack(self.eris.buf["vvvv_p"][: pv * pv].view(pv, pv), 3, ops.empty(v, v, v, v))
 
     def cc_Wvvvv(self, t1, t2):                                             # CCSD.py:396-402 (small sizes only: v^4)

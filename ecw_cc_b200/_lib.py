@@ -57,6 +57,10 @@ class _Lib(object):
             "ecw_version": (c_s, []),
             "ecw_ctx_set_shard": (c_i, [c_p, c_i, c_i]),
             "ecw_resume": (c_i, [c_p, c_p]),
+            "ecw_ctx_set_gemm": (c_i, [c_p, c_i, c_d]),
+            "ecw_ctx_get_gemm": (c_i, [c_p]),
+            "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),
+            "ecw_eris_vvvv_planes": (c_i, [c_p, c_p, c_l, c_l, c_p]),
             "ecw_pending_collective": (c_i, [c_p, ctypes.POINTER(c_l)]),
             "ecw_slot_elems": (c_l, [c_p, c_s]),
             "ecw_bind": (c_i, [c_p, c_s, c_p]),
@@ -78,6 +82,7 @@ class _Lib(object):
             "ecw_ozaki_plane_bytes": (c_l, [c_l, c_l, c_i]),
             "ecw_ozaki_padded_rows": (c_l, [c_l]),
             "ecw_ozaki_split": (c_i, [c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p, c_p]),
+            "ecw_ozaki_split_rows": (c_i, [c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p, c_l, c_l, c_p]),
             "ecw_ozaki_gemm": (c_i, [c_p, c_p, c_p, c_p, c_l, c_l, c_l, c_p, c_l, c_l, c_d, c_d, c_i, c_p]),
             "ecw_op_contract": (c_i, [c_p, c_d, c_p, c_s, c_p, c_s, c_d, c_p, c_s, c_p]),
             "ecw_op_axpby": (c_i, [c_p, c_d, c_p, c_s, c_d, c_p, c_s, c_p]),

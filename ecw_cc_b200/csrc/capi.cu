@@ -32,6 +32,7 @@ struct ecw_ctx {
   int64_t need_ws = 0;
   std::vector<cudaEvent_t> ev;
   const Plan* last_plan = nullptr;
+  int sm_count = 0;        // 0: launchers query / assume 148
   ecw_ctx() { for (auto& p : ptr) p = nullptr; }
 };
 
@@ -56,10 +57,13 @@ int64_t slot_elems(const Sizes& z, int s) {
     case S_OOOO_P: return po * po;
     case S_OOVV_P: return po * pv;
     case S_OVVV_P: return o * v * pv;
-    case S_VVVV_P: {
+    case S_VVVV_P: case S_VVVV_OZ: case S_VVVV_OZS: {
       const int64_t nshmax = (pv + z.world - 1) / z.world;
       const int64_t n0 = std::min<int64_t>(pv, (int64_t)z.rank * nshmax);
-      return (std::min<int64_t>(pv, n0 + nshmax) - n0) * pv;
+      const int64_t nsh = std::min<int64_t>(pv, n0 + nshmax) - n0;
+      if (s == S_VVVV_P) return nsh * pv;
+      if (s == S_VVVV_OZS) return ozaki_padded_rows(nsh);
+      return (ozaki_plane_bytes(nsh, pv, z.oz_ns > 0 ? z.oz_ns : 7) + 7) / 8;   // in 8-byte units
     }
     default: return -1;
   }
@@ -193,6 +197,16 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
         if (c->profile) ck(cudaEventRecord(c->ev[c->pc], st), "cudaEventRecord");
         return 1;
       }
+      case OP_OZ_SPLIT:
+        ck(launch_ozaki_split(resolve(c, op.a), op.M, op.K, op.lda, op.ldb, (int)op.i0,
+                              reinterpret_cast<int8_t*>(resolve(c, op.c)), resolve(c, op.d), st), "ozaki_split");
+        break;
+      case OP_OZ_GEMM:
+        ck(launch_ozaki_gemm(reinterpret_cast<const int8_t*>(resolve(c, op.a)), resolve(c, op.d),
+                             reinterpret_cast<const int8_t*>(resolve(c, op.b)), resolve(c, op.e), op.M, op.N, op.K,
+                             resolve(c, op.c), op.i1, op.i2, op.alpha, op.beta, (int)op.i0, st, c->sm_count),
+           "ozaki_gemm");
+        break;
       default:
         throw Fail("unknown op kind");
     }
@@ -305,6 +319,46 @@ int ecw_ctx_set_shard(ecw_ctx* c, int rank, int world) {
   return 0;
 }
 
+int ecw_ctx_set_gemm(ecw_ctx* c, int int8_digits, double min_flops) {
+  if (!c || (int8_digits != 0 && (int8_digits < 3 || int8_digits > 8))) return -1;
+  if (c->z.vvvv_planes && int8_digits != c->z.oz_ns) {
+    c->err = "ecw_ctx_set_gemm: the vvvv digit planes are already bound for another digit count";
+    return -1;
+  }
+  c->z.oz_ns = int8_digits;
+  c->z.oz_min_flops = min_flops;
+  c->plans.clear();
+  c->run_plan_ptr = nullptr;
+  return 0;
+}
+
+int ecw_ctx_get_gemm(ecw_ctx* c) { return c ? c->z.oz_ns : -1; }
+
+int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* c) {
+  if (!c || c->z.oz_ns <= 0) return -1;
+  c->z.vvvv_planes = true;
+  c->plans.clear();
+  return 0;
+}
+
+int ecw_eris_vvvv_planes(ecw_ctx* c, const double* rows, int64_t row0, int64_t nrows, void* stream) {
+  return guarded(c, [&] {
+    require_device();
+    if (c->z.oz_ns <= 0) throw Fail("ecw_eris_vvvv_planes: the INT8 GEMM engine is off (ecw_ctx_set_gemm)");
+    if (!c->ptr[S_VVVV_OZ] || !c->ptr[S_VVVV_OZS]) throw Fail("slots 'vvvv_oz' / 'vvvv_ozs' are not bound");
+    const int64_t pv = npair(c->z.nvir);
+    const int64_t nsh = slot_elems(c->z, S_VVVV_P) / std::max<int64_t>(pv, 1);
+    if (row0 < 0 || nrows < 0 || row0 + nrows > nsh) throw Fail("ecw_eris_vvvv_planes: row range outside this rank's shard");
+    if (nrows > 0)
+      ck(launch_ozaki_split(rows, nrows, pv, pv, 1, c->z.oz_ns, reinterpret_cast<int8_t*>(c->ptr[S_VVVV_OZ]),
+                            c->ptr[S_VVVV_OZS], static_cast<cudaStream_t>(stream), row0, nsh), "ozaki_split(vvvv)");
+    if (row0 + nrows == nsh) {          // last chunk: from now on plans read the planes, not "vvvv_p"
+      c->z.vvvv_planes = true;
+      c->plans.clear();
+    }
+  });
+}
+
 int ecw_resume(ecw_ctx* c, void* stream) {
   return guarded_rc(c, [&] {
     if (!c->run_plan_ptr) throw Fail("ecw_resume: no call in flight");
@@ -382,6 +436,9 @@ int ecw_eris_synthetic(ecw_ctx* c, double scale, void* stream) {
         {S_OVOV_PH, SY_OVOV_PH, o}, {S_OVVV, SY_OVVV, o}, {S_OOOO_P, SY_OOOO_P, po}, {S_OOVV_P, SY_OOVV_P, po},
         {S_OVVV_P, SY_OVVV_P, o}, {S_VVVV_P, SY_VVVV_P, pv}};
     for (auto& t : tab) {
+      // INT8 engine: the packed vvvv exists only as digit planes, cut chunk by chunk by the caller
+      // (ecw_synth_tensor rows -> ecw_eris_vvvv_planes)
+      if (t.slot == S_VVVV_P && !c->ptr[t.slot] && c->z.oz_ns > 0) continue;
       if (!c->ptr[t.slot]) throw Fail(std::string("slot '") + slot_name(t.slot) + "' is not bound");
       int64_t r0 = 0, nr = t.rows;
       if (t.slot == S_VVVV_P) {   // this rank's rows of the packed virtual pair index
@@ -484,7 +541,7 @@ int64_t ecw_plan_launches(ecw_ctx* c, const char* func, int flags) {
   guarded(c, [&] {
     const Plan& P = get_plan(c, func, flags);
     int64_t n = 0;
-    for (auto& op : P.ops) n += (op.kind == OP_DOT) ? 2 : 1;
+    for (auto& op : P.ops) n += (op.kind == OP_DOT || op.kind == OP_OZ_SPLIT) ? 2 : (op.kind == OP_ALLGATHER ? 0 : 1);
     r = n;
   });
   return r;
@@ -511,6 +568,16 @@ int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t k
     require_device();
     ck(launch_ozaki_split(X, R, K, rs, ks, ns, static_cast<int8_t*>(planes), scale, static_cast<cudaStream_t>(stream)),
        "ozaki_split");
+  });
+}
+
+int ecw_ozaki_split_rows(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes,
+                         double* scale, int64_t row0, int64_t total_rows, void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    ck(launch_ozaki_split(X, R, K, rs, ks, ns, static_cast<int8_t*>(planes), scale, static_cast<cudaStream_t>(stream),
+                          row0, total_rows),
+       "ozaki_split_rows");
   });
 }
 
@@ -557,6 +624,7 @@ int ecw_op_contract(ecw_ctx* c, double alpha, const ecw_tensor* A, const char* s
   return guarded_rc(c, [&] {
     require_device();
     Plan P;
+    P.oz_ns = c->z.oz_ns; P.oz_min_flops = c->z.oz_min_flops;
     c->ptr[S_A0] = (double*)A->ptr; c->ptr[S_A1] = (double*)B->ptr; c->ptr[S_B0] = (double*)C->ptr;
     P.contract(alpha, from_desc(A, S_A0), sa, from_desc(B, S_A1), sb, beta, from_desc(C, S_B0), sc, "op");
     c->op_plan = std::move(P);
@@ -670,7 +738,7 @@ int64_t ecw_profile_dump(ecw_ctx* c, char* buf, int64_t buflen) {
     if (!c->last_plan || c->ev.empty()) throw Fail("no profiled run");
     ck(cudaEventSynchronize(c->ev.back()), "cudaEventSynchronize");
     static const char* kn[] = {"gemm", "reduce", "permute", "fill", "tau", "pack", "unpack", "finish",
-                               "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather"};
+                               "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather", "oz_split", "oz_gemm"};
     std::ostringstream o;
     o << "[";
     for (size_t i = 0; i < c->last_plan->ops.size(); ++i) {

@@ -163,8 +163,7 @@ void ladder_dist(Plan& P, const Slots& s, const Tensor& X, const Tensor& acc, do
 }  // namespace
 
 void build_ccsd_energy(Plan& P, const Sizes& z) {
-  P.rank = z.rank;
-  P.world = z.world;
+  z.apply(P);
   Slots s(z);
   Tensor f = P.tmp({s.o, s.v});
   P.axpby(1.0, s.fov, 0.0, f);
@@ -173,8 +172,7 @@ void build_ccsd_energy(Plan& P, const Sizes& z) {
 }
 
 void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
-  P.rank = z.rank;
-  P.world = z.world;
+  z.apply(P);
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv;
   const bool shift = !equation && !has_alpha;  // CCSD.py:283-285
@@ -295,8 +293,7 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
 }
 
 void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
-  P.rank = z.rank;
-  P.world = z.world;
+  z.apply(P);
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv;
   const bool shift = !equation && !has_alpha;  // CCSD.py:449-456 (Q2)
@@ -521,8 +518,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
 // rows of the ladders stay dense.  Spec: oracle/refactored_np.py *_general.
 // ======================================================================
 void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equation) {
-  P.rank = z.rank;
-  P.world = z.world;
+  z.apply(P);
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv, oo = o * o, vv = v * v;
   const bool shift = !equation && !has_alpha;
@@ -651,8 +647,7 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
 }
 
 void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equation) {
-  P.rank = z.rank;
-  P.world = z.world;
+  z.apply(P);
   Slots s(z);
   const int64_t o = s.o, v = s.v, po = s.po, pv = s.pv, oo = o * o, vv = v * v;
   const bool shift = !equation && !has_alpha;
@@ -876,8 +871,7 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
 }
 
 void build_ccsd_gamma(Plan& P, const Sizes& z) {
-  P.rank = z.rank;
-  P.world = z.world;
+  z.apply(P);
   Slots s(z);
   const int64_t o = s.o, v = s.v;
   const Tensor &t1 = s.t1, &t2 = s.t2, &l1 = s.l1, &l2 = s.l2;

@@ -7,6 +7,16 @@ namespace ecw {
 struct Sizes {
   int64_t nocc = 0, nvir = 0;
   int rank = 0, world = 1;   // vvvv_p is row-sharded over the packed virtual pair index; heavy GEMMs owner-computes
+  // GEMM engine: oz_ns > 0 routes large unbatched GEMMs to the INT8 tcgen05 pipe (ozaki.cu) with oz_ns
+  // 7-bit digits when 2MNK >= oz_min_flops (negative: every unbatched GEMM); vvvv_planes: the packed
+  // vvvv shard is bound as digit planes ("vvvv_oz"/"vvvv_ozs") instead of FP64 ("vvvv_p")
+  int oz_ns = 0;
+  double oz_min_flops = 2e10;
+  bool vvvv_planes = false;
+  void apply(Plan& P) const {
+    P.rank = rank; P.world = world;
+    P.oz_ns = oz_ns; P.oz_min_flops = oz_min_flops; P.vvvv_planes = vvvv_planes && oz_ns > 0;
+  }
 };
 
 // mode flags mirror the reference keyword arguments of GCC.tupdate/lupdate

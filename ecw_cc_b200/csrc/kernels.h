@@ -26,8 +26,10 @@ cudaError_t launch_gemm_tma(const GemmArgs& a, cudaStream_t st, int cfg);
 // planes (ozaki_plane_bytes) plus one FP64 scale per padded row (ozaki_padded_rows doubles).
 int64_t ozaki_padded_rows(int64_t R);
 int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns);
+// row0/total_rows: X holds rows [row0, row0+R) of an operand of total_rows rows whose plane set is cut chunk
+// by chunk (row0 a multiple of 128; every chunk but the last a multiple of 128 rows)
 cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, int8_t* planes,
-                               double* scale, cudaStream_t st);
+                               double* scale, cudaStream_t st, int64_t row0 = 0, int64_t total_rows = 0);
 // C[m*crs + n*ccs] = alpha * sum_k A[m,k] B[n,k] + beta * C  from the digit planes of A (M rows) and B (N rows)
 cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* pb, const double* sb, int64_t M, int64_t N,
                               int64_t K, double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns,

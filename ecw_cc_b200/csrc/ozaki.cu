@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
 // row scales: s_r = 2^(e_r - 6) with |X[r,:]| < 2^e_r  (s_r = 1 for an all-zero or padded row)
 // X[r*rs + k*ks]; one of rs, ks is 1.
 __global__ void ozaki_rowmax_kcontig(const double* __restrict__ X, int64_t R, int64_t K, int64_t rs, int64_t Rp,
-                                     double* __restrict__ scale) {
+                                     double* __restrict__ scale) {   // scale already offset to the chunk's first row
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= Rp) return;
@@ -369,8 +369,10 @@ __global__ void ozaki_rowmax_rcontig(const double* __restrict__ X, int64_t R, in
 // thread t: row t%128, 16-byte k-chunk t/128.
 template <int NS>
 __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restrict__ X, int64_t R, int64_t K, int64_t rs,
-                                                          int64_t ks, int64_t Rp, const double* __restrict__ scale,
+                                                          int64_t ks, int64_t Rp, int64_t row0,
+                                                          const double* __restrict__ scale,
                                                           int8_t* __restrict__ planes) {
+  // X, scale: the chunk (local rows 0..R); planes: the whole set of Rp padded rows, chunk rows start at row0
   const int t = threadIdx.x;
   const int64_t r = (int64_t)blockIdx.x * 128 + (t & 127);
   const int j = t >> 7;
@@ -396,7 +398,8 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
     for (int i = 0; i < 16; ++i) x[i] = 0.0;
   }
   const int64_t slab = Rp * OZ_BK;
-  int8_t* dst = planes + (kb * NS) * slab + (r >> 3) * 256 + j * 128 + (r & 7) * 16;
+  const int64_t rg = row0 + r;
+  int8_t* dst = planes + (kb * NS) * slab + (rg >> 3) * 256 + j * 128 + (rg & 7) * 16;
 #pragma unroll
   for (int p = 0; p < NS; ++p) {
     uint32_t w[4] = {0, 0, 0, 0};
@@ -430,20 +433,24 @@ int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns) {
 }
 
 cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, int8_t* planes,
-                               double* scale, cudaStream_t st) {
-  if (ns < 3 || ns > 8 || (rs != 1 && ks != 1)) return cudaErrorInvalidValue;
-  const int64_t Rp = ozaki_padded_rows(R);
+                               double* scale, cudaStream_t st, int64_t row0, int64_t total_rows) {
+  if (ns < 3 || ns > 8 || (rs != 1 && ks != 1) || (row0 & 127)) return cudaErrorInvalidValue;
+  if (total_rows <= 0) total_rows = row0 + R;
+  if (row0 + R > total_rows || (row0 + R < total_rows && (R & 127))) return cudaErrorInvalidValue;
+  const int64_t Rp = ozaki_padded_rows(R);              // rows this launch writes (incl. zero padding)
+  const int64_t Rp_total = ozaki_padded_rows(total_rows);
+  double* sc = scale + row0;
   if (ks == 1) {
-    ozaki_rowmax_kcontig<<<(unsigned)((Rp + 7) / 8), 256, 0, st>>>(X, R, K, rs, Rp, scale);
+    ozaki_rowmax_kcontig<<<(unsigned)((Rp + 7) / 8), 256, 0, st>>>(X, R, K, rs, Rp, sc);
   } else {
-    ozaki_rowmax_rcontig<<<(unsigned)((Rp + 31) / 32), 256, 0, st>>>(X, R, K, ks, Rp, scale);
+    ozaki_rowmax_rcontig<<<(unsigned)((Rp + 31) / 32), 256, 0, st>>>(X, R, K, ks, Rp, sc);
   }
   const int64_t nkb = (K + OZ_BK - 1) / OZ_BK;
   if (nkb > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)(Rp / 128), (unsigned)nkb, 1);
   switch (ns) {
 #define ECW_OZ_SPLIT(NS_) \
-  case NS_: ozaki_split_kernel<NS_><<<grid, 256, 0, st>>>(X, R, K, rs, ks, Rp, scale, planes); break;
+  case NS_: ozaki_split_kernel<NS_><<<grid, 256, 0, st>>>(X, R, K, rs, ks, Rp_total, row0, sc, planes); break;
     ECW_OZ_SPLIT(3) ECW_OZ_SPLIT(4) ECW_OZ_SPLIT(5) ECW_OZ_SPLIT(6) ECW_OZ_SPLIT(7) ECW_OZ_SPLIT(8)
 #undef ECW_OZ_SPLIT
   }

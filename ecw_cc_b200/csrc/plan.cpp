@@ -15,6 +15,7 @@ const char* slot_name(int s) {
   static const char* names[] = {
       "ws", "t1", "t2", "l1", "l2", "fsp", "fock", "out1", "out2", "rdm1", "scal",
       "oooo", "ooov", "oovv", "oovv_ph", "ovov_ph", "ovvv", "oooo_p", "oovv_p", "ovvv_p", "vvvv_p",
+      "vvvv_oz", "vvvv_ozs",
       "a0", "a1", "a2", "a3", "a4", "a5", "a6", "a7", "a8", "a9",
       "b0", "b1", "b2", "b3", "b4", "b5", "b6", "b7"};
   if (s < 0 || s >= S_COUNT) return "?";
@@ -577,6 +578,63 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
   g.alpha = alpha;
   g.note = std::string(note) + " [" + tag + "]";
 
+  // ---- INT8 tensor-core route (ozaki.cu): one unbatched GEMM, operands cut into digit planes
+  {
+    const bool const_planes = vvvv_planes && (A.slot == S_VVVV_P || B.slot == S_VVVV_P);
+    const double fl = 2.0 * (double)Md * (double)Nd * (double)Kd;
+    bool oz = oz_ns > 0 && ch.bcls == 0 && Kd >= 1 && (Kd + 31) / 32 <= 65535;
+    if (oz && oz_min_flops >= 0.0) {
+      // cost model (seconds): INT8 route = padded product at ~100 TFLOP/s FP64-equivalent scaled by how many of
+      // the 148 SMs get a 128x64 tile, plus cutting both operands (8 B read + ns B written, re-read once);
+      // DMMA route = 30 TFLOP/s.  Skinny or few-tile products stay on the DMMA kernels.
+      auto pad = [](int64_t x, int64_t g) { return (x + g - 1) / g * g; };
+      const double t1m = (double)pad(Md, 128) * (double)pad(Nd, 64), t2m = (double)pad(Md, 64) * (double)pad(Nd, 128);
+      const bool sw = t2m < t1m;
+      const double tiles = sw ? (double)(pad(Md, 64) / 64) * (double)(pad(Nd, 128) / 128)
+                              : (double)(pad(Md, 128) / 128) * (double)(pad(Nd, 64) / 64);
+      const double eff = std::min(1.0, tiles / (double)sm_count);
+      const double cut = (8.0 + 2.0 * oz_ns) * ((const_planes && A.slot == S_VVVV_P ? 0.0 : (double)Md) +
+                                                (const_planes && B.slot == S_VVVV_P ? 0.0 : (double)Nd)) * (double)Kd / 5e12;
+      const double t_oz = 2.0 * (double)Kd * std::min(t1m, t2m) / (1.0e14 * eff) + cut + 2e-5;
+      oz = fl >= oz_min_flops && t_oz < 0.8 * fl / 3.0e13;
+    }
+    if (const_planes && !(oz_ns > 0 && ch.bcls == 0 && ch.a_dir && ch.b_dir))
+      throw PlanError("contract: vvvv_p is bound as digit planes but the contraction is not a plain GEMM: " + tag);
+    if (oz || const_planes) {
+      Tensor tA = A, tB = B;
+      int64_t ars, aks, brs, bks;
+      if (ch.a_dir) { ars = ch.ta ? 1 : ch.lda; aks = ch.ta ? ch.lda : 1; }
+      else {
+        std::vector<int64_t> dv = dimvec(ch.om + ch.ok);
+        tA = tmpv(dv);
+        permute(1.0, A, sa, 0.0, tA, (ch.om + ch.ok).c_str(), "engine:A");
+        to_free.push_back(tA);
+        ars = std::max<int64_t>(Kd, 1); aks = 1;
+      }
+      if (ch.b_dir) { brs = ch.tb ? ch.ldb : 1; bks = ch.tb ? 1 : ch.ldb; }
+      else {
+        std::vector<int64_t> dv = dimvec(ch.ok + ch.on);
+        tB = tmpv(dv);
+        permute(1.0, B, sb, 0.0, tB, (ch.ok + ch.on).c_str(), "engine:B");
+        to_free.push_back(tB);
+        brs = 1; bks = std::max<int64_t>(Nd, 1);
+      }
+      MatView vc = mat_view(C, sc, ch.om, ch.on);
+      const std::string nt = std::string(note) + " [" + tag + "]";
+      if (vc.any) {
+        emit_oz(alpha, tA, ars, aks, tB, brs, bks, Md, Nd, Kd, beta, C, Md == 1 ? 0 : vc.sr, Nd == 1 ? 0 : vc.scol, nt);
+      } else {
+        std::string lay = ch.om + ch.on;
+        Tensor tC = tmpv(dimvec(lay));
+        emit_oz(alpha, tA, ars, aks, tB, brs, bks, Md, Nd, Kd, 0.0, tC, Nd, 1, nt);
+        permute(1.0, tC, lay.c_str(), beta, C, sc, "engine:C");
+        release(tC);
+      }
+      for (auto& t : to_free) release(t);
+      return;
+    }
+  }
+
   // ---- A operand
   if (ch.a_dir) {
     g.a = A; g.ta = ch.ta; g.lda = ch.lda; g.sA = ch.sA;
@@ -679,6 +737,65 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
   for (auto& t : to_free) release(t);
 }
 
+// ---------------------------------------------------------------- INT8-pipe GEMM
+static int64_t oz_pad_rows(int64_t r) { return (r + 127) / 128 * 128; }
+static int64_t oz_plane_elems(int64_t R, int64_t K, int ns) {
+  return (oz_pad_rows(R) * ((K + 31) / 32 * 32) * ns + 7) / 8;
+}
+
+void Plan::emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, const Tensor& B, int64_t brs, int64_t bks,
+                   int64_t M, int64_t N, int64_t K, double beta, const Tensor& C, int64_t crs, int64_t ccs,
+                   const std::string& note) {
+  struct Side { Tensor planes, scales; bool owned; };
+  auto prepare = [&](const Tensor& X, int64_t R, int64_t rs, int64_t ks) {
+    Side s;
+    if (vvvv_planes && X.slot == S_VVVV_P) {
+      // the constant row shard of the packed vvvv: [R, K] with K contiguous, cut once at upload time
+      if (X.off != 0 || ks != 1 || rs != K) throw PlanError("vvvv_p digit planes: unexpected operand view in " + note);
+      s.planes = make_tensor(S_VVVV_OZ, 0, {oz_plane_elems(R, K, oz_ns)});
+      s.scales = make_tensor(S_VVVV_OZS, 0, {oz_pad_rows(R)});
+      s.owned = false;
+      return s;
+    }
+    s.planes = tmp({oz_plane_elems(R, K, oz_ns)});
+    s.scales = tmp({oz_pad_rows(R)});
+    s.owned = true;
+    Op sp;
+    sp.kind = OP_OZ_SPLIT;
+    sp.a = X;
+    sp.c = s.planes;
+    sp.d = s.scales;
+    sp.M = R; sp.K = K; sp.lda = rs; sp.ldb = ks;
+    sp.i0 = oz_ns;
+    sp.note = note;
+    ops.push_back(sp);
+    return s;
+  };
+  Side a = prepare(A, M, ars, aks), b = prepare(B, N, brs, bks);
+  Op g;
+  g.kind = OP_OZ_GEMM;
+  g.alpha = alpha; g.beta = beta;
+  g.c = C;
+  g.K = K;
+  g.i0 = oz_ns;
+  g.note = note;
+  // tile = 128 rows of the first operand x 64 rows of the second: pick the roles with less padding
+  auto pad = [](int64_t x, int64_t gq) { return (x + gq - 1) / gq * gq; };
+  const bool swap = (double)pad(N, 128) * (double)pad(M, 64) < (double)pad(M, 128) * (double)pad(N, 64);
+  if (!swap) {
+    g.a = a.planes; g.d = a.scales; g.b = b.planes; g.e = b.scales;
+    g.M = M; g.N = N; g.i1 = crs; g.i2 = ccs;
+  } else {
+    g.a = b.planes; g.d = b.scales; g.b = a.planes; g.e = a.scales;
+    g.M = N; g.N = M; g.i1 = ccs; g.i2 = crs;
+  }
+  ops.push_back(g);
+  gemm_flops += 2.0 * (double)M * N * K;
+  oz_flops += 2.0 * (double)M * N * K;
+  if (b.owned) { release(b.scales); release(b.planes); }
+  if (a.owned) { release(a.scales); release(a.planes); }
+}
+
 // ---------------------------------------------------------------- dump
 static void dump_tensor(std::ostringstream& o, const char* key, const Tensor& t) {
   o << "\"" << key << "\":";
@@ -692,10 +809,10 @@ static void dump_tensor(std::ostringstream& o, const char* key, const Tensor& t)
 
 std::string Plan::dump_json() const {
   static const char* kn[] = {"gemm", "reduce", "permute", "fill", "tau", "pack", "unpack", "finish",
-                             "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather"};
+                             "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather", "oz_split", "oz_gemm"};
   std::ostringstream o;
   o.precision(17);
-  o << "{\"workspace_elems\":" << arena.peak << ",\"gemm_flops\":" << gemm_flops
+  o << "{\"workspace_elems\":" << arena.peak << ",\"gemm_flops\":" << gemm_flops << ",\"oz_flops\":" << oz_flops
     << ",\"perm_bytes\":" << perm_bytes << ",\"ops\":[";
   for (size_t i = 0; i < ops.size(); ++i) {
     const Op& p = ops[i];

@@ -28,6 +28,9 @@ enum Slot : int {
   // constant integral layouts (eris container)
   S_OOOO, S_OOOV, S_OOVV, S_OOVV_PH, S_OVOV_PH, S_OVVV,
   S_OOOO_P, S_OOVV_P, S_OVVV_P, S_VVVV_P,
+  // int8 digit planes + row scales of vvvv_p for the INT8-tensor-core GEMM (ozaki.cu); element
+  // offsets into these two slots are in units of 8 bytes like everywhere else
+  S_VVVV_OZ, S_VVVV_OZS,
   // generic argument slots for the CCS entry points
   S_A0, S_A1, S_A2, S_A3, S_A4, S_A5, S_A6, S_A7, S_A8, S_A9,
   S_B0, S_B1, S_B2, S_B3, S_B4, S_B5, S_B6, S_B7,
@@ -67,6 +70,8 @@ enum OpKind : int {
   OP_RDM1,        // assemble the symmetrised rdm1 (CCSD.py:154-160)
   OP_EWISE,       // small CCS element-wise helpers (sub-kind in i0)
   OP_ALLGATHER,   // collective: every rank contributes `a` (i0 elements); `c` receives world*i0 (host runs it)
+  OP_OZ_SPLIT,    // a = X[R=M, K] (element strides lda, ldb) -> c = i0 int8 digit planes, d = row scales
+  OP_OZ_GEMM,     // C[m*i1 + n*i2] = alpha sum_k A[m,k] B[n,k] + beta C from planes a (scales d) and b (scales e)
 };
 
 struct Op {
@@ -100,6 +105,12 @@ class Plan {
   Arena arena;
   int sm_count = 148;
   int rank = 0, world = 1;     // owner-computes distribution of the heavy contractions
+  // Large unbatched GEMMs run on the INT8 tcgen05 pipe by error-free splitting (ozaki.cu) when
+  // oz_ns > 0 and 2MNK >= oz_min_flops; oz_ns = number of 7-bit digits (7: FP64-level accuracy).
+  int oz_ns = 0;
+  double oz_min_flops = 0.0;
+  bool vvvv_planes = false;    // vvvv_p is bound as digit planes (S_VVVV_OZ/S_VVVV_OZS), not as FP64
+  double oz_flops = 0.0;       // part of gemm_flops that runs on the INT8 pipe
   double gemm_flops = 0.0;     // sum of 2MNK over GEMM ops (executed flops)
   double perm_bytes = 0.0;     // bytes moved by engine-inserted permutes
 
@@ -147,7 +158,10 @@ class Plan {
   std::string dump_json() const;
 
  private:
-  void emit_gemm(Op op, bool allow_split);
+  // INT8-pipe route of one unbatched GEMM: X[M,K] (strides ars, aks) . Y[N,K]^T (strides brs, bks)
+  void emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, const Tensor& B, int64_t brs, int64_t bks,
+               int64_t M, int64_t N, int64_t K, double beta, const Tensor& C, int64_t crs, int64_t ccs,
+               const std::string& note);
 };
 
 int64_t npair(int64_t n);

@@ -7,6 +7,7 @@ antisymmetrised <pq||rs>) and keeps the constant layouts the kernels read
 molecule (PySCF ao2mo, Eris.py:47-128) is out of scope.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -15,6 +16,26 @@ from ._lib import lib, EcwError
 _LAYOUTS = ("oooo", "ooov", "oovv", "ovvv", "oovv_ph", "ovov_ph", "oooo_p", "oovv_p", "ovvv_p", "vvvv_p")
 SYNTH_KIND = dict(oooo=0, ooov=1, oovv=2, oovv_ph=3, ovov_ph=4, ovvv=5, oooo_p=6, oovv_p=7, ovvv_p=8, vvvv_p=9,
                   fock=10, fsp=11, t1=12, l1=13, t2=14, l2=15)
+
+
+# GEMM engine of the contraction plans (include/ecw_b200.h, ecw_ctx_set_gemm):
+#   "int8" (default) - large unbatched GEMMs on the INT8 tcgen05 tensor pipe by error-free splitting
+#                      into INT8_DIGITS 7-bit digits; the packed vvvv lives on the device as digit planes;
+#   "dmma"           - everything on the FP64 DMMA kernels.
+# Environment overrides for experiments: ECW_GEMM, ECW_INT8_DIGITS, ECW_INT8_MIN_FLOPS (-1: every GEMM).
+INT8_DIGITS = 7
+INT8_MIN_FLOPS = 2e10
+
+
+def _gemm_config(gemm, int8_digits, int8_min_flops):
+    gemm = gemm or os.environ.get("ECW_GEMM", "int8")
+    if gemm not in ("int8", "dmma"):
+        raise ValueError("gemm must be 'int8' or 'dmma', got %r" % (gemm,))
+    if gemm == "dmma":
+        return 0, 0.0
+    nd = int(int8_digits if int8_digits is not None else os.environ.get("ECW_INT8_DIGITS", INT8_DIGITS))
+    mf = float(int8_min_flops if int8_min_flops is not None else os.environ.get("ECW_INT8_MIN_FLOPS", INT8_MIN_FLOPS))
+    return nd, mf
 
 
 def _torch():
@@ -27,9 +48,11 @@ def _torch():
 class DeviceEris(object):
     """Owns the C context, the bound integral layouts and the workspace."""
 
-    def __init__(self, nocc, nvir, device=None, rank=0, world=1, group=None):
+    def __init__(self, nocc, nvir, device=None, rank=0, world=1, group=None, gemm=None, int8_digits=None,
+                 int8_min_flops=None):
         """rank/world/group: one process per GPU; `vvvv_p` is then row-sharded over the packed
-        virtual pair index and the heavy contractions are distributed (include/ecw_b200.h)."""
+        virtual pair index and the heavy contractions are distributed (include/ecw_b200.h).
+        gemm: "int8" | "dmma" (see module header)."""
         torch = _torch()
         self.nocc = int(nocc)
         self.nvir = int(nvir)
@@ -40,6 +63,8 @@ class DeviceEris(object):
             raise EcwError("ecw_ctx_create failed")
         if self.world > 1 and lib.ecw_ctx_set_shard(self._h, self.rank, self.world) != 0:
             raise EcwError("ecw_ctx_set_shard failed")
+        self.int8_digits, self.int8_min_flops = _gemm_config(gemm, int8_digits, int8_min_flops)
+        self.check(lib.ecw_ctx_set_gemm(self._h, self.int8_digits, self.int8_min_flops), "ecw_ctx_set_gemm")
         self.buf = {}
         self._ws = None
         self._scal = torch.zeros(16, dtype=torch.float64, device=self.device)
@@ -113,12 +138,14 @@ class DeviceEris(object):
 
     # -- constructors ----------------------------------------------------------
     @classmethod
-    def from_geris(cls, eris, device=None, rank=0, world=1, group=None):
+    def from_geris(cls, eris, device=None, rank=0, world=1, group=None, gemm=None, int8_digits=None,
+                   int8_min_flops=None):
         """Upload a reference-style container (numpy blocks, Eris.py:132-150)."""
         torch = _torch()
         fock = np.asarray(eris.fock)
         nocc = int(eris.nocc)
-        self = cls(nocc, fock.shape[0] - nocc, device)          # packed whole first, sharded below
+        self = cls(nocc, fock.shape[0] - nocc, device, gemm=gemm, int8_digits=int8_digits,
+                   int8_min_flops=int8_min_flops)          # packed whole first, sharded below
         self.set_fock(fock)
         for name in ("oooo", "ooov", "oovv", "ovvv"):
             t = torch.from_numpy(np.ascontiguousarray(getattr(eris, name), dtype=np.float64)).to(self.device)
@@ -143,25 +170,84 @@ class DeviceEris(object):
                 1, dtype=torch.float64, device=self.device)
             self.buf["vvvv_p"] = shard
             self._bind("vvvv_p", shard)
+        if self.int8_digits:
+            # a dense upload is small: the FP64 shard stays (cc_Wvvvv / Linter getters read it), the
+            # residual plans read the digit planes
+            self._cut_vvvv_planes(lambda r0, nr: self.buf["vvvv_p"][r0 * self._pv(): (r0 + nr) * self._pv()])
         for attr in ("mo_occ", "EHF", "orbspin"):
             if hasattr(eris, attr):
                 setattr(self, attr, getattr(eris, attr))
         return self
 
     @classmethod
-    def synthetic(cls, nocc, nvir, device=None, scale=0.01, rank=0, world=1, group=None):
+    def synthetic(cls, nocc, nvir, device=None, scale=0.01, rank=0, world=1, group=None, gemm=None,
+                  int8_digits=None, int8_min_flops=None, keep_fp64_vvvv=False):
         """Function-defined synthetic integrals generated in place on the device (each rank
-        generates only its own rows of the packed vvvv)."""
+        generates only its own rows of the packed vvvv).  With the INT8 engine the packed vvvv is
+        generated in row chunks and kept as digit planes only (keep_fp64_vvvv: also the FP64 layout)."""
         torch = _torch()
-        self = cls(nocc, nvir, device, rank=rank, world=world, group=group)
+        self = cls(nocc, nvir, device, rank=rank, world=world, group=group, gemm=gemm, int8_digits=int8_digits,
+                   int8_min_flops=int8_min_flops)
+        planes_only = bool(self.int8_digits) and not keep_fp64_vvvv
         for name in _LAYOUTS:
+            if name == "vvvv_p" and planes_only:
+                continue
             self._alloc_layout(name)
         self.check(lib.ecw_eris_synthetic(self._h, float(scale), self.stream()), "ecw_eris_synthetic")
+        if self.int8_digits:
+            if planes_only:
+                n0 = self._shard_rows()[0]
+                pv = self._pv()
+                chunk_rows = max(128, min(4096, (1 << 28) // max(pv, 1) // 128 * 128))     # <= 2 GiB of FP64 rows
+                tmp = torch.empty(chunk_rows * pv, dtype=torch.float64, device=self.device)
+
+                def rows(r0, nr):
+                    rc = lib.ecw_synth_tensor(SYNTH_KIND["vvvv_p"], tmp.data_ptr(), self.nocc, self.nvir, n0 + r0, nr,
+                                              float(scale), self.stream())
+                    if rc != 0:
+                        raise EcwError("ecw_synth_tensor(vvvv_p rows) failed")
+                    return tmp
+                self._cut_vvvv_planes(rows, chunk_rows)
+                del tmp
+            else:
+                self._cut_vvvv_planes(lambda r0, nr: self.buf["vvvv_p"][r0 * self._pv(): (r0 + nr) * self._pv()])
         n = self.nocc + self.nvir
         self.fock_dev = self.synth_tensor("fock", (n, n))
         self.fock = self.fock_dev.cpu().numpy()
         torch.cuda.current_stream(self.device).synchronize()
         return self
+
+    def _pv(self):
+        return self.nvir * (self.nvir - 1) // 2
+
+    def _shard_rows(self):
+        """(first row, number of rows) of this rank's shard of the packed vvvv."""
+        pv = self._pv()
+        nshmax = (pv + self.world - 1) // self.world
+        n0 = min(pv, self.rank * nshmax)
+        return n0, min(pv, n0 + nshmax) - n0
+
+    def _cut_vvvv_planes(self, rows_of, chunk_rows=None):
+        """Cut this rank's packed-vvvv rows into int8 digit planes (ecw_eris_vvvv_planes).
+        rows_of(r0, nr) -> device tensor holding the FP64 rows [r0, r0+nr) of the shard."""
+        torch = _torch()
+        nsh = self._shard_rows()[1]
+        for name, dt, unit in (("vvvv_oz", torch.int8, 8), ("vvvv_ozs", torch.float64, 1)):
+            n = lib.ecw_slot_elems(self._h, name.encode())
+            if n < 0:
+                self.check(-1, "ecw_slot_elems(%s)" % name)
+            self.buf[name] = torch.empty(max(int(n), 1) * unit, dtype=dt, device=self.device)
+            self._bind(name, self.buf[name])
+        chunk_rows = int(chunk_rows or max(nsh, 1))
+        r0 = 0
+        while True:
+            nr = min(chunk_rows, nsh - r0)
+            src = rows_of(r0, nr) if nr > 0 else self.buf["vvvv_ozs"]
+            self.check(lib.ecw_eris_vvvv_planes(self._h, src.data_ptr(), r0, nr, self.stream()), "ecw_eris_vvvv_planes")
+            r0 += nr
+            if r0 >= nsh:
+                break
+        torch.cuda.current_stream(self.device).synchronize()
 
     def synth_tensor(self, kind, shape, scale=0.01):
         """Synthetic fock / fsp / t1 / l1 / t2 / l2 on the device."""

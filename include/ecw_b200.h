@@ -54,6 +54,13 @@ const char* ecw_version(void);
  * ecw_resume until it returns 0. */
 int ecw_ctx_set_shard(ecw_ctx* ctx, int rank, int world);
 int ecw_resume(ecw_ctx* ctx, void* stream);
+/* GEMM engine.  int8_digits = 0: every contraction runs on the FP64 DMMA kernels.  int8_digits = 3..8:
+ * unbatched GEMMs with 2MNK >= min_flops (negative: all of them) run on the INT8 tcgen05 tensor pipe by
+ * error-free splitting into that many 7-bit digits (csrc/ozaki.cu; 7 digits = FP64-level accuracy,
+ * |err| <= 2^-47 K max|A_row| max|B_row|).  Replaces the BLAS dgemm behind numpy/pyscf einsum
+ * (CCSD.py:25).  A context starts with int8_digits = 0. */
+int ecw_ctx_set_gemm(ecw_ctx* ctx, int int8_digits, double min_flops);
+int ecw_ctx_get_gemm(ecw_ctx* ctx);
 int ecw_pending_collective(ecw_ctx* ctx, int64_t* desc6);
 
 /* ---- integral container (consumed type `Eris.geris`, Eris.py:132-154) ---- */
@@ -61,6 +68,7 @@ int ecw_pending_collective(ecw_ctx* ctx, int64_t* desc6);
  *   "oooo" [o,o,o,o]  "ooov" [o,o,o,v]  "oovv" [o,o,v,v]  "ovvv" [o,v,v,v]
  *   "oovv_ph" [(m,e),(n,f)] = oovv[m,n,e,f]     "ovov_ph" [(i,a),(n,f)] = ovov[n,a,i,f]
  *   "oooo_p" [ij_p,kl_p]  "oovv_p" [ij_p,ab_p]  "ovvv_p" [m,a,ef_p]  "vvvv_p" [ab_p,cd_p]
+ *   "vvvv_oz" / "vvvv_ozs": int8 digit planes / row scales of vvvv_p (ecw_eris_vvvv_planes)
  * with the antisymmetric pair index p(x<y) = y(y-1)/2 + x.  Also bindable:
  * "scal" (16 doubles of device scratch for scalars). */
 int64_t ecw_slot_elems(ecw_ctx* ctx, const char* slot);
@@ -69,6 +77,11 @@ int ecw_bind(ecw_ctx* ctx, const char* slot, void* device_ptr);
  * already on the device; "oooo","ooov","oovv","ovvv" must be bound to the dense
  * blocks themselves.  Replaces the block copies of Eris.py:132-150. */
 int ecw_eris_pack_from_dense(ecw_ctx* ctx, const double* ovov_dense, const double* vvvv_dense, void* stream);
+/* INT8 engine: the packed vvvv shard lives on the device as digit planes only.  Bind "vvvv_oz"
+ * (ecw_slot_elems x 8 bytes) and "vvvv_ozs", then pass the FP64 rows [row0, row0+nrows) of this rank's
+ * shard ([nrows, P_v], row0 a multiple of 128, every chunk but the last a multiple of 128 rows) chunk by
+ * chunk; after the last chunk the plans read the planes and "vvvv_p" need not be bound. */
+int ecw_eris_vvvv_planes(ecw_ctx* ctx, const double* rows, int64_t row0, int64_t nrows, void* stream);
 /* Fill every bound integral layout with the function-defined synthetic
  * integrals (DESIGN.md "Synthetic inputs"); dense vvvv never exists. */
 int ecw_eris_synthetic(ecw_ctx* ctx, double scale, void* stream);
@@ -142,6 +155,9 @@ int ecw_op_dot(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const ecw_tensor
 int64_t ecw_op_workspace_needed(ecw_ctx* ctx);
 
 /* ---- introspection / test hooks ---------------------------------------------- */
+/* Host-only test hook: plan as if ecw_eris_vvvv_planes had completed (so the lowering of the
+ * digit-plane ladders can be dumped and replayed on a box without a GPU). */
+int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* ctx);
 /* JSON dump of the op list a call would launch (host only, no CUDA). */
 int64_t ecw_plan_dump(ecw_ctx* ctx, const char* func, int mode_flags, char* buf, int64_t buflen);
 /* executed GEMM flops (sum of 2MNK) and launches of a plan */
@@ -162,6 +178,10 @@ int64_t ecw_ozaki_plane_bytes(int64_t R, int64_t K, int ns);
 int64_t ecw_ozaki_padded_rows(int64_t R);
 int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes, double* scale,
                     void* stream);
+/* chunked cut: X holds rows [row0, row0+R) of an operand of total_rows rows (row0 and every chunk but the
+ * last multiples of 128); planes/scale address the whole plane set */
+int ecw_ozaki_split_rows(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes,
+                         double* scale, int64_t row0, int64_t total_rows, void* stream);
 int ecw_ozaki_gemm(const void* planes_a, const double* scale_a, const void* planes_b, const double* scale_b, int64_t M,
                    int64_t N, int64_t K, double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns,
                    void* stream);

@@ -33,3 +33,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=["int8", "int8_all", "dmma"])
+def engine(request, monkeypatch):
+    """GEMM engine of the contraction plans: "int8" = product default (large GEMMs and the packed-vvvv
+    ladders on the INT8 tcgen05 pipe), "int8_all" = every unbatched GEMM forced onto it, "dmma" = FP64
+    DMMA kernels only.  Parity tests run under all three."""
+    monkeypatch.setenv("ECW_GEMM", "dmma" if request.param == "dmma" else "int8")
+    monkeypatch.setenv("ECW_INT8_MIN_FLOPS", "-1" if request.param == "int8_all" else "2e10")
+    return request.param

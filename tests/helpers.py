@@ -13,11 +13,18 @@ def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name)))
 
 
-def plan_json(lib, o, v, func, flags, rank=0, world=1):
+def plan_json(lib, o, v, func, flags, rank=0, world=1, int8_digits=0, min_flops=-1.0, vvvv_planes=False):
+    """Plan of one call.  int8_digits > 0: INT8 tensor-core engine for every unbatched GEMM with
+    2MNK >= min_flops; vvvv_planes: the packed vvvv is bound as digit planes (needs a device for the
+    real entry point, so the flag is flipped through the test hook ecw_ctx_test_assume_vvvv_planes)."""
     h = ctypes.c_void_p()
     assert lib.ecw_ctx_create(ctypes.byref(h), o, v) == 0
     if world > 1:
         assert lib.ecw_ctx_set_shard(h, rank, world) == 0
+    if int8_digits:
+        assert lib.ecw_ctx_set_gemm(h, int8_digits, float(min_flops)) == 0
+        if vvvv_planes:
+            assert lib.ecw_ctx_test_assume_vvvv_planes(h) == 0
     try:
         n = 1 << 24
         buf = ctypes.create_string_buffer(n)

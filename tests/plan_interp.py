@@ -21,6 +21,50 @@ def pair_decode(n):
     return lo, hi
 
 
+# ---- INT8-pipe GEMM (csrc/ozaki.cu): numpy statement of the digit cut and the device plane order
+def oz_scale(X):
+    mx = np.abs(X).max(axis=1) if X.shape[1] else np.zeros(X.shape[0])
+    _, e = np.frexp(mx)
+    return np.where(mx > 0, np.ldexp(1.0, e - 6), 1.0)
+
+
+def oz_digits(X, ns):
+    s = oz_scale(X)
+    x = X / s[:, None]
+    out = []
+    for _ in range(ns):
+        d = np.rint(x)
+        x = (x - d) * 128.0
+        out.append(d.astype(np.int8))
+    return np.stack(out), s
+
+
+def oz_to_planes(D):
+    """digits [ns][R][K] -> device order [kb][p][rg][j][ri][16], rows padded to 128, k to 32 (flat int8)."""
+    ns, R, K = D.shape
+    Rp, Kp = (R + 127) // 128 * 128, (K + 31) // 32 * 32
+    P = np.zeros((ns, Rp, Kp), dtype=np.int8)
+    P[:, :R, :K] = D
+    return np.ascontiguousarray(P.reshape(ns, Rp // 8, 8, Kp // 32, 2, 16).transpose(3, 0, 1, 4, 2, 5)).reshape(-1)
+
+
+def oz_from_planes(buf, ns, R, K):
+    Rp, Kp = (R + 127) // 128 * 128, (K + 31) // 32 * 32
+    P = buf[: ns * Rp * Kp].reshape(Kp // 32, ns, Rp // 8, 2, 8, 16).transpose(1, 2, 4, 0, 3, 5).reshape(ns, Rp, Kp)
+    return P[:, :R, :K]
+
+
+def oz_const_slots(X, ns):
+    """(planes, scales) slot arrays for a constant operand X[R,K] (what ecw_eris_vvvv_planes leaves bound)."""
+    D, s = oz_digits(X, ns)
+    pl = oz_to_planes(D)
+    pad = (-pl.size) % 8
+    pl = np.concatenate([pl, np.zeros(pad, np.int8)]).view(np.float64).copy()
+    sc = np.ones((X.shape[0] + 127) // 128 * 128)
+    sc[: X.shape[0]] = s
+    return pl, sc
+
+
 class Interp(object):
     def __init__(self, plan_json, slots, alpha=0.0, allgather=None):
         self.allgather = allgather      # callable(send ndarray, recv ndarray) for multi-rank plans
@@ -105,6 +149,42 @@ class Interp(object):
         recv = ws[op["c"]["off"]: op["c"]["off"] + world * count]
         assert self.allgather is not None, "multi-rank plan needs an allgather callable"
         self.allgather(send, recv)
+
+    def _bytes(self, t):
+        return self.slots[t["slot"]].reshape(-1).view(np.int8)[8 * t["off"]:]
+
+    def op_oz_split(self, op):
+        a = op["a"]
+        R, K, ns = op["M"], op["K"], op["i0"]
+        X = self._mat(a["slot"], a["off"], R, K, op["lda"], op["ldb"])
+        assert not np.isnan(X).any(), op["note"]
+        D, s = oz_digits(np.array(X), ns)
+        pl = oz_to_planes(D)
+        assert pl.size <= 8 * op["c"]["dim"][0], op["note"]
+        self._bytes(op["c"])[: pl.size] = pl
+        sc = self.view(op["d"])
+        assert sc.shape[0] == (R + 127) // 128 * 128
+        sc[...] = 1.0
+        sc[:R] = s
+
+    def op_oz_gemm(self, op):
+        M, N, K, ns = op["M"], op["N"], op["K"], op["i0"]
+        DA = oz_from_planes(self._bytes(op["a"]), ns, M, K).astype(np.float64)
+        DB = oz_from_planes(self._bytes(op["b"]), ns, N, K).astype(np.float64)
+        sa, sb = self.view(op["d"])[:M], self.view(op["e"])[:N]
+        assert not np.isnan(sa).any() and not np.isnan(sb).any(), op["note"]
+        acc = np.zeros((M, N))
+        for w in range(ns - 1, -1, -1):          # Horner over the weights, as the device epilogue
+            part = np.zeros((M, N))
+            for p in range(w + 1):
+                part += DA[p] @ DB[w - p].T       # exact: integers far below 2^53
+            acc = acc * 0.0078125 + part
+        c = op["c"]
+        C = self._mat(c["slot"], c["off"], M, N, op["i1"], op["i2"])
+        res = (op["alpha"] * sa)[:, None] * sb[None, :] * acc
+        if op["beta"] != 0.0:
+            res = res + op["beta"] * C
+        C[...] = res
 
     def op_fill(self, op):
         self.view(op["c"])[...] = op["alpha"]

@@ -19,7 +19,7 @@ def _mod(cc):
 
 
 @pytest.mark.parametrize("name", ["ccs_o4v6.npz", "ccs_o6v9.npz"])
-def test_ccs_matches_golden(built_lib, name):
+def test_ccs_matches_golden(built_lib, name, engine):
     import ecw_cc_b200 as ecw
     from oracle import synth
     from oracle.make_golden import ccs_calls
@@ -33,7 +33,7 @@ def test_ccs_matches_golden(built_lib, name):
 
 
 @pytest.mark.parametrize("ov", [(3, 5), (7, 12), (10, 34)])
-def test_ccs_matches_oracle(built_lib, ov):
+def test_ccs_matches_oracle(built_lib, ov, engine):
     import ecw_cc_b200 as ecw
     from oracle import synth, ccs_np
     from oracle.make_golden import ccs_calls, ccs_inputs

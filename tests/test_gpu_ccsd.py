@@ -62,7 +62,7 @@ def test_synthetic_tensors_bit_exact(ecw):
     from oracle import synth
     from oracle import refactored_np as R
     o, v = 5, 9
-    de = ecw.DeviceEris.synthetic(o, v)
+    de = ecw.DeviceEris.synthetic(o, v, gemm="int8", keep_fp64_vvvv=True)
     er = synth.SynthEris(o, v)
     E = R.DeviceErisSpec(er)
     host = dict(oooo=E.oooo, ooov=E.ooov, oovv=E.oovv, ovvv=E.ovvv, oovv_ph=E.oovv_ph, ovov_ph=E.ovov_ph,
@@ -71,6 +71,14 @@ def test_synthetic_tensors_bit_exact(ecw):
         got = de.buf[name].cpu().numpy()[: ref.size].reshape(ref.shape)
         assert np.array_equal(got, ref), name
     assert np.array_equal(de.fock, synth.fock(o, v))
+    # digit planes of the packed vvvv (INT8 engine): cut from the FP64 layout, or generated in row
+    # chunks without it — both bit-identical to the numpy statement of the cut
+    from plan_interp import oz_const_slots
+    pl, sc = oz_const_slots(E.vvvv_p, de.int8_digits)
+    for d2 in (de, ecw.DeviceEris.synthetic(o, v, gemm="int8")):
+        assert np.array_equal(d2.buf["vvvv_oz"].cpu().numpy()[: pl.size * 8], pl.view(np.int8))
+        assert np.array_equal(d2.buf["vvvv_ozs"].cpu().numpy(), sc)
+    assert "vvvv_p" not in d2.buf
     n = o + v
     t1, t2, l1, l2 = synth.amplitudes(o, v)
     assert np.array_equal(de.synth_tensor("fsp", (n, n)).cpu().numpy(), synth.fsp(o, v))
@@ -81,7 +89,7 @@ def test_synthetic_tensors_bit_exact(ecw):
 
 
 @pytest.mark.parametrize("ov", [(2, 3), (4, 6), (5, 7), (6, 11), (8, 20), (10, 33)])
-def test_ccsd_matches_oracle(ecw, ov):
+def test_ccsd_matches_oracle(ecw, ov, engine):
     from oracle import synth
     from oracle.ccsd_np import OracleGCC
     o, v = ov
@@ -110,7 +118,7 @@ def test_ccsd_matches_oracle(ecw, ov):
 
 
 @pytest.mark.parametrize("name", ["ccsd_o4v6.npz", "ccsd_o5v8.npz"])
-def test_ccsd_matches_golden(ecw, name):
+def test_ccsd_matches_golden(ecw, name, engine):
     """Against outputs of the reference itself (tests/golden, made by oracle/make_golden.py)."""
     from oracle import synth
     g = load_golden(name)
@@ -134,7 +142,7 @@ def test_ccsd_matches_golden(ecw, name):
     assert np.abs(a - g["rawL1"]).max() < TOL and np.abs(b - g["rawL2"]).max() < TOL
 
 
-def test_device_resident_and_synthetic_eris(ecw):
+def test_device_resident_and_synthetic_eris(ecw, engine):
     """torch tensors in -> torch tensors out; synthetic device eris == uploaded eris."""
     import torch
     from oracle import synth
@@ -160,7 +168,7 @@ def test_device_resident_and_synthetic_eris(ecw):
 
 
 @pytest.mark.parametrize("ov", [(3, 4), (5, 9), (8, 21)])
-def test_general_path_unsymmetric_amplitudes(ecw, ov):
+def test_general_path_unsymmetric_amplitudes(ecw, ov, engine):
     """t2/l2 without permutational symmetry (what the reference's L1 update produces, Q1):
     the host measures the antisymmetry defect on the device and runs the general path."""
     from oracle import synth
@@ -191,7 +199,7 @@ def test_general_path_unsymmetric_amplitudes(ecw, ov):
 
 
 @pytest.mark.parametrize("ov", [(4, 6), (6, 11)])
-def test_gcc_intermediate_getters(ecw, ov):
+def test_gcc_intermediate_getters(ecw, ov, engine):
     """make_tau, cc_Fvv/Foo/Fov, cc_Woooo/Wvvvv/Wovvo, Linter, gamma_inter (CCSD.py:165-182, 346-413, 543-623)."""
     from oracle import synth
     from oracle.ccsd_np import OracleGCC
@@ -225,7 +233,7 @@ def test_subdiff_kernel(ecw):
         ecw.subdiff(np.zeros(3), np.zeros(4), 0.1)
 
 
-def test_solver_iterations_track_oracle(ecw):
+def test_solver_iterations_track_oracle(ecw, engine):
     """Body of Solver_CCSD.SCF (Solver_GS.py:683-705) driven by the GPU object vs the oracle:
     gamma -> energy -> tupdate -> lupdate with warm-started amplitudes, with and without L1."""
     from oracle import synth
@@ -253,7 +261,7 @@ def test_solver_iterations_track_oracle(ecw):
                 assert np.abs(np.asarray(x) - np.asarray(y)).max() < TOL, (alpha, it)
 
 
-def test_size_independent_properties(ecw):
+def test_size_independent_properties(ecw, engine):
     """At a size the oracle would need minutes for: antisymmetry of the doubles residuals,
     tupdate(alpha=0) == tupdate(alpha=None) (CCSD.py:732-739), tr(gamma)=nocc, gamma symmetric,
     and the soft-threshold identity  subdiff(eq-mode output) applied by hand == L1-equation mode."""

@@ -13,12 +13,12 @@ import torch.multiprocessing as mp
 from helpers import plan_json, eris_slots, flags_of
 from oracle import synth
 from oracle.ccsd_np import OracleGCC
-from plan_interp import Interp
+from plan_interp import Interp, oz_const_slots
 
 TOL = 1e-13
 
 
-def _worker(rank, world, port, o, v, antisym, q):
+def _worker(rank, world, port, o, v, antisym, q, int8=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -39,6 +39,9 @@ def _worker(rank, world, port, o, v, antisym, q):
         n0, n1 = min(pv, rank * nshmax), min(pv, (rank + 1) * nshmax)
         base["vvvv_p"] = np.ascontiguousarray(base["vvvv_p"][n0:n1])        # this rank's rows only
         base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=fsp, fock=er.fock.copy())
+        if int8:      # INT8 engine: the rank's shard is bound as digit planes, every unbatched GEMM on that route
+            base["vvvv_oz"], base["vvvv_ozs"] = oz_const_slots(base["vvvv_p"], int8)
+            base["vvvv_p"] = np.full(1, np.nan)
 
         def allgather(send, recv):
             out = torch.from_numpy(recv)
@@ -49,7 +52,8 @@ def _worker(rank, world, port, o, v, antisym, q):
         ncoll = 0
         for alpha, eq in ((None, False), (1e-3, True)):
             for fn in ("tupdate", "lupdate"):
-                pl = plan_json(lib, o, v, fn, flags_of(alpha, eq, antisym), rank=rank, world=world)
+                pl = plan_json(lib, o, v, fn, flags_of(alpha, eq, antisym), rank=rank, world=world, int8_digits=int8,
+                               vvvv_planes=bool(int8))
                 ncoll += sum(1 for op in pl["ops"] if op["kind"] == "allgather")
                 sl = dict(base)
                 sl["out1"] = np.full((o, v), np.nan)
@@ -64,13 +68,13 @@ def _worker(rank, world, port, o, v, antisym, q):
 
 
 @pytest.mark.parametrize("antisym", [True, False])
-@pytest.mark.parametrize("world,ov", [(2, (4, 6)), (2, (5, 7)), (3, (5, 7))])
-def test_sharded_plans_match_oracle(built_lib, world, ov, antisym):
+@pytest.mark.parametrize("world,ov,int8", [(2, (4, 6), 0), (2, (5, 7), 0), (3, (5, 7), 0), (2, (5, 7), 7)])
+def test_sharded_plans_match_oracle(built_lib, world, ov, antisym, int8):
     o, v = ov
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + 7 * world + (3 if antisym else 0) + o
-    procs = [ctx.Process(target=_worker, args=(r, world, port, o, v, antisym, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + 7 * world + (3 if antisym else 0) + o + (11 if int8 else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, o, v, antisym, q, int8)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
@@ -78,5 +82,5 @@ def test_sharded_plans_match_oracle(built_lib, world, ov, antisym):
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, worst, ncoll in res:
-        assert worst < TOL, (rank, worst)
+        assert worst < (1e-12 if int8 else TOL), (rank, worst)
         assert ncoll >= 10          # K1/K2 ladders, R1-R4, R6-R9 are distributed

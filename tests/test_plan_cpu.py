@@ -137,3 +137,83 @@ def test_north_star_plan_has_no_integral_permutes(built_lib):
         total += pl["gemm_flops"]
     assert total < 9.93e13          # F_alg of SURVEY.md §8(d)
     assert total > 5e13
+
+
+# ---------------------------------------------------------------- INT8 tensor-core engine (csrc/ozaki.cu)
+from plan_interp import oz_const_slots
+
+
+def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_planes=True):
+    orc = OracleGCC(er)
+    base = eris_slots(er)
+    base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=fsp, fock=er.fock.copy())
+    if vvvv_planes:
+        base["vvvv_oz"], base["vvvv_ozs"] = oz_const_slots(base["vvvv_p"], ns)
+        base["vvvv_p"] = np.full(1, np.nan)          # FP64 vvvv is not bound in this mode
+    worst = 0.0
+    n_oz = 0
+    for tag, alpha, eq in MODES:
+        for fn in ("tupdate", "lupdate"):
+            pl = plan_json(built_lib, o, v, fn, flags_of(alpha, eq, antisym=antisym), int8_digits=ns, min_flops=-1.0,
+                           vvvv_planes=vvvv_planes)
+            n_oz += sum(op["kind"] == "oz_gemm" for op in pl["ops"])
+            sl = dict(base)
+            sl["out1"] = np.full((o, v), np.nan)
+            sl["out2"] = np.full((o, o, v, v), np.nan)
+            Interp(pl, sl, alpha=alpha or 0.0).run()
+            if fn == "tupdate":
+                ref = orc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq)
+            else:
+                ref = orc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq)
+            worst = max(worst, np.abs(sl["out1"] - ref[0]).max(), np.abs(sl["out2"] - ref[1]).max())
+    assert n_oz > 0
+    assert worst < tol, worst
+    return worst
+
+
+@pytest.mark.parametrize("ov", [(3, 4), (4, 6), (6, 11)])
+def test_int8_engine_plans_match_oracle(built_lib, ov):
+    """Every unbatched GEMM forced onto the digit-plane route (7 digits), packed vvvv bound as planes:
+    the replayed plan (exact integer arithmetic in numpy) matches the oracle far below the 1e-10 bar."""
+    o, v = ov
+    er = synth.SynthEris(o, v)
+    t1, t2, l1, l2 = synth.amplitudes(o, v)
+    _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, True, 7, 1e-12)
+
+
+def test_int8_engine_general_path_and_digit_count(built_lib):
+    o, v = 4, 7
+    er = synth.SynthEris(o, v)
+    rng = np.random.default_rng(5)
+    t1, l1 = 0.05 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, v))
+    t2, l2 = 0.02 * rng.standard_normal((o, o, v, v)), 0.02 * rng.standard_normal((o, o, v, v))
+    e7 = _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, False, 7, 1e-12)
+    e8 = _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, False, 8, 1e-12, vvvv_planes=False)
+    # fewer digits = a coarser product: the truncation error is visible and grows by ~2^7 per digit
+    o4 = OracleGCC(er)
+    base = eris_slots(er)
+    base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=synth.fsp(o, v), fock=er.fock.copy())
+    sl = dict(base)
+    sl["out1"], sl["out2"] = np.full((o, v), np.nan), np.full((o, o, v, v), np.nan)
+    Interp(plan_json(built_lib, o, v, "tupdate", flags_of(None, True, antisym=False), int8_digits=4), sl).run()
+    ref = o4.tupdate(t1, t2, fsp=synth.fsp(o, v), equation=True)
+    e4 = np.abs(sl["out2"] - ref[1]).max()
+    assert e4 > 100 * max(e7, e8, 1e-16) and e4 < 1e-5
+
+
+def test_int8_engine_north_star_plan(built_lib):
+    """(40,400) with the default threshold: both ladders, the five o^3v^3 rings and R4/R6/R9 run on the
+    INT8 pipe (> 90 % of the flops); the vvvv planes replace the FP64 layout; everything fits one B200."""
+    o, v = 40, 400
+    oz = tot = 0.0
+    for fn in ("tupdate", "lupdate"):
+        pl = plan_json(built_lib, o, v, fn, 4, int8_digits=7, min_flops=2e10, vvvv_planes=True)
+        assert pl["workspace_elems"] * 8 < 45e9
+        oz += pl["oz_flops"]
+        tot += pl["gemm_flops"]
+        for op in pl["ops"]:
+            for k in "abcde":
+                assert not (op[k] and op[k]["slot"] == "vvvv_p"), op["note"]
+        big = [op for op in pl["ops"] if op["kind"] == "gemm" and 2.0 * op["M"] * op["N"] * op["K"] * op["batch"] / op["splitk"] > 5e11]
+        assert not big, [b["note"] for b in big]
+    assert oz / tot > 0.9

@@ -1,5 +1,5 @@
 """Per-op device timing of one CCSD T+Lambda residual evaluation (CUDA events around every
-launch of the plan).  Usage: python tools/profile_eval.py NOCC NVIR out.json"""
+launch of the plan).  Usage: python tools/profile_eval.py NOCC NVIR [out.json] [int8|dmma] [digits]"""
 import ctypes, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +8,10 @@ from ecw_cc_b200 import lib
 
 o, v = int(sys.argv[1]), int(sys.argv[2])
 t0 = time.time()
-de = ecw.DeviceEris.synthetic(o, v)
+gemm = sys.argv[4] if len(sys.argv) > 4 else None
+digits = int(sys.argv[5]) if len(sys.argv) > 5 else None
+de = ecw.DeviceEris.synthetic(o, v, gemm=gemm, int8_digits=digits)
+print("gemm engine: %s" % ("int8, %d digits" % de.int8_digits if de.int8_digits else "dmma"), flush=True)
 torch.cuda.synchronize()
 print("eris ready %.1fs, mem %.1f GB" % (time.time() - t0, torch.cuda.memory_allocated() / 1e9), flush=True)
 cc = ecw.GCC(de)
@@ -35,9 +38,9 @@ for name, fn in (("tupdate", lambda: cc.tupdate(t1, t2, fsp=fsp)), ("lupdate", l
         bykind[x["kind"]] = bykind.get(x["kind"], 0.0) + x["ms"]
     print("   by kind:", {k: round(val, 1) for k, val in sorted(bykind.items(), key=lambda kv: -kv[1])})
     for x in sorted(ops, key=lambda x: -x["ms"])[:22]:
-        fl = 2.0 * x["M"] * x["N"] * x["K"] * x["batch"] / max(x["splitk"], 1) if x["kind"] == "gemm" else 0
+        fl = 2.0 * x["M"] * x["N"] * x["K"] * x["batch"] / max(x["splitk"], 1) if x["kind"] in ("gemm", "oz_gemm") else 0
         print("   %8.2f ms %-8s M%-7d N%-7d K%-8d b%-5d %6.1f TF  %s" % (x["ms"], x["kind"], x["M"], x["N"], x["K"], x["batch"], fl / max(x["ms"], 1e-9) / 1e9, x["note"]))
     res[name] = {"ms": s.elapsed_time(e), "ops": ops}
 print("peak mem %.1f GB" % (torch.cuda.max_memory_allocated() / 1e9))
-if len(sys.argv) > 3:
+if len(sys.argv) > 3 and sys.argv[3] != "-":
     json.dump(res, open(sys.argv[3], "w"))
