@@ -179,6 +179,19 @@ def measure_fp64_peak(torch, n=8192, reps=5):
     return 2.0 * n ** 3 / best / 1e9
 
 
+def ncu_traffic():
+    """dram bytes read+written by the dominant launch, from the committed ncu --set full capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_int8_ladder_ncu_summary.json")))
+        rd, wr = d["dram__bytes_read.sum"].split(), d["dram__bytes_write.sum"].split()
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        return {"bytes_per_launch": float(rd[0]) * unit[rd[1]] + float(wr[0]) * unit[wr[1]],
+                "algorithmic_bytes_per_launch": 3.86e10 + 0.5e9,
+                "source": "profiles/r1_int8_ladder_ncu_summary.json (ncu --set full, same launch)"}
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -302,7 +315,7 @@ def run_ours(args):
                     "kernel": "ecw::ozaki_gemm_kernel<%d> (tcgen05.mma kind::i8, TMEM accumulators), launch = packed "
                               "pp-ladder %dx%dx%d (CCSD.py:305)" % (ns, ladder["M"], ladder["N"], ladder["K"]),
                     "achieved": fp64_equiv * nprod, "peak": int8_peak, "unit": "TOP/s (int8 dense)",
-                    "frac": fp64_equiv * nprod / int8_peak, "traffic": None,
+                    "frac": fp64_equiv * nprod / int8_peak, "traffic": ncu_traffic(),
                     "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst %.1f): the INT8 dense rate of the "
                                     "tcgen05 pipe is twice the bf16 rate (nominal 4500 vs 2250)" % bf16) if bf16 > 0
                     else "nominal INT8 dense 4500 TOP/s (B200_PROFILING.md fallback)",

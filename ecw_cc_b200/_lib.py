@@ -18,20 +18,34 @@ class EcwError(RuntimeError):
 
 
 def build(force=False, verbose=False):
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", s) for s in _SRC]
-    deps = srcs + [os.path.join(_HERE, "csrc", h) for h in ("plan.h", "kernels.h", "ccsd_plan.h")]
-    deps.append(os.path.join(_HERE, "..", "include", "ecw_b200.h"))
-    if not force and os.path.exists(LIB_PATH):
-        mt = os.path.getmtime(LIB_PATH)
-        if all(os.path.getmtime(d) <= mt for d in deps):
-            return LIB_PATH
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU).
+    One object per source under csrc/build/ (recompiled only when stale), then one link."""
+    csrc = os.path.join(_HERE, "csrc")
+    hdrs = [os.path.join(csrc, h) for h in ("plan.h", "kernels.h", "ccsd_plan.h")]
+    hdrs.append(os.path.join(_HERE, "..", "include", "ecw_b200.h"))
+    hdr_mt = max(os.path.getmtime(h) for h in hdrs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"] + srcs + ["-o", LIB_PATH]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+             "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+    bdir = os.path.join(csrc, "build")
+    os.makedirs(bdir, exist_ok=True)
+    objs, jobs = [], []
+    for s in _SRC:
+        src, obj = os.path.join(csrc, s), os.path.join(bdir, s + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_mt):
+            cmd = [nvcc] + flags + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd))
+            jobs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in jobs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    if jobs or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB_PATH]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
     return LIB_PATH
 
 
@@ -81,6 +95,8 @@ class _Lib(object):
             "ecw_dgemm": (c_i, [c_i, c_i, c_l, c_l, c_l, c_d, c_p, c_l, c_p, c_l, c_d, c_p, c_l, c_i, c_p]),
             "ecw_ozaki_plane_bytes": (c_l, [c_l, c_l, c_i]),
             "ecw_ozaki_padded_rows": (c_l, [c_l]),
+            "ecw_ozaki_stat_elems": (c_l, [c_l]),
+            "ecw_ozaki_tile_n": (c_i, [c_i]),
             "ecw_ozaki_split": (c_i, [c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p, c_p]),
             "ecw_ozaki_split_rows": (c_i, [c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p, c_l, c_l, c_p]),
             "ecw_ozaki_gemm": (c_i, [c_p, c_p, c_p, c_p, c_l, c_l, c_l, c_p, c_l, c_l, c_d, c_d, c_i, c_p]),

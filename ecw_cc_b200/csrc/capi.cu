@@ -62,7 +62,7 @@ int64_t slot_elems(const Sizes& z, int s) {
       const int64_t n0 = std::min<int64_t>(pv, (int64_t)z.rank * nshmax);
       const int64_t nsh = std::min<int64_t>(pv, n0 + nshmax) - n0;
       if (s == S_VVVV_P) return nsh * pv;
-      if (s == S_VVVV_OZS) return ozaki_padded_rows(nsh);
+      if (s == S_VVVV_OZS) return 2 * ozaki_padded_rows(nsh);       // [row scales | row sums]
       return (ozaki_plane_bytes(nsh, pv, z.oz_ns > 0 ? z.oz_ns : 7) + 7) / 8;   // in 8-byte units
     }
     default: return -1;
@@ -561,6 +561,8 @@ int ecw_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, con
 // ---- FP64 GEMM on the INT8 tcgen05 pipe (ozaki.cu): raw entry points for tools/ and tests/
 int64_t ecw_ozaki_plane_bytes(int64_t R, int64_t K, int ns) { return ozaki_plane_bytes(R, K, ns); }
 int64_t ecw_ozaki_padded_rows(int64_t R) { return ozaki_padded_rows(R); }
+int64_t ecw_ozaki_stat_elems(int64_t R) { return 2 * ozaki_padded_rows(R); }
+int ecw_ozaki_tile_n(int ns) { return ozaki_tile_n(ns); }
 
 int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes, double* scale,
                     void* stream) {

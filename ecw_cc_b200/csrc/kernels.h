@@ -23,7 +23,9 @@ cudaError_t launch_gemm_tma(const GemmArgs& a, cudaStream_t st, int cfg);
 
 // FP64 GEMM by error-free splitting on the INT8 tcgen05 tensor pipe (ozaki.cu).
 // An operand X[R,K] (element (r,k) at X[r*rs + k*ks], one of rs/ks == 1) is cut into `ns` int8 digit
-// planes (ozaki_plane_bytes) plus one FP64 scale per padded row (ozaki_padded_rows doubles).
+// planes (ozaki_plane_bytes) plus row statistics `scale` = [2^e scales | row sums / scale], each
+// ozaki_padded_rows doubles long.
+int ozaki_tile_n(int ns);
 int64_t ozaki_padded_rows(int64_t R);
 int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns);
 // row0/total_rows: X holds rows [row0, row0+R) of an operand of total_rows rows whose plane set is cut chunk

@@ -2,36 +2,43 @@
 //
 // Blackwell's tcgen05 path has no FP64 kind; the native FP64 tensor instruction is the legacy DMMA
 // (gemm_tma.cu, 37 TFLOP/s pipe peak).  The large contractions of the CC residual (CCSD.py:305 ladder,
-// :411 ring, :602 Lambda intermediates) are instead evaluated with an error-free splitting (Ozaki
-// scheme I) on the INT8 tensor pipe (4.5 POP/s):
+// :411 ring, :602 Lambda intermediates) are instead evaluated by splitting the FP64 operands into int8
+// digits (Ozaki scheme I) and multiplying the digit planes on the INT8 tensor pipe (4.5 POP/s nominal):
 //
-//   row r of an operand X[R,K] is scaled by 2^e_r (|X[r,:]| < 2^e_r) and cut into NS signed digits
-//   of 7 bits (the first of 6):  X[r,k] = s_r * sum_p d_p[r,k] * 128^-p,  s_r = 2^(e_r-6),
-//   d_p in [-64, 64] (int8).  Every step of the cut is exact in FP64.
-//   C[m,n] = sA_m sB_n * sum_{p+q<NS} 128^-(p+q) * (A_p . B_q^T)[m,n]      (triangular truncation)
-//   Each int8 product A_p . B_q^T is exact in the int32 accumulator (|d d'| <= 2^12, flushed to FP64
-//   every 32768 k, at most NS products per accumulator: < 2^31).  The only approximation is the
-//   truncation p+q >= NS: |dC| <= (NS+1)/4 * 2^-(7 NS - 2) * K * 2^(e_m + f_n)  — for NS = 7 that is
-//   2^-47 relative to K*rowmax*colmax, i.e. at the FP64 rounding level of the DMMA result itself.
+//   row r of an operand X[R,K]:  s_r = 2^e_r with |X[r,:]| < s_r;  y = (X[r,k]/s_r + 1)/2 in [0,1) is
+//   written in base 256,  y = sum_{p=1..NS} u_p 256^-p,  u_p in [0,255] (last digit rounded to nearest),
+//   and stored as the int8 digit  d_p = u_p - 128.  The offsets cancel the "-1" almost exactly:
+//       X[r,k] = s_r (2 D + c) + delta,   D = sum_p d_p 256^-p,  c = sum_{p=1..NS-1} 256^-p,
+//       |delta| <= s_r 256^-NS (2 s_r 256^-NS when the rounded last digit is clamped at 255).
+//       (8 bits per int8 digit: NS = 6 digits carry 48 bits.)
+//   C[m,n] = sA_m sB_n sum_k (2 Da + c)(2 Db + c) = sA_m sB_n ( 4 P[m,n] + c (tA_m + tB_n) - c^2 K ),
+//       P = sum_k Da Db  ~  sum_{p+q <= NS+1} 256^-(p+q) (A_p . B_q^T)      (triangular truncation),
+//       t_r = sum_k X[r,k] / s_r  (FP64 row sums, taken while looking for the row maximum).
+//   Every int8 product A_p . B_q^T is exact in the int32 accumulator (|d d'| <= 2^14; the accumulators
+//   are drained to FP64 every 8192 k, at most NS products each: < 2^31).  Worst-case error: representation
+//   4 K 256^-NS + truncation (NS-1) K 256^-NS, relative to sA_m sB_n (< 4 max|A_m| max|B_n|): for NS = 6
+//   that is 2^-44.8 K sA sB; observed 1e-14 at 8192^3 on N(0,1) data — the size of the rounding error of a
+//   DMMA/FMA dot product of that length.
+//   NS(NS+1)/2 int8 products replace one FP64 product: 21 at NS = 6.
+//   K-padding holds d = 0 (D = 0 contributes nothing to P; the rank-one terms use the true K).
 //
 // Data layout (memory laid out for the MMA, not for the host): an operand is stored as *digit planes*
 //   planes[kb][p][rg][j][ri][16]   kb = k/32, p = digit, rg = r/8, j = (k%32)/16, ri = r%8
 // i.e. for a fixed (k-block, digit) all rows are contiguous in the tcgen05 "no-swizzle K-major" core
 // matrix order (8 rows x 16 bytes = 128 contiguous bytes; SBO = 256 B between 8-row groups, LBO =
 // 128 B between the two 16-byte k-chunks).  A 128-row A tile of one digit is ONE contiguous 4 KB span,
-// a 64-row B tile a 2 KB span: the producer streams them with linear bulk TMA (cp.async.bulk), no
+// a TN-row B tile a TN*32-byte span: the producer streams them with linear bulk TMA (cp.async.bulk), no
 // tensor maps, no swizzle, and any operand can serve on either side.  Rows are padded to 128, k to 32.
 //
-// Kernel (one CTA per SM, persistent over 128x64 output tiles, 192 threads):
-//   warp 0   lane 0: TMA producer — per k-block one stage = NS A-planes + NS B-planes (42 KB at NS=7),
-//                    5-stage mbarrier ring;
+// Kernel (one CTA per SM, persistent over 128 x TN output tiles, 192 threads; TN = 80 at NS = 6):
+//   warp 0   lane 0: TMA producer — per k-block one stage = NS A-planes + NS B-planes, mbarrier ring;
 //   warp 1   lane 0: MMA issuer — tcgen05.mma kind::i8 (s8 x s8 -> s32, M128 K32); product (p,q)
-//                    accumulates into TMEM columns [64(p+q), 64(p+q)+64): all products of one weight share
+//                    accumulates into TMEM columns [TN(p+q), TN(p+q)+TN): all products of one weight share
 //                    an accumulator and all NS digits of A and B are loaded once per k-block.  Digits
 //                    q = 0..NS-1-p of B are contiguous in shared memory, so they are issued as one MMA of
-//                    N = 64 (NS-p) columns (split at 256): 10 instructions per stage at NS = 7;
-//   warps 2-5      : epilogue — tcgen05.ld the NS accumulators, Horner in FP64
-//                    (acc_d + 2^-7 (acc_{d+1} + ...)), scale by sA sB alpha, add beta C, store.
+//                    N = TN (NS-p) columns (split at 256);
+//   warps 2-5      : epilogue — tcgen05.ld the NS accumulators, Horner in FP64, rank-one terms, scales,
+//                    alpha/beta, store (coalesced across lanes when the tile rows are contiguous in C).
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -44,8 +51,7 @@ namespace {
 
 constexpr int OZ_BK = 32;        // k per stage = K of one kind::i8 MMA
 constexpr int OZ_TM = 128;       // tile rows  (MMA M)
-constexpr int OZ_TN = 64;        // tile cols  (MMA N); NS accumulators of 64 columns fit TMEM's 512
-constexpr int OZ_KFLUSH = 32768; // int32 accumulators are drained to FP64 at least every OZ_KFLUSH k
+constexpr int OZ_KFLUSH = 8192;  // int32 accumulators are drained to FP64 every OZ_KFLUSH k (8 * 2^13 * 2^14 <= 2^30)
 constexpr int OZ_SMEM_MAX = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,24 +122,32 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 struct OzGemmParams {
   const int8_t* pa;      // digit planes of the M-side operand
   const int8_t* pb;      // digit planes of the N-side operand
-  const double* sa;      // row scales 2^(e-6), length Mp
+  const double* sa;      // row scales 2^e, length Mp
   const double* sb;
+  const double* ta;      // row sums  sum_k X[r,k] / s_r, length Mp
+  const double* tb;
   double* C;
   int64_t M, N, K;       // logical extents
   int64_t Mp, Np;        // padded row counts of the two plane sets (multiples of 128)
   int64_t crs, ccs;      // C[m*crs + n*ccs]
   double alpha, beta;
+  double cprime;         // c = sum_{p=1..NS-1} 256^-p
   uint32_t lbo, sbo;     // descriptor strides (bytes)
 };
 
-template <int NS>
+// tile columns: NS accumulators of TN int32 columns must fit the 512 TMEM columns; every MMA needs N % 16 == 0
+template <int NS> struct OzTile { static constexpr int TN = NS <= 5 ? 96 : (NS == 6 ? 80 : 64); };
+
+template <int NS, int TN>
 struct OzCfg {
   static constexpr int A_PLANE = OZ_TM * OZ_BK;           // 4096
-  static constexpr int B_PLANE = OZ_TN * OZ_BK;           // 2048
+  static constexpr int B_PLANE = TN * OZ_BK;
   static constexpr int STAGE = NS * (A_PLANE + B_PLANE);
   static constexpr int STAGES = (OZ_SMEM_MAX - 2048) / STAGE > 8 ? 8 : (OZ_SMEM_MAX - 2048) / STAGE;
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 512;
+  static_assert(NS * TN <= 512, "accumulators exceed TMEM");
+  static_assert(TN % 16 == 0, "MMA N granularity");
 };
 
 // tile index -> (m block, n block); groups of 8 m-blocks are swept along n so that the CTAs running
@@ -146,9 +160,9 @@ __device__ __forceinline__ void tile_coord(int64_t tile, int64_t tiles_m, int64_
   tn = (tile % per_group) / gsz;
 }
 
-template <int NS>
+template <int NS, int TN>
 __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
-  using Cfg = OzCfg<NS>;
+  using Cfg = OzCfg<NS, TN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t tiles_m = (p.M + OZ_TM - 1) / OZ_TM, tiles_n = (p.N + OZ_TN - 1) / OZ_TN;
+  const int64_t tiles_m = (p.M + OZ_TM - 1) / OZ_TM, tiles_n = (p.N + TN - 1) / TN;
   const int64_t ntiles = tiles_m * tiles_n;
   const int nkb = (int)((p.K + OZ_BK - 1) / OZ_BK);
   constexpr int KB_FLUSH = OZ_KFLUSH / OZ_BK;
@@ -230,18 +244,17 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
             tc_fence_after();
             const uint32_t sa = sbase + st * Cfg::STAGE, sb = sa + NS * Cfg::A_PLANE;
             // The B digit planes of a stage are contiguous, so digits q = 0..NS-1-pd form ONE operand of
-            // 64 (NS-pd) rows: A_pd . [B_0; ..; B_{NS-1-pd}]^T lands in the TMEM columns of the weights
-            // pd .. NS-1, which are contiguous too.  One MMA per <= 256 columns: A is read from shared
-            // memory once per 256 output columns instead of once per 64.
+            // TN (NS-pd) rows: A_pd . [B_0; ..; B_{NS-1-pd}]^T lands in the TMEM columns of the weights
+            // pd .. NS-1, which are contiguous too.  One MMA per <= 256 columns.
 #pragma unroll
             for (int pd = 0; pd < NS; ++pd) {
               const uint64_t adesc = desc0 | (uint64_t)(((sa + pd * Cfg::A_PLANE) >> 4) & 0x3fff);
-              const int ncols = OZ_TN * (NS - pd);
+              const int ncols = TN * (NS - pd);
 #pragma unroll
               for (int n0 = 0; n0 < ncols; n0 += 256) {
                 const int nlen = ncols - n0 < 256 ? ncols - n0 : 256;
                 const uint64_t bdesc = desc0 | (uint64_t)(((sb + n0 * OZ_BK) >> 4) & 0x3fff);
-                mma_i8(tmem_base + (uint32_t)(pd * OZ_TN + n0), adesc, bdesc, idesc0 | ((uint32_t)(nlen >> 3) << 17),
+                mma_i8(tmem_base + (uint32_t)(pd * TN + n0), adesc, bdesc, idesc0 | ((uint32_t)(nlen >> 3) << 17),
                        (kb > kb0 || pd > 0) ? 1u : 0u);
               }
             }
@@ -256,23 +269,24 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
     const int quad = warp & 3;                 // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int row = quad * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const double w = 0.0078125;                // 2^-7
+    const double w = 0.00390625;               // 2^-8
+    const double cK = p.cprime * p.cprime * (double)p.K;
     uint32_t acc_it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
       tile_coord(tile, tiles_m, tiles_n, tm, tn);
-      const int64_t m = tm * OZ_TM + row, n0 = tn * OZ_TN;
-      double run[OZ_TN];
+      const int64_t m = tm * OZ_TM + row, n0 = tn * TN;
+      double run[TN];
 #pragma unroll
-      for (int j = 0; j < OZ_TN; ++j) run[j] = 0.0;
+      for (int j = 0; j < TN; ++j) run[j] = 0.0;
       for (int c = 0; c < nchunk; ++c, ++acc_it) {
         mbar_wait(tmem_full, acc_it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int cb = 0; cb < OZ_TN / 8; ++cb) {
+        for (int cb = 0; cb < TN / 8; ++cb) {
           int32_t v[NS][8];
 #pragma unroll
-          for (int d = 0; d < NS; ++d) tmem_ld8(tlane + (uint32_t)(d * OZ_TN + cb * 8), v[d]);
+          for (int d = 0; d < NS; ++d) tmem_ld8(tlane + (uint32_t)(d * TN + cb * 8), v[d]);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -286,30 +300,44 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
         mbar_arrive(tmem_empty);
       }
       if (m < p.M) {
+        // C = alpha sA sB (4 * 2^-16 H + c (tA + tB) - c^2 K) + beta C
         const double fa = p.alpha * p.sa[m];
+        const double um = p.cprime * p.ta[m] - cK;
         double* crow = p.C + m * p.crs + n0 * p.ccs;
-        const int nn = (int)min((int64_t)OZ_TN, p.N - n0);
-        if (p.ccs == 1 && nn == OZ_TN && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+        const int nn = (int)min((int64_t)TN, p.N - n0);
+        const bool vec = p.ccs == 1 && nn == TN && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
 #pragma unroll
-          for (int j = 0; j < OZ_TN; j += 2) {
-            double2 o;
-            o.x = fa * p.sb[n0 + j] * run[j];
-            o.y = fa * p.sb[n0 + j + 1] * run[j + 1];
-            if (p.beta != 0.0) {
-              const double2 old = *reinterpret_cast<const double2*>(crow + j);
-              o.x += p.beta * old.x;
-              o.y += p.beta * old.y;
-            }
-            *reinterpret_cast<double2*>(crow + j) = o;
+        for (int jc = 0; jc < TN; jc += 8) {
+          double o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int64_t n = min(n0 + jc + q, p.N - 1);
+            o[q] = fa * p.sb[n] * (fma(run[jc + q], 6.103515625e-05 /* 4 * 2^-16 */, um) + p.cprime * p.tb[n]);
           }
-        } else {
+          if (vec) {
+            if (p.beta != 0.0) {
+              double2 old[4];
 #pragma unroll
-          for (int j = 0; j < OZ_TN; ++j) {
-            if (j < nn) {
-              double o = fa * p.sb[n0 + j] * run[j];
-              if (p.beta != 0.0) o += p.beta * crow[j * p.ccs];
-              crow[j * p.ccs] = o;
+              for (int q = 0; q < 4; ++q) old[q] = *reinterpret_cast<const double2*>(crow + jc + 2 * q);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                o[2 * q] += p.beta * old[q].x;
+                o[2 * q + 1] += p.beta * old[q].y;
+              }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<double2*>(crow + jc + 2 * q) = make_double2(o[2 * q], o[2 * q + 1]);
+          } else {
+            if (p.beta != 0.0) {
+              double old[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) old[q] = (jc + q < nn) ? crow[(jc + q) * p.ccs] : 0.0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] += p.beta * old[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (jc + q < nn) crow[(jc + q) * p.ccs] = o[q];
           }
         }
       }
@@ -326,42 +354,62 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// row scales: s_r = 2^(e_r - 6) with |X[r,:]| < 2^e_r  (s_r = 1 for an all-zero or padded row)
-// X[r*rs + k*ks]; one of rs, ks is 1.
-__global__ void ozaki_rowmax_kcontig(const double* __restrict__ X, int64_t R, int64_t K, int64_t rs, int64_t Rp,
-                                     double* __restrict__ scale) {   // scale already offset to the chunk's first row
+// row statistics: s_r = 2^e_r with |X[r,:]| < s_r (1 for an all-zero or padded row) and
+// t_r = sum_k X[r,k] / s_r (fixed summation order).  X[r*rs + k*ks]; one of rs, ks is 1.
+__device__ __forceinline__ double oz_scale_of(double mx) {
+  int e = 0;
+  if (mx > 0.0) frexp(mx, &e);          // mx = f 2^e, f in [0.5, 1)
+  return mx > 0.0 ? ldexp(1.0, e) : 1.0;
+}
+__global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, int64_t K, int64_t rs, int64_t Rp,
+                                      double* __restrict__ scale, double* __restrict__ rsum) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= Rp) return;
-  double mx = 0.0;
+  double mx = 0.0, sm = 0.0;
   if (r < R) {
     const double* x = X + r * rs;
-    for (int64_t k = lane; k < K; k += 32) mx = fmax(mx, fabs(x[k]));
+    for (int64_t k = lane; k < K; k += 32) {
+      const double v = x[k];
+      mx = fmax(mx, fabs(v));
+      sm += v;
+    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o; o >>= 1) {
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    }
   }
   if (lane == 0) {
-    int e = 0;
-    if (mx > 0.0) frexp(mx, &e);          // mx = f 2^e, f in [0.5, 1)
-    scale[r] = mx > 0.0 ? ldexp(1.0, e - 6) : 1.0;
+    const double s = oz_scale_of(mx);
+    scale[r] = s;
+    rsum[r] = sm / s;
   }
 }
-__global__ void ozaki_rowmax_rcontig(const double* __restrict__ X, int64_t R, int64_t K, int64_t ks, int64_t Rp,
-                                     double* __restrict__ scale) {
-  __shared__ double red[8][33];
+__global__ void ozaki_rowstat_rcontig(const double* __restrict__ X, int64_t R, int64_t K, int64_t ks, int64_t Rp,
+                                      double* __restrict__ scale, double* __restrict__ rsum) {
+  __shared__ double red[8][33], reds[8][33];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * 32 + lane;
-  double mx = 0.0;
+  double mx = 0.0, sm = 0.0;
   if (r < R)
-    for (int64_t k = wy; k < K; k += 8) mx = fmax(mx, fabs(X[r + k * ks]));
+    for (int64_t k = wy; k < K; k += 8) {
+      const double v = X[r + k * ks];
+      mx = fmax(mx, fabs(v));
+      sm += v;
+    }
   red[wy][lane] = mx;
+  reds[wy][lane] = sm;
   __syncthreads();
   if (wy == 0 && r < Rp) {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) mx = fmax(mx, red[i][lane]);
-    int e = 0;
-    if (mx > 0.0) frexp(mx, &e);
-    scale[r] = mx > 0.0 ? ldexp(1.0, e - 6) : 1.0;
+    for (int i = 1; i < 8; ++i) {
+      mx = fmax(mx, red[i][lane]);
+      sm += reds[i][lane];
+    }
+    const double s = oz_scale_of(mx);
+    scale[r] = s;
+    rsum[r] = sm / s;
   }
 }
 
@@ -378,24 +426,24 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
   const int j = t >> 7;
   const int64_t kb = blockIdx.y;
   const int64_t k0 = kb * OZ_BK + j * 16;
-  double x[16];
+  double y[16];          // (x/s + 1)/2 in [0,1]; negative = padding (all digits 0)
   if (r < R) {
-    const double inv = 1.0 / scale[r];     // exact: a power of two
+    const double inv = 0.5 / scale[r];     // exact: a power of two
     const double* src = X + r * rs + k0 * ks;
     if (ks == 1 && k0 + 16 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
         const double2 v = *reinterpret_cast<const double2*>(src + i);
-        x[i] = v.x * inv;
-        x[i + 1] = v.y * inv;
+        y[i] = fma(v.x, inv, 0.5);
+        y[i + 1] = fma(v.y, inv, 0.5);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = (k0 + i < K) ? src[i * ks] * inv : 0.0;
+      for (int i = 0; i < 16; ++i) y[i] = (k0 + i < K) ? fma(src[i * ks], inv, 0.5) : -1.0;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = 0.0;
+    for (int i = 0; i < 16; ++i) y[i] = -1.0;
   }
   const int64_t slab = Rp * OZ_BK;
   const int64_t rg = row0 + r;
@@ -405,21 +453,31 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const double d = rint(x[i]);
-      x[i] = (x[i] - d) * 128.0;           // exact
-      w[i >> 2] |= ((uint32_t)(__double2int_rn(d)) & 0xffu) << ((i & 3) * 8);
+      int d = 0;
+      if (y[i] >= 0.0) {
+        const double z = y[i] * 256.0;                               // exact
+        double u = (p == NS - 1) ? floor(z + 0.5) : floor(z);        // last digit: to nearest
+        u = fmin(u, 255.0);
+        y[i] = fmax(z - u, 0.0);                                     // exact; in [0,1] ((.,1] only after a clamp)
+        d = (int)u - 128;
+      }
+      w[i >> 2] |= ((uint32_t)d & 0xffu) << ((i & 3) * 8);
     }
     *reinterpret_cast<uint4*>(dst + p * slab) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
 template <int NS>
-cudaError_t launch_gemm_ns(const OzGemmParams& p, cudaStream_t st, int sm_count) {
-  using Cfg = OzCfg<NS>;
-  auto kern = ozaki_gemm_kernel<NS>;
+cudaError_t launch_gemm_ns(OzGemmParams p, cudaStream_t st, int sm_count) {
+  constexpr int TN = OzTile<NS>::TN;
+  using Cfg = OzCfg<NS, TN>;
+  auto kern = ozaki_gemm_kernel<NS, TN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return e;
-  const int64_t tiles = ((p.M + OZ_TM - 1) / OZ_TM) * ((p.N + OZ_TN - 1) / OZ_TN);
+  double c = 0.0;
+  for (int q = 1; q < NS; ++q) c += ldexp(1.0, -8 * q);
+  p.cprime = c;
+  const int64_t tiles = ((p.M + OZ_TM - 1) / OZ_TM) * ((p.N + TN - 1) / TN);
   const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
   kern<<<grid, 192, Cfg::SMEM, st>>>(p);
   return cudaGetLastError();
@@ -427,9 +485,17 @@ cudaError_t launch_gemm_ns(const OzGemmParams& p, cudaStream_t st, int sm_count)
 
 }  // namespace
 
+int ozaki_tile_n(int ns) {
+  switch (ns) {
+    case 3: return OzTile<3>::TN; case 4: return OzTile<4>::TN; case 5: return OzTile<5>::TN;
+    case 6: return OzTile<6>::TN; case 7: return OzTile<7>::TN; case 8: return OzTile<8>::TN;
+  }
+  return 64;
+}
 int64_t ozaki_padded_rows(int64_t R) { return (R + 127) / 128 * 128; }
+// + one B tile of slack: the last N-side tile of the last slab may start inside the padded rows and run past them
 int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns) {
-  return ozaki_padded_rows(R) * ((K + OZ_BK - 1) / OZ_BK * OZ_BK) * ns;
+  return ozaki_padded_rows(R) * ((K + OZ_BK - 1) / OZ_BK * OZ_BK) * ns + 4096;
 }
 
 cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, int8_t* planes,
@@ -439,11 +505,12 @@ cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs
   if (row0 + R > total_rows || (row0 + R < total_rows && (R & 127))) return cudaErrorInvalidValue;
   const int64_t Rp = ozaki_padded_rows(R);              // rows this launch writes (incl. zero padding)
   const int64_t Rp_total = ozaki_padded_rows(total_rows);
-  double* sc = scale + row0;
+  double* sc = scale + row0;                            // stats: [scales (Rp_total) | row sums (Rp_total)]
+  double* sm = scale + Rp_total + row0;
   if (ks == 1) {
-    ozaki_rowmax_kcontig<<<(unsigned)((Rp + 7) / 8), 256, 0, st>>>(X, R, K, rs, Rp, sc);
+    ozaki_rowstat_kcontig<<<(unsigned)((Rp + 7) / 8), 256, 0, st>>>(X, R, K, rs, Rp, sc, sm);
   } else {
-    ozaki_rowmax_rcontig<<<(unsigned)((Rp + 31) / 32), 256, 0, st>>>(X, R, K, ks, Rp, sc);
+    ozaki_rowstat_rcontig<<<(unsigned)((Rp + 31) / 32), 256, 0, st>>>(X, R, K, ks, Rp, sc, sm);
   }
   const int64_t nkb = (K + OZ_BK - 1) / OZ_BK;
   if (nkb > 65535) return cudaErrorInvalidValue;
@@ -464,11 +531,9 @@ cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* 
   p.pa = pa; p.pb = pb; p.sa = sa; p.sb = sb; p.C = C;
   p.M = M; p.N = N; p.K = K;
   p.Mp = ozaki_padded_rows(M); p.Np = ozaki_padded_rows(N);
+  p.ta = sa + p.Mp; p.tb = sb + p.Np;                   // stats arrays: [scales | row sums]
   p.crs = crs; p.ccs = ccs; p.alpha = alpha; p.beta = beta;
   p.lbo = 128; p.sbo = 256;
-  // bring-up overrides (tools/ozaki_check.py): descriptor strides
-  if (const char* s = getenv("ECW_OZ_LBO")) p.lbo = (uint32_t)atoi(s);
-  if (const char* s = getenv("ECW_OZ_SBO")) p.sbo = (uint32_t)atoi(s);
   if (sm_count <= 0) sm_count = 148;
   switch (ns) {
     case 3: return launch_gemm_ns<3>(p, st, sm_count);

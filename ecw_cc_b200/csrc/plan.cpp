@@ -381,6 +381,9 @@ void Plan::ewise(int sub, const Tensor& a, const Tensor& b, const Tensor& c, dou
 }
 
 // ---------------------------------------------------------------- contraction engine
+static double oz_time(int ns, int sm_count, int64_t M, int64_t N, int64_t K, int64_t crs, int64_t ccs, double beta,
+                      bool* swap_out);
+
 namespace {
 
 struct Group {
@@ -584,18 +587,13 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
     const double fl = 2.0 * (double)Md * (double)Nd * (double)Kd;
     bool oz = oz_ns > 0 && ch.bcls == 0 && Kd >= 1 && (Kd + 31) / 32 <= 65535;
     if (oz && oz_min_flops >= 0.0) {
-      // cost model (seconds): INT8 route = padded product at ~100 TFLOP/s FP64-equivalent scaled by how many of
-      // the 148 SMs get a 128x64 tile, plus cutting both operands (8 B read + ns B written, re-read once);
-      // DMMA route = 30 TFLOP/s.  Skinny or few-tile products stay on the DMMA kernels.
-      auto pad = [](int64_t x, int64_t g) { return (x + g - 1) / g * g; };
-      const double t1m = (double)pad(Md, 128) * (double)pad(Nd, 64), t2m = (double)pad(Md, 64) * (double)pad(Nd, 128);
-      const bool sw = t2m < t1m;
-      const double tiles = sw ? (double)(pad(Md, 64) / 64) * (double)(pad(Nd, 128) / 128)
-                              : (double)(pad(Md, 128) / 128) * (double)(pad(Nd, 64) / 64);
-      const double eff = std::min(1.0, tiles / (double)sm_count);
+      // INT8 route (model in oz_time) + cutting the operands (8 B read + ns B written and re-read) against the
+      // DMMA route at 30 TFLOP/s: skinny, few-tile or short-K products stay on the DMMA kernels
+      MatView vcm = mat_view(C, sc, ch.om, ch.on);
       const double cut = (8.0 + 2.0 * oz_ns) * ((const_planes && A.slot == S_VVVV_P ? 0.0 : (double)Md) +
                                                 (const_planes && B.slot == S_VVVV_P ? 0.0 : (double)Nd)) * (double)Kd / 5e12;
-      const double t_oz = 2.0 * (double)Kd * std::min(t1m, t2m) / (1.0e14 * eff) + cut + 2e-5;
+      const double t_oz = oz_time(oz_ns, sm_count, Md, Nd, Kd, vcm.any ? vcm.sr : Nd, vcm.any ? vcm.scol : 1, beta, nullptr) +
+                          cut + 2e-5;
       oz = fl >= oz_min_flops && t_oz < 0.8 * fl / 3.0e13;
     }
     if (const_planes && !(oz_ns > 0 && ch.bcls == 0 && ch.a_dir && ch.b_dir))
@@ -738,9 +736,33 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
 }
 
 // ---------------------------------------------------------------- INT8-pipe GEMM
+// sizes mirror ozaki.cu (ozaki_padded_rows / ozaki_plane_bytes / ozaki_tile_n); this file stays CUDA-free
 static int64_t oz_pad_rows(int64_t r) { return (r + 127) / 128 * 128; }
 static int64_t oz_plane_elems(int64_t R, int64_t K, int ns) {
-  return (oz_pad_rows(R) * ((K + 31) / 32 * 32) * ns + 7) / 8;
+  return (oz_pad_rows(R) * ((K + 31) / 32 * 32) * ns + 4096 + 7) / 8;
+}
+static int64_t oz_stat_elems(int64_t R) { return 2 * oz_pad_rows(R); }   // [row scales | row sums]
+static int oz_tile_n(int ns) { return ns <= 5 ? 96 : (ns == 6 ? 80 : 64); }
+
+// Seconds (model) of one INT8-route GEMM for both role assignments; tile = 128 rows of the first operand x TN rows
+// of the second.  Main loop: padded product at ~100 TFLOP/s FP64-equivalent for 7 digits (scaled by the digit-pair
+// count), derated when fewer tiles than SMs; epilogue: the C tile is written (and read when beta != 0) by one thread
+// per tile row — coalesced when the tile rows are contiguous in C, 16-byte pieces otherwise.
+static double oz_time(int ns, int sm_count, int64_t M, int64_t N, int64_t K, int64_t crs, int64_t ccs, double beta,
+                      bool* swap_out) {
+  auto pad = [](int64_t x, int64_t g) { return (x + g - 1) / g * g; };
+  const int TN = oz_tile_n(ns);
+  const double rate = 1.0e14 * 28.0 / (0.5 * ns * (ns + 1));
+  double best = 1e300;
+  for (int sw = 0; sw < 2; ++sw) {
+    const int64_t m = sw ? N : M, n = sw ? M : N, rs = sw ? ccs : crs;
+    const double tiles = (double)(pad(m, 128) / 128) * (double)(pad(n, TN) / TN);
+    const double eff = std::min(1.0, tiles / (double)sm_count);
+    const double main = 2.0 * (double)K * (double)pad(m, 128) * (double)pad(n, TN) / (rate * eff);
+    const double epi = 8.0 * (double)M * (double)N * (beta != 0.0 ? 2.0 : 1.0) / (rs == 1 ? 3.0e12 : 0.5e12);
+    if (main + epi < best) { best = main + epi; if (swap_out) *swap_out = sw != 0; }
+  }
+  return best;
 }
 
 void Plan::emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, const Tensor& B, int64_t brs, int64_t bks,
@@ -753,12 +775,12 @@ void Plan::emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, cons
       // the constant row shard of the packed vvvv: [R, K] with K contiguous, cut once at upload time
       if (X.off != 0 || ks != 1 || rs != K) throw PlanError("vvvv_p digit planes: unexpected operand view in " + note);
       s.planes = make_tensor(S_VVVV_OZ, 0, {oz_plane_elems(R, K, oz_ns)});
-      s.scales = make_tensor(S_VVVV_OZS, 0, {oz_pad_rows(R)});
+      s.scales = make_tensor(S_VVVV_OZS, 0, {oz_stat_elems(R)});
       s.owned = false;
       return s;
     }
     s.planes = tmp({oz_plane_elems(R, K, oz_ns)});
-    s.scales = tmp({oz_pad_rows(R)});
+    s.scales = tmp({oz_stat_elems(R)});
     s.owned = true;
     Op sp;
     sp.kind = OP_OZ_SPLIT;
@@ -779,9 +801,9 @@ void Plan::emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, cons
   g.K = K;
   g.i0 = oz_ns;
   g.note = note;
-  // tile = 128 rows of the first operand x 64 rows of the second: pick the roles with less padding
-  auto pad = [](int64_t x, int64_t gq) { return (x + gq - 1) / gq * gq; };
-  const bool swap = (double)pad(N, 128) * (double)pad(M, 64) < (double)pad(M, 128) * (double)pad(N, 64);
+  // tile = 128 rows of the first operand x TN rows of the second: pick the cheaper role assignment
+  bool swap = false;
+  oz_time(oz_ns, sm_count, M, N, K, crs, ccs, beta, &swap);
   if (!swap) {
     g.a = a.planes; g.d = a.scales; g.b = b.planes; g.e = b.scales;
     g.M = M; g.N = N; g.i1 = crs; g.i2 = ccs;

@@ -19,21 +19,33 @@ SYNTH_KIND = dict(oooo=0, ooov=1, oovv=2, oovv_ph=3, ovov_ph=4, ovvv=5, oooo_p=6
 
 
 # GEMM engine of the contraction plans (include/ecw_b200.h, ecw_ctx_set_gemm):
-#   "int8" (default) - large unbatched GEMMs on the INT8 tcgen05 tensor pipe by error-free splitting
-#                      into INT8_DIGITS 7-bit digits; the packed vvvv lives on the device as digit planes;
+#   "int8" (default) - large unbatched GEMMs on the INT8 tcgen05 tensor pipe: FP64 operands cut into
+#                      base-256 int8 digits (csrc/ozaki.cu); the packed vvvv lives on the device as digit
+#                      planes only;
 #   "dmma"           - everything on the FP64 DMMA kernels.
+# Digits: 6 (48 bits) when the worst-case error bound of the longest contraction (the pp ladder, K = P_v),
+#   4 (NS+3) 256^-NS K max|<pq||rs>| max|tau|  with max|tau| taken as 1/4, stays below AUTO_DIGIT_BOUND; else 7 (or 8).
 # Environment overrides for experiments: ECW_GEMM, ECW_INT8_DIGITS, ECW_INT8_MIN_FLOPS (-1: every GEMM).
-INT8_DIGITS = 7
 INT8_MIN_FLOPS = 2e10
+AUTO_DIGIT_BOUND = 5e-11
 
 
-def _gemm_config(gemm, int8_digits, int8_min_flops):
+def auto_digits(nvir, eri_max):
+    k = nvir * (nvir - 1) // 2
+    for nd in (6, 7):
+        if 4.0 * (nd + 3) * 256.0 ** (-nd) * k * float(eri_max) * 0.25 <= AUTO_DIGIT_BOUND:
+            return nd
+    return 8
+
+
+def _gemm_config(gemm, int8_digits, int8_min_flops, nvir, eri_max):
     gemm = gemm or os.environ.get("ECW_GEMM", "int8")
     if gemm not in ("int8", "dmma"):
         raise ValueError("gemm must be 'int8' or 'dmma', got %r" % (gemm,))
     if gemm == "dmma":
         return 0, 0.0
-    nd = int(int8_digits if int8_digits is not None else os.environ.get("ECW_INT8_DIGITS", INT8_DIGITS))
+    nd = int8_digits if int8_digits is not None else os.environ.get("ECW_INT8_DIGITS")
+    nd = int(nd) if nd is not None else auto_digits(nvir, eri_max)
     mf = float(int8_min_flops if int8_min_flops is not None else os.environ.get("ECW_INT8_MIN_FLOPS", INT8_MIN_FLOPS))
     return nd, mf
 
@@ -49,10 +61,10 @@ class DeviceEris(object):
     """Owns the C context, the bound integral layouts and the workspace."""
 
     def __init__(self, nocc, nvir, device=None, rank=0, world=1, group=None, gemm=None, int8_digits=None,
-                 int8_min_flops=None):
+                 int8_min_flops=None, eri_max=1.0):
         """rank/world/group: one process per GPU; `vvvv_p` is then row-sharded over the packed
         virtual pair index and the heavy contractions are distributed (include/ecw_b200.h).
-        gemm: "int8" | "dmma" (see module header)."""
+        gemm: "int8" | "dmma"; int8_digits: None = chosen from eri_max = max |<pq||rs>| (module header)."""
         torch = _torch()
         self.nocc = int(nocc)
         self.nvir = int(nvir)
@@ -63,7 +75,7 @@ class DeviceEris(object):
             raise EcwError("ecw_ctx_create failed")
         if self.world > 1 and lib.ecw_ctx_set_shard(self._h, self.rank, self.world) != 0:
             raise EcwError("ecw_ctx_set_shard failed")
-        self.int8_digits, self.int8_min_flops = _gemm_config(gemm, int8_digits, int8_min_flops)
+        self.int8_digits, self.int8_min_flops = _gemm_config(gemm, int8_digits, int8_min_flops, self.nvir, eri_max)
         self.check(lib.ecw_ctx_set_gemm(self._h, self.int8_digits, self.int8_min_flops), "ecw_ctx_set_gemm")
         self.buf = {}
         self._ws = None
@@ -144,8 +156,10 @@ class DeviceEris(object):
         torch = _torch()
         fock = np.asarray(eris.fock)
         nocc = int(eris.nocc)
+        eri_max = max(float(np.abs(np.asarray(getattr(eris, k))).max()) if np.asarray(getattr(eris, k)).size else 0.0
+                      for k in ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv"))
         self = cls(nocc, fock.shape[0] - nocc, device, gemm=gemm, int8_digits=int8_digits,
-                   int8_min_flops=int8_min_flops)          # packed whole first, sharded below
+                   int8_min_flops=int8_min_flops, eri_max=eri_max)          # packed whole first, sharded below
         self.set_fock(fock)
         for name in ("oooo", "ooov", "oovv", "ovvv"):
             t = torch.from_numpy(np.ascontiguousarray(getattr(eris, name), dtype=np.float64)).to(self.device)
@@ -187,7 +201,7 @@ class DeviceEris(object):
         generated in row chunks and kept as digit planes only (keep_fp64_vvvv: also the FP64 layout)."""
         torch = _torch()
         self = cls(nocc, nvir, device, rank=rank, world=world, group=group, gemm=gemm, int8_digits=int8_digits,
-                   int8_min_flops=int8_min_flops)
+                   int8_min_flops=int8_min_flops, eri_max=abs(float(scale)))
         planes_only = bool(self.int8_digits) and not keep_fp64_vvvv
         for name in _LAYOUTS:
             if name == "vvvv_p" and planes_only:

@@ -56,8 +56,8 @@ int ecw_ctx_set_shard(ecw_ctx* ctx, int rank, int world);
 int ecw_resume(ecw_ctx* ctx, void* stream);
 /* GEMM engine.  int8_digits = 0: every contraction runs on the FP64 DMMA kernels.  int8_digits = 3..8:
  * unbatched GEMMs with 2MNK >= min_flops (negative: all of them) run on the INT8 tcgen05 tensor pipe by
- * error-free splitting into that many 7-bit digits (csrc/ozaki.cu; 7 digits = FP64-level accuracy,
- * |err| <= 2^-47 K max|A_row| max|B_row|).  Replaces the BLAS dgemm behind numpy/pyscf einsum
+ * splitting the operands into that many base-256 int8 digits (csrc/ozaki.cu; 6 digits = 48 bits,
+ * |err| <= 2^-42.8 K max|A_row| max|B_row| worst case, the size of an FP64 dot product's own rounding error).  Replaces the BLAS dgemm behind numpy/pyscf einsum
  * (CCSD.py:25).  A context starts with int8_digits = 0. */
 int ecw_ctx_set_gemm(ecw_ctx* ctx, int int8_digits, double min_flops);
 int ecw_ctx_get_gemm(ecw_ctx* ctx);
@@ -168,14 +168,16 @@ int64_t ecw_plan_launches(ecw_ctx* ctx, const char* func, int mode_flags);
  * cfg < 0 picks the tile configuration automatically. */
 int ecw_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
               const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int cfg, void* stream);
-/* FP64 GEMM by error-free splitting on the INT8 tcgen05 tensor pipe (csrc/ozaki.cu).
+/* FP64 GEMM on the INT8 tcgen05 tensor pipe (csrc/ozaki.cu: operands cut into base-256 int8 digits).
  * ecw_ozaki_split cuts X[R,K] (element (r,k) at X[r*rs + k*ks], one of rs/ks == 1) into `ns` int8
- * digit planes (ecw_ozaki_plane_bytes bytes) and one FP64 scale per padded row
- * (ecw_ozaki_padded_rows doubles); ecw_ozaki_gemm forms C[m*crs + n*ccs] = alpha * sum_k A[m,k] B[n,k]
+ * digit planes (ecw_ozaki_plane_bytes bytes) and row statistics (ecw_ozaki_stat_elems doubles: power-of-two
+ * row scales, then row sums); ecw_ozaki_gemm forms C[m*crs + n*ccs] = alpha * sum_k A[m,k] B[n,k]
  * + beta * C from two plane sets.  Replaces the numpy einsum of the large contractions
  * (CCSD.py:305, 411, 484, 602) together with ecw_dgemm. */
 int64_t ecw_ozaki_plane_bytes(int64_t R, int64_t K, int ns);
 int64_t ecw_ozaki_padded_rows(int64_t R);
+int64_t ecw_ozaki_stat_elems(int64_t R);
+int ecw_ozaki_tile_n(int ns);
 int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes, double* scale,
                     void* stream);
 /* chunked cut: X holds rows [row0, row0+R) of an operand of total_rows rows (row0 and every chunk but the

@@ -23,20 +23,34 @@ def pair_decode(n):
 
 # ---- INT8-pipe GEMM (csrc/ozaki.cu): numpy statement of the digit cut and the device plane order
 def oz_scale(X):
+    """power-of-two row scales s_r > max|X[r,:]| (1 for an all-zero row)."""
     mx = np.abs(X).max(axis=1) if X.shape[1] else np.zeros(X.shape[0])
     _, e = np.frexp(mx)
-    return np.where(mx > 0, np.ldexp(1.0, e - 6), 1.0)
+    return np.where(mx > 0, np.ldexp(1.0, e), 1.0)
+
+
+def oz_cprime(ns):
+    return sum(256.0 ** (-q) for q in range(1, ns))
 
 
 def oz_digits(X, ns):
+    """X[r,k] = s_r (2 sum_p d_p 256^-(p+1) + c) + delta: int8 digits [ns][R][K] and the scales."""
     s = oz_scale(X)
-    x = X / s[:, None]
+    y = X * (0.5 / s)[:, None] + 0.5                 # one rounding, as the device fma
     out = []
-    for _ in range(ns):
-        d = np.rint(x)
-        x = (x - d) * 128.0
-        out.append(d.astype(np.int8))
+    for p in range(ns):
+        z = y * 256.0
+        u = np.floor(z + 0.5) if p == ns - 1 else np.floor(z)
+        u = np.minimum(u, 255.0)
+        y = np.maximum(z - u, 0.0)
+        out.append((u - 128.0).astype(np.int8))
     return np.stack(out), s
+
+
+def oz_value(D, s, ns):
+    """the FP64 numbers the digits stand for."""
+    Dv = sum(D[p].astype(np.float64) * 256.0 ** (-(p + 1)) for p in range(ns))
+    return s[:, None] * (2.0 * Dv + oz_cprime(ns))
 
 
 def oz_to_planes(D):
@@ -54,15 +68,35 @@ def oz_from_planes(buf, ns, R, K):
     return P[:, :R, :K]
 
 
+def oz_stats(X, s):
+    """device statistics array [row scales (padded to 128) | row sums / scale]."""
+    Rp = (X.shape[0] + 127) // 128 * 128
+    st = np.zeros(2 * Rp)
+    st[:Rp] = 1.0
+    st[: X.shape[0]] = s
+    st[Rp: Rp + X.shape[0]] = X.sum(axis=1) / s
+    return st
+
+
 def oz_const_slots(X, ns):
-    """(planes, scales) slot arrays for a constant operand X[R,K] (what ecw_eris_vvvv_planes leaves bound)."""
+    """(planes, stats) slot arrays for a constant operand X[R,K] (what ecw_eris_vvvv_planes leaves bound)."""
     D, s = oz_digits(X, ns)
     pl = oz_to_planes(D)
-    pad = (-pl.size) % 8
-    pl = np.concatenate([pl, np.zeros(pad, np.int8)]).view(np.float64).copy()
-    sc = np.ones((X.shape[0] + 127) // 128 * 128)
-    sc[: X.shape[0]] = s
-    return pl, sc
+    pl = np.concatenate([pl, np.zeros(4096 + (-pl.size) % 8, np.int8)]).view(np.float64).copy()
+    return pl, oz_stats(X, s)
+
+
+def oz_product(DA, sa, ta, DB, sb, tb, K, ns):
+    """what ozaki_gemm_kernel forms from two digit sets (exact integer products, FP64 Horner)."""
+    DA, DB = DA.astype(np.float64), DB.astype(np.float64)
+    H = np.zeros((DA.shape[1], DB.shape[1]))
+    for w in range(ns - 1, -1, -1):
+        part = np.zeros_like(H)
+        for p in range(w + 1):
+            part += DA[p] @ DB[w - p].T               # exact: integers far below 2^53
+        H = H * 0.00390625 + part
+    c = oz_cprime(ns)
+    return sa[:, None] * sb[None, :] * (H * 6.103515625e-05 + (c * ta - c * c * K)[:, None] + (c * tb)[None, :])
 
 
 class Interp(object):
@@ -156,32 +190,26 @@ class Interp(object):
     def op_oz_split(self, op):
         a = op["a"]
         R, K, ns = op["M"], op["K"], op["i0"]
-        X = self._mat(a["slot"], a["off"], R, K, op["lda"], op["ldb"])
+        X = np.array(self._mat(a["slot"], a["off"], R, K, op["lda"], op["ldb"]))
         assert not np.isnan(X).any(), op["note"]
-        D, s = oz_digits(np.array(X), ns)
+        D, s = oz_digits(X, ns)
         pl = oz_to_planes(D)
-        assert pl.size <= 8 * op["c"]["dim"][0], op["note"]
+        assert pl.size + 4096 <= 8 * op["c"]["dim"][0], op["note"]
         self._bytes(op["c"])[: pl.size] = pl
-        sc = self.view(op["d"])
-        assert sc.shape[0] == (R + 127) // 128 * 128
-        sc[...] = 1.0
-        sc[:R] = s
+        st = self.view(op["d"])
+        assert st.shape[0] == 2 * ((R + 127) // 128 * 128)
+        st[...] = oz_stats(X, s)
 
     def op_oz_gemm(self, op):
         M, N, K, ns = op["M"], op["N"], op["K"], op["i0"]
-        DA = oz_from_planes(self._bytes(op["a"]), ns, M, K).astype(np.float64)
-        DB = oz_from_planes(self._bytes(op["b"]), ns, N, K).astype(np.float64)
-        sa, sb = self.view(op["d"])[:M], self.view(op["e"])[:N]
-        assert not np.isnan(sa).any() and not np.isnan(sb).any(), op["note"]
-        acc = np.zeros((M, N))
-        for w in range(ns - 1, -1, -1):          # Horner over the weights, as the device epilogue
-            part = np.zeros((M, N))
-            for p in range(w + 1):
-                part += DA[p] @ DB[w - p].T       # exact: integers far below 2^53
-            acc = acc * 0.0078125 + part
+        DA = oz_from_planes(self._bytes(op["a"]), ns, M, K)
+        DB = oz_from_planes(self._bytes(op["b"]), ns, N, K)
+        Mp, Np = (M + 127) // 128 * 128, (N + 127) // 128 * 128
+        sta, stb = self.view(op["d"]), self.view(op["e"])
+        assert not np.isnan(sta).any() and not np.isnan(stb).any(), op["note"]
         c = op["c"]
         C = self._mat(c["slot"], c["off"], M, N, op["i1"], op["i2"])
-        res = (op["alpha"] * sa)[:, None] * sb[None, :] * acc
+        res = op["alpha"] * oz_product(DA, sta[:M], sta[Mp:Mp + M], DB, stb[:N], stb[Np:Np + N], K, ns)
         if op["beta"] != 0.0:
             res = res + op["beta"] * C
         C[...] = res

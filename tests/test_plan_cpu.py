@@ -173,12 +173,12 @@ def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_
 
 @pytest.mark.parametrize("ov", [(3, 4), (4, 6), (6, 11)])
 def test_int8_engine_plans_match_oracle(built_lib, ov):
-    """Every unbatched GEMM forced onto the digit-plane route (7 digits), packed vvvv bound as planes:
+    """Every unbatched GEMM forced onto the digit-plane route (6 base-256 digits), packed vvvv bound as planes:
     the replayed plan (exact integer arithmetic in numpy) matches the oracle far below the 1e-10 bar."""
     o, v = ov
     er = synth.SynthEris(o, v)
     t1, t2, l1, l2 = synth.amplitudes(o, v)
-    _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, True, 7, 1e-12)
+    _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, True, 6, 1e-12)
 
 
 def test_int8_engine_general_path_and_digit_count(built_lib):
@@ -187,15 +187,15 @@ def test_int8_engine_general_path_and_digit_count(built_lib):
     rng = np.random.default_rng(5)
     t1, l1 = 0.05 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, v))
     t2, l2 = 0.02 * rng.standard_normal((o, o, v, v)), 0.02 * rng.standard_normal((o, o, v, v))
-    e7 = _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, False, 7, 1e-12)
-    e8 = _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, False, 8, 1e-12, vvvv_planes=False)
-    # fewer digits = a coarser product: the truncation error is visible and grows by ~2^7 per digit
+    e7 = _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, False, 6, 1e-12)
+    e8 = _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, False, 7, 1e-13, vvvv_planes=False)
+    # fewer digits = a coarser product: the truncation error is visible and grows by 2^8 per digit
     o4 = OracleGCC(er)
     base = eris_slots(er)
     base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=synth.fsp(o, v), fock=er.fock.copy())
     sl = dict(base)
     sl["out1"], sl["out2"] = np.full((o, v), np.nan), np.full((o, o, v, v), np.nan)
-    Interp(plan_json(built_lib, o, v, "tupdate", flags_of(None, True, antisym=False), int8_digits=4), sl).run()
+    Interp(plan_json(built_lib, o, v, "tupdate", flags_of(None, True, antisym=False), int8_digits=3), sl).run()
     ref = o4.tupdate(t1, t2, fsp=synth.fsp(o, v), equation=True)
     e4 = np.abs(sl["out2"] - ref[1]).max()
     assert e4 > 100 * max(e7, e8, 1e-16) and e4 < 1e-5
@@ -207,7 +207,7 @@ def test_int8_engine_north_star_plan(built_lib):
     o, v = 40, 400
     oz = tot = 0.0
     for fn in ("tupdate", "lupdate"):
-        pl = plan_json(built_lib, o, v, fn, 4, int8_digits=7, min_flops=2e10, vvvv_planes=True)
+        pl = plan_json(built_lib, o, v, fn, 4, int8_digits=6, min_flops=2e10, vvvv_planes=True)
         assert pl["workspace_elems"] * 8 < 45e9
         oz += pl["oz_flops"]
         tot += pl["gemm_flops"]

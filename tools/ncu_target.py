@@ -1,0 +1,22 @@
+"""Smallest program that launches the hot kernels at the benchmark shape, for ncu:
+one `GCC.tupdate` at (nocc, nvir) = (40, 400) on synthetic integrals (INT8 engine by default).
+    python tools/ncu_target.py [int8|dmma] [nocc nvir]
+Order of the ozaki_gemm_kernel launches in a packed-path tupdate: 0 [ijae,be->ijab], 1 Woooo tau.oovv,
+2 hh ladder, 3 K1 pp ladder (79800 x 780 x 79800), 4 R9, 5 R1 ring, 6 R2 ring."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ecw_cc_b200 as ecw
+
+gemm = sys.argv[1] if len(sys.argv) > 1 else None
+o, v = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (40, 400)
+de = ecw.DeviceEris.synthetic(o, v, gemm=gemm)
+cc = ecw.GCC(de, assume_antisym=True)
+n = o + v
+t1, t2 = de.synth_tensor("t1", (o, v)), de.synth_tensor("t2", (o, o, v, v))
+fsp = de.synth_tensor("fsp", (n, n))
+a, b = cc.tupdate(t1, t2, fsp=fsp)
+torch.cuda.synchronize()
+print("tupdate done: |t1new| %.6e |t2new| %.6e" % (float(a.norm()), float(b.norm())))
