@@ -74,6 +74,13 @@ class _Lib(object):
             "ecw_ctx_set_gemm": (c_i, [c_p, c_i, c_d]),
             "ecw_ctx_get_gemm": (c_i, [c_p]),
             "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),
+            "ecw_ctx_test_assume_ovvv_planes": (c_i, [c_p]),
+            "ecw_eris_ovvv_planes": (c_i, [c_p, c_p]),
+            "ecw_ozaki_plane_bytes2": (c_l, [c_l, c_l, c_l, c_i]),
+            "ecw_ozaki_stat_elems2": (c_l, [c_l, c_l]),
+            "ecw_ozaki_split2": (c_i, [c_p, c_l, c_l, c_l, c_l, c_l, c_l, c_i, c_p, c_p, c_p]),
+            "ecw_ozaki_gemm_batched": (c_i, [c_p, c_p, c_l, c_p, c_p, c_l, c_l, c_l, c_l, c_p, c_l, c_l, c_d, c_d, c_i,
+                                           ctypes.POINTER(c_l), c_p]),
             "ecw_eris_vvvv_planes": (c_i, [c_p, c_p, c_l, c_l, c_p]),
             "ecw_pending_collective": (c_i, [c_p, ctypes.POINTER(c_l)]),
             "ecw_slot_elems": (c_l, [c_p, c_s]),

@@ -62,9 +62,13 @@ int64_t slot_elems(const Sizes& z, int s) {
       const int64_t n0 = std::min<int64_t>(pv, (int64_t)z.rank * nshmax);
       const int64_t nsh = std::min<int64_t>(pv, n0 + nshmax) - n0;
       if (s == S_VVVV_P) return nsh * pv;
-      if (s == S_VVVV_OZS) return 2 * ozaki_padded_rows(nsh);       // [row scales | row sums]
+      if (s == S_VVVV_OZS) return ozaki_stat_elems(nsh, 1);         // [row scales | row sums]
       return (ozaki_plane_bytes(nsh, pv, z.oz_ns > 0 ? z.oz_ns : 7) + 7) / 8;   // in 8-byte units
     }
+    case S_OVVV_OZ1: return (ozaki_plane_bytes2(o * v, 1, pv, z.oz_ns > 0 ? z.oz_ns : 7) + 7) / 8;
+    case S_OVVV_OZ1S: return ozaki_stat_elems(o * v, 1);
+    case S_OVVV_OZ2: return (ozaki_plane_bytes2(pv, o, v, z.oz_ns > 0 ? z.oz_ns : 7) + 7) / 8;
+    case S_OVVV_OZ2S: return ozaki_stat_elems(pv, o);
     default: return -1;
   }
 }
@@ -198,15 +202,24 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
         return 1;
       }
       case OP_OZ_SPLIT:
-        ck(launch_ozaki_split(resolve(c, op.a), op.M, op.K, op.lda, op.ldb, (int)op.i0,
-                              reinterpret_cast<int8_t*>(resolve(c, op.c)), resolve(c, op.d), st), "ozaki_split");
+        ck(launch_ozaki_split2(resolve(c, op.a), op.M, op.i1, op.K, op.lda, op.ldc, op.ldb, (int)op.i0,
+                               reinterpret_cast<int8_t*>(resolve(c, op.c)), resolve(c, op.d), st), "ozaki_split");
         break;
-      case OP_OZ_GEMM:
-        ck(launch_ozaki_gemm(reinterpret_cast<const int8_t*>(resolve(c, op.a)), resolve(c, op.d),
-                             reinterpret_cast<const int8_t*>(resolve(c, op.b)), resolve(c, op.e), op.M, op.N, op.K,
-                             resolve(c, op.c), op.i1, op.i2, op.alpha, op.beta, (int)op.i0, st, c->sm_count),
+      case OP_OZ_GEMM: {
+        OzBatch bt{};
+        bt.batch = op.batch;
+        bt.a_row0 = op.oz[0]; bt.a_rowb = op.oz[1]; bt.b_row0 = op.oz[2]; bt.b_rowb = op.oz[3];
+        bt.a_kb0 = op.oz[4]; bt.a_kbb = op.oz[5]; bt.b_kb0 = op.oz[6]; bt.b_kbb = op.oz[7];
+        bt.a_t0 = op.oz[8]; bt.a_tb = op.oz[9]; bt.b_t0 = op.oz[10]; bt.b_tb = op.oz[11];
+        bt.nkb = op.oz[12];
+        bt.c_b = op.sC;
+        ck(launch_ozaki_gemm_batched(reinterpret_cast<const int8_t*>(resolve(c, op.a)), resolve(c, op.d), op.lda,
+                                     reinterpret_cast<const int8_t*>(resolve(c, op.b)), resolve(c, op.e), op.ldb, op.M,
+                                     op.N, op.K, resolve(c, op.c), op.i1, op.i2, op.alpha, op.beta, (int)op.i0, bt, st,
+                                     c->sm_count),
            "ozaki_gemm");
         break;
+      }
       default:
         throw Fail("unknown op kind");
     }
@@ -341,6 +354,13 @@ int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* c) {
   return 0;
 }
 
+int ecw_ctx_test_assume_ovvv_planes(ecw_ctx* c) {
+  if (!c || c->z.oz_ns <= 0 || (c->z.nocc % 8) || (c->z.nvir % 8)) return -1;
+  c->z.ovvv_planes = true;
+  c->plans.clear();
+  return 0;
+}
+
 int ecw_eris_vvvv_planes(ecw_ctx* c, const double* rows, int64_t row0, int64_t nrows, void* stream) {
   return guarded(c, [&] {
     require_device();
@@ -356,6 +376,25 @@ int ecw_eris_vvvv_planes(ecw_ctx* c, const double* rows, int64_t row0, int64_t n
       c->z.vvvv_planes = true;
       c->plans.clear();
     }
+  });
+}
+
+int ecw_eris_ovvv_planes(ecw_ctx* c, void* stream) {
+  return guarded(c, [&] {
+    require_device();
+    if (c->z.oz_ns <= 0) throw Fail("ecw_eris_ovvv_planes: the INT8 GEMM engine is off (ecw_ctx_set_gemm)");
+    const int64_t o = c->z.nocc, v = c->z.nvir, pv = npair(v);
+    if ((o % 8) || (v % 8)) throw Fail("ecw_eris_ovvv_planes: needs nocc % 8 == 0 and nvir % 8 == 0");
+    for (int s : {S_OVVV_P, S_OVVV_OZ1, S_OVVV_OZ1S, S_OVVV_OZ2, S_OVVV_OZ2S})
+      if (!c->ptr[s]) throw Fail(std::string("slot '") + slot_name(s) + "' is not bound");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // OZ1: rows (m,a), k = ef_p (contiguous);  OZ2: rows ef_p (contiguous), k = (m, a) with a padded to 32 per m
+    ck(launch_ozaki_split2(c->ptr[S_OVVV_P], o * v, 1, pv, pv, 0, 1, c->z.oz_ns,
+                           reinterpret_cast<int8_t*>(c->ptr[S_OVVV_OZ1]), c->ptr[S_OVVV_OZ1S], st), "ozaki_split(ovvv 1)");
+    ck(launch_ozaki_split2(c->ptr[S_OVVV_P], pv, o, v, 1, v * pv, pv, c->z.oz_ns,
+                           reinterpret_cast<int8_t*>(c->ptr[S_OVVV_OZ2]), c->ptr[S_OVVV_OZ2S], st), "ozaki_split(ovvv 2)");
+    c->z.ovvv_planes = true;          // from now on plans read the planes, not "ovvv_p"
+    c->plans.clear();
   });
 }
 
@@ -561,7 +600,9 @@ int ecw_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, con
 // ---- FP64 GEMM on the INT8 tcgen05 pipe (ozaki.cu): raw entry points for tools/ and tests/
 int64_t ecw_ozaki_plane_bytes(int64_t R, int64_t K, int ns) { return ozaki_plane_bytes(R, K, ns); }
 int64_t ecw_ozaki_padded_rows(int64_t R) { return ozaki_padded_rows(R); }
-int64_t ecw_ozaki_stat_elems(int64_t R) { return 2 * ozaki_padded_rows(R); }
+int64_t ecw_ozaki_stat_elems(int64_t R) { return ozaki_stat_elems(R, 1); }
+int64_t ecw_ozaki_stat_elems2(int64_t R, int64_t K1) { return ozaki_stat_elems(R, K1); }
+int64_t ecw_ozaki_plane_bytes2(int64_t R, int64_t K1, int64_t K2, int ns) { return ozaki_plane_bytes2(R, K1, K2, ns); }
 int ecw_ozaki_tile_n(int ns) { return ozaki_tile_n(ns); }
 
 int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes, double* scale,
@@ -570,6 +611,33 @@ int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t k
     require_device();
     ck(launch_ozaki_split(X, R, K, rs, ks, ns, static_cast<int8_t*>(planes), scale, static_cast<cudaStream_t>(stream)),
        "ozaki_split");
+  });
+}
+
+int ecw_ozaki_split2(const double* X, int64_t R, int64_t K1, int64_t K2, int64_t rs, int64_t ks1, int64_t ks2, int ns,
+                     void* planes, double* stats, void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    ck(launch_ozaki_split2(X, R, K1, K2, rs, ks1, ks2, ns, static_cast<int8_t*>(planes), stats,
+                           static_cast<cudaStream_t>(stream)), "ozaki_split2");
+  });
+}
+
+int ecw_ozaki_gemm_batched(const void* pa, const double* sa, int64_t a_rows, const void* pb, const double* sb,
+                           int64_t b_rows, int64_t M, int64_t N, int64_t K, double* C, int64_t crs, int64_t ccs,
+                           double alpha, double beta, int ns, const int64_t* bt14, void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    OzBatch bt{};
+    bt.batch = bt14[0];
+    bt.a_row0 = bt14[1]; bt.a_rowb = bt14[2]; bt.b_row0 = bt14[3]; bt.b_rowb = bt14[4];
+    bt.a_kb0 = bt14[5]; bt.a_kbb = bt14[6]; bt.b_kb0 = bt14[7]; bt.b_kbb = bt14[8];
+    bt.a_t0 = bt14[9]; bt.a_tb = bt14[10]; bt.b_t0 = bt14[11]; bt.b_tb = bt14[12];
+    bt.c_b = bt14[13];
+    bt.nkb = bt14[14];
+    ck(launch_ozaki_gemm_batched(static_cast<const int8_t*>(pa), sa, a_rows, static_cast<const int8_t*>(pb), sb, b_rows, M,
+                                 N, K, C, crs, ccs, alpha, beta, ns, bt, static_cast<cudaStream_t>(stream), 0),
+       "ozaki_gemm_batched");
   });
 }
 
@@ -626,7 +694,7 @@ int ecw_op_contract(ecw_ctx* c, double alpha, const ecw_tensor* A, const char* s
   return guarded_rc(c, [&] {
     require_device();
     Plan P;
-    P.oz_ns = c->z.oz_ns; P.oz_min_flops = c->z.oz_min_flops;
+    P.oz_ns = c->z.oz_ns; P.oz_min_flops = c->z.oz_min_flops; P.nocc = c->z.nocc; P.nvir = c->z.nvir;
     c->ptr[S_A0] = (double*)A->ptr; c->ptr[S_A1] = (double*)B->ptr; c->ptr[S_B0] = (double*)C->ptr;
     P.contract(alpha, from_desc(A, S_A0), sa, from_desc(B, S_A1), sb, beta, from_desc(C, S_B0), sc, "op");
     c->op_plan = std::move(P);

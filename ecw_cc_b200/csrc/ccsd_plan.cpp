@@ -113,8 +113,64 @@ void emit_wovvo(Plan& P, const Slots& s, const Tensor& t1, const Tensor& t2x, do
   P.allgather(mine, chunk * Wph.str[0], full, "Wovvo rows");
 }
 
+
+// ---- ovvv-streaming terms on the INT8 pipe from the constant digit planes of ovvv_p (one GPU, nocc, nvir % 8 == 0)
+bool ovvv_fast(const Plan& P) { return P.ovvv_planes && P.world == 1; }
+
+// out[i,a] += alpha * sum_{m,e,f} amp[i,m,e,f] ovvv[m,a,e,f]      (CCSD.py:294 T1, :585-586 v5, :499-500 L1)
+// = alpha * sum_m sum_{e<f} (amp[imef] - amp[imfe]) ovvv_p[(m,a), ef_p]: one product per m over rows of the plane
+// set OZ1, partial results summed in a fixed order.
+void emit_pair_ovvv(Plan& P, const Slots& s, double alpha, const Tensor& amp, const Tensor& out, const char* note) {
+  const int64_t o = s.o, v = s.v, pv = s.pv;
+  Tensor av = amp;                                   // view [m,i,e,f]
+  std::swap(av.dim[0], av.dim[1]);
+  std::swap(av.str[0], av.str[1]);
+  Tensor Tp = P.tmp({o * o, pv});
+  P.pack(1.0, av, 2 | 4, 0.0, Tp);
+  OzSet T = P.oz_cut(Tp, o * o, pv, 1, 0, pv, 1, note);
+  P.release(Tp);
+  Tensor part = P.tmp({o, o, v});                    // [m, i, a]
+  OzSel sa, sb;
+  sa.rowb = v;                                       // rows (m, a) of OZ1
+  sb.rowb = o;                                       // rows (m, i) of the amplitude planes
+  P.oz_mm(1.0, P.oz_const_ovvv1(), sa, T, sb, v, o, o, 0.0, part, 1, v, o * v, note);
+  P.oz_release(T);
+  Op r;
+  r.kind = OP_REDUCE;
+  r.a = part;
+  r.i0 = o;
+  r.M = o; r.N = v;
+  r.c = out;
+  r.i1 = out.str[0]; r.i2 = out.str[1];
+  r.alpha = alpha; r.beta = 1.0;
+  r.note = std::string(note) + " [sum over m]";
+  P.ops.push_back(r);
+  P.release(part);
+}
+
+// xp[i,j,ab_p] = alpha * sum_e amp1[i,e] ovvv[j,e,a,b]  for a<b   (CCSD.py:311-312, :484-486): one product per j
+// over one k1 = j of the plane set OZ2 (rows ab_p, k = (j, e)).
+void emit_t1_ovvv_packed(Plan& P, const Slots& s, double alpha, const Tensor& amp1, const Tensor& xp, const char* note) {
+  const int64_t o = s.o, v = s.v, pv = s.pv;
+  OzSet T = P.oz_cut(amp1, o, amp1.str[0], 1, 0, v, amp1.str[1], note);
+  OzSel sa, sb;
+  sa.k1b = 1; sa.nk1 = 1;                            // k1 = j
+  P.oz_mm(alpha, P.oz_const_ovvv2(), sa, T, sb, pv, o, o, 0.0, xp, 1, o * pv, pv, note);
+  P.oz_release(T);
+}
+
 // r2[ijab] += x[ijab] - x[jiab] with x[ijab] = -sum_e t1[ie] ovvv[jeab] (CCSD.py:311-312), distributed over j
 void emit_t1_ovvv_term(Plan& P, const Slots& s, const Tensor& t1, const Tensor& x, const Tensor& r2) {
+  if (ovvv_fast(P)) {
+    Tensor xp = P.tmp({s.o * s.o, s.pv});            // [(i,j), ab_p]
+    emit_t1_ovvv_packed(P, s, -1.0, t1, xp, "t1.ovvv (packed pair, INT8)");
+    Tensor r2T = r2;
+    std::swap(r2T.str[0], r2T.str[1]);
+    P.unpack(1.0, xp, 2, 1.0, r2);
+    P.unpack(-1.0, xp, 2, 1.0, r2T);
+    P.release(xp);
+    return;
+  }
   if (P.world == 1) {
     P.contract(-1.0, t1, "ie", s.ovvv, "jeab", 0.0, x, "ijab");
     P.axpby(1.0, x, 1.0, r2);
@@ -214,7 +270,8 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(-1.0, Foo, "mi", t1, "ma", 1.0, r1, "ia");
   P.contract(1.0, t2ph, "iame", Fov, "me", 1.0, r1, "ia");
   P.contract(-1.0, s.ovov_ph, "ianf", t1, "nf", 1.0, r1, "ia");
-  P.contract_split(-0.5, t2, "imef", s.ovvv, "maef", r1, "ia", 'm', "T1 ovvv");
+  if (ovvv_fast(P)) emit_pair_ovvv(P, s, -0.5, t2, r1, "T1 ovvv");
+  else P.contract_split(-0.5, t2, "imef", s.ovvv, "maef", r1, "ia", 'm', "T1 ovvv");
   P.contract(0.5, t2, "mnea", s.ooov, "mnie", 1.0, r1, "ia");
 
   // T2 residual, CCSD.py:297-314
@@ -338,7 +395,8 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(1.0, q, "kj", t1, "kb", 1.0, v5T, "jb");
   P.release(q);
   P.contract(0.5, s.ooov, "kljc", t2, "klcb", 1.0, v5T, "jb");
-  P.contract_split(-0.5, t2, "jkdc", s.ovvv, "kbdc", v5T, "jb", 'k', "v5 ovvv");
+  if (ovvv_fast(P)) emit_pair_ovvv(P, s, -0.5, t2, v5T, "v5 ovvv");
+  else P.contract_split(-0.5, t2, "jkdc", s.ovvv, "kbdc", v5T, "jb", 'k', "v5 ovvv");
 
   Tensor w3T = P.tmp({o, v});          // w3T[k,c] = w3[c,k]
   P.axpby(1.0, v5T, 0.0, w3T);
@@ -441,7 +499,15 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.contract(1.0, x_vv, "ca", s.oovv, "ijcb", 1.0, y, "ijab");
   P.axpby(-1.0, y, 1.0, r2);
   P.permute(1.0, y, "ijba", 1.0, r2, "ijab");
-  if (P.world == 1) {
+  if (ovvv_fast(P)) {
+    // y[pqrs] = sum_c l1[qc] ovvv[pcrs]: yp[q,p,rs_p] from the planes, expanded with the (p,q) view of y
+    Tensor yp = P.tmp({o * o, s.pv});
+    emit_t1_ovvv_packed(P, s, 1.0, l1, yp, "l1.ovvv (packed pair, INT8)");
+    Tensor yT = y;
+    std::swap(yT.str[0], yT.str[1]);
+    P.unpack(1.0, yp, 2, 0.0, yT);
+    P.release(yp);
+  } else if (P.world == 1) {
     P.contract(1.0, l1, "qc", s.ovvv, "pcrs", 0.0, y, "pqrs");
   } else {
     Tensor yp = P.tmp_lead_padded({o, o, v, v});
@@ -471,7 +537,8 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.release(lt_p);
   P.contract(-0.25, lt, "ikjl", s.ooov, "jlka", 1.0, r1, "ia", "wvvvo: ooov.tau");
   P.release(lt);
-  P.contract_split(-0.5, l2, "ikbc", s.ovvv, "kabc", r1, "ia", 'k', "wvvvo: ovvv");
+  if (ovvv_fast(P)) emit_pair_ovvv(P, s, -0.5, l2, r1, "wvvvo: ovvv");
+  else P.contract_split(-0.5, l2, "ikbc", s.ovvv, "kabc", r1, "ia", 'k', "wvvvo: ovvv");
   Tensor Xph = P.tmp_lead_padded({o, v, o, v});
   P.contract_lead_dist(1.0, l2ph, "ibjc", t2ph, "jckd", Xph, "ibkd", "R8 l2.t2");
   P.contract_split(1.0, Xph, "ibkd", s.ovvv, "kbda", r1, "ia", 'k', "wvvvo: ovvv.t2 (K4 refactored)");
@@ -560,7 +627,8 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(-1.0, Foo, "mi", t1, "ma", 1.0, r1, "ia");
   P.contract(1.0, t2ph, "iame", Fov, "me", 1.0, r1, "ia");
   P.contract(-1.0, s.ovov_ph, "ianf", t1, "nf", 1.0, r1, "ia");
-  P.contract_split(-0.5, t2, "imef", s.ovvv, "maef", r1, "ia", 'm', "T1 ovvv");
+  if (ovvv_fast(P)) emit_pair_ovvv(P, s, -0.5, t2, r1, "T1 ovvv");
+  else P.contract_split(-0.5, t2, "imef", s.ovvv, "maef", r1, "ia", 'm', "T1 ovvv");
   P.contract(-0.5, t2, "mnae", s.ooov, "mnie", 1.0, r1, "ia");
 
   Tensor x = P.tmp({o, o, v, v});
@@ -692,7 +760,8 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(1.0, q, "kj", t1, "kb", 1.0, v5T, "jb");
   P.release(q);
   P.contract(-0.5, s.ooov, "kljc", t2, "klbc", 1.0, v5T, "jb");
-  P.contract_split(-0.5, t2, "jkdc", s.ovvv, "kbdc", v5T, "jb", 'k', "v5 ovvv");
+  if (ovvv_fast(P)) emit_pair_ovvv(P, s, -0.5, t2, v5T, "v5 ovvv");
+  else P.contract_split(-0.5, t2, "jkdc", s.ovvv, "kbdc", v5T, "jb", 'k', "v5 ovvv");
 
   Tensor w3T = P.tmp({o, v});
   P.axpby(1.0, v5T, 0.0, w3T);
@@ -802,7 +871,15 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.contract(1.0, x_vv, "ca", s.oovv, "ijcb", 1.0, y, "ijab");
   P.axpby(-1.0, y, 1.0, r2);
   P.permute(1.0, y, "ijba", 1.0, r2, "ijab");
-  if (P.world == 1) {
+  if (ovvv_fast(P)) {
+    // y[pqrs] = sum_c l1[qc] ovvv[pcrs]: yp[q,p,rs_p] from the planes, expanded with the (p,q) view of y
+    Tensor yp = P.tmp({o * o, s.pv});
+    emit_t1_ovvv_packed(P, s, 1.0, l1, yp, "l1.ovvv (packed pair, INT8)");
+    Tensor yT = y;
+    std::swap(yT.str[0], yT.str[1]);
+    P.unpack(1.0, yp, 2, 0.0, yT);
+    P.release(yp);
+  } else if (P.world == 1) {
     P.contract(1.0, l1, "qc", s.ovvv, "pcrs", 0.0, y, "pqrs");
   } else {
     Tensor yp = P.tmp_lead_padded({o, o, v, v});
@@ -830,7 +907,8 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.release(v4ph);
   P.contract(-0.25, lt, "ikjl", s.ooov, "jlka", 1.0, r1, "ia", "wvvvo: ooov.tau");
   P.release(lt);
-  P.contract_split(-0.5, l2, "ikbc", s.ovvv, "kabc", r1, "ia", 'k', "wvvvo: ovvv");
+  if (ovvv_fast(P)) emit_pair_ovvv(P, s, -0.5, l2, r1, "wvvvo: ovvv");
+  else P.contract_split(-0.5, l2, "ikbc", s.ovvv, "kabc", r1, "ia", 'k', "wvvvo: ovvv");
   Tensor l2ph = P.tmp({o, v, o, v});
   P.permute(1.0, l2, "ijab", 0.0, l2ph, "iajb", "l2 ph layout");
   Tensor Xph = P.tmp_lead_padded({o, v, o, v});

@@ -13,9 +13,15 @@ struct Sizes {
   int oz_ns = 0;
   double oz_min_flops = 2e10;
   bool vvvv_planes = false;
+  // ovvv_p is bound as digit planes in both orientations ("ovvv_oz1/2" + statistics) instead of FP64: R4/R6/R9 skip
+  // their per-call cuts and the ovvv-streaming terms with a contracted or free antisymmetric pair run on the INT8
+  // pipe as batched products (needs nocc % 8 == 0 and nvir % 8 == 0: sub-blocks start on 8-row groups)
+  bool ovvv_planes = false;
   void apply(Plan& P) const {
     P.rank = rank; P.world = world;
+    P.nocc = nocc; P.nvir = nvir;
     P.oz_ns = oz_ns; P.oz_min_flops = oz_min_flops; P.vvvv_planes = vvvv_planes && oz_ns > 0;
+    P.ovvv_planes = ovvv_planes && oz_ns > 0;
   }
 };
 

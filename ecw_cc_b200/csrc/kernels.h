@@ -32,10 +32,38 @@ int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns);
 // by chunk (row0 a multiple of 128; every chunk but the last a multiple of 128 rows)
 cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, int8_t* planes,
                                double* scale, cudaStream_t st, int64_t row0 = 0, int64_t total_rows = 0);
+// two-level contraction index k = (k1, k2), element at X[r*rs + k1*ks1 + k2*ks2] (rs == 1 or ks2 == 1); k2 is padded
+// to a multiple of 32 per k1 (k-block index k1*ceil(K2/32) + k2/32), and the statistics also hold the row sums per k1:
+// stats = [scales | row sums | row sums of k1 = 0 | ... ] (ozaki_stat_elems doubles).  A contiguous range of k1
+// values of such a plane set is itself a valid operand (OzBatch::*_kb0/_kbb/_t0/_tb).
+int64_t ozaki_kblocks(int64_t K1, int64_t K2);
+int64_t ozaki_plane_bytes2(int64_t R, int64_t K1, int64_t K2, int ns);
+int64_t ozaki_stat_elems(int64_t R, int64_t K1);
+cudaError_t launch_ozaki_split2(const double* X, int64_t R, int64_t K1, int64_t K2, int64_t rs, int64_t ks1, int64_t ks2,
+                                int ns, int8_t* planes, double* stats, cudaStream_t st, int64_t row0 = 0,
+                                int64_t total_rows = 0);
 // C[m*crs + n*ccs] = alpha * sum_k A[m,k] B[n,k] + beta * C  from the digit planes of A (M rows) and B (N rows)
 cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* pb, const double* sb, int64_t M, int64_t N,
                               int64_t K, double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns,
                               cudaStream_t st, int sm_count);
+// batch of independent products b = 0..batch-1 over sub-blocks of two plane sets:
+//   rows   [x_row0 + b*x_rowb, +M or +N)   (multiples of 8) of the set,
+//   k-blocks [x_kb0 + b*x_kbb, + nkb)  (nkb = 0: ceil(K/32); a two-level index has nk1*ceil(K2/32)),
+//   row sums at stats[x_t0 + b*x_tb + row]  (x_t0 = padded rows of the set: whole-K sums; (2+k1)*padded: per-k1 sums),
+//   C_b = C + b*c_b.
+struct OzBatch {
+  int64_t batch;
+  int64_t a_row0, a_rowb, b_row0, b_rowb;
+  int64_t a_kb0, a_kbb, b_kb0, b_kbb;
+  int64_t a_t0, a_tb, b_t0, b_tb;
+  int64_t c_b;
+  int64_t nkb;
+};
+// a_rows / b_rows: total rows of the two plane sets (their slab size)
+cudaError_t launch_ozaki_gemm_batched(const int8_t* pa, const double* sa, int64_t a_rows, const int8_t* pb,
+                                      const double* sb, int64_t b_rows, int64_t M, int64_t N, int64_t K, double* C,
+                                      int64_t crs, int64_t ccs, double alpha, double beta, int ns, const OzBatch& bt,
+                                      cudaStream_t st, int sm_count);
 
 constexpr int KMAXD = 6;
 struct PermArgs {

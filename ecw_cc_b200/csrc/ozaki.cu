@@ -122,17 +122,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 struct OzGemmParams {
   const int8_t* pa;      // digit planes of the M-side operand
   const int8_t* pb;      // digit planes of the N-side operand
-  const double* sa;      // row scales 2^e, length Mp
+  const double* sa;      // statistics of the M-side plane set: [scales | row sums | per-k1 row sums ...]
   const double* sb;
-  const double* ta;      // row sums  sum_k X[r,k] / s_r, length Mp
-  const double* tb;
   double* C;
-  int64_t M, N, K;       // logical extents
+  int64_t M, N, K;       // logical extents of ONE product (K = true contraction length of a batch)
   int64_t Mp, Np;        // padded row counts of the two plane sets (multiples of 128)
-  int64_t crs, ccs;      // C[m*crs + n*ccs]
+  int64_t crs, ccs;      // C[b*c_b + m*crs + n*ccs]
   double alpha, beta;
   double cprime;         // c = sum_{p=1..NS-1} 256^-p
   uint32_t lbo, sbo;     // descriptor strides (bytes)
+  // batch b = 0..batch-1 of independent products (OzBatch, kernels.h)
+  OzBatch bt;
 };
 
 // tile columns: NS accumulators of TN int32 columns must fit the 512 TMEM columns; every MMA needs N % 16 == 0
@@ -174,8 +174,9 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t tiles_m = (p.M + OZ_TM - 1) / OZ_TM, tiles_n = (p.N + TN - 1) / TN;
-  const int64_t ntiles = tiles_m * tiles_n;
-  const int nkb = (int)((p.K + OZ_BK - 1) / OZ_BK);
+  const int64_t tiles_mn = tiles_m * tiles_n;
+  const int64_t ntiles = tiles_mn * p.bt.batch;
+  const int nkb = p.bt.nkb > 0 ? (int)p.bt.nkb : (int)((p.K + OZ_BK - 1) / OZ_BK);
   constexpr int KB_FLUSH = OZ_KFLUSH / OZ_BK;
   const int nchunk = (nkb + KB_FLUSH - 1) / KB_FLUSH;
 
@@ -207,9 +208,12 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int64_t tm, tn;
-        tile_coord(tile, tiles_m, tiles_n, tm, tn);
-        const int8_t* ga = p.pa + tm * Cfg::A_PLANE;
-        const int8_t* gb = p.pb + tn * Cfg::B_PLANE;
+        const int64_t b = tile / tiles_mn;
+        tile_coord(tile - b * tiles_mn, tiles_m, tiles_n, tm, tn);
+        const int8_t* ga = p.pa + (p.bt.a_row0 + b * p.bt.a_rowb) * OZ_BK + tm * Cfg::A_PLANE +
+                           (p.bt.a_kb0 + b * p.bt.a_kbb) * NS * a_slab;
+        const int8_t* gb = p.pb + (p.bt.b_row0 + b * p.bt.b_rowb) * OZ_BK + tn * Cfg::B_PLANE +
+                           (p.bt.b_kb0 + b * p.bt.b_kbb) * NS * b_slab;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const uint32_t st = it % STAGES, use = it / STAGES;
           mbar_wait(&empty[st], (use & 1) ^ 1);
@@ -274,7 +278,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
     uint32_t acc_it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
-      tile_coord(tile, tiles_m, tiles_n, tm, tn);
+      const int64_t b = tile / tiles_mn;
+      tile_coord(tile - b * tiles_mn, tiles_m, tiles_n, tm, tn);
       const int64_t m = tm * OZ_TM + row, n0 = tn * TN;
       double run[TN];
 #pragma unroll
@@ -301,9 +306,12 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
       }
       if (m < p.M) {
         // C = alpha sA sB (4 * 2^-16 H + c (tA + tB) - c^2 K) + beta C
-        const double fa = p.alpha * p.sa[m];
-        const double um = p.cprime * p.ta[m] - cK;
-        double* crow = p.C + m * p.crs + n0 * p.ccs;
+        const int64_t ar = p.bt.a_row0 + b * p.bt.a_rowb + m, br = p.bt.b_row0 + b * p.bt.b_rowb;
+        const double* __restrict__ ta = p.sa + p.bt.a_t0 + b * p.bt.a_tb;
+        const double* __restrict__ tb = p.sb + p.bt.b_t0 + b * p.bt.b_tb;
+        const double fa = p.alpha * p.sa[ar];
+        const double um = p.cprime * ta[ar] - cK;
+        double* crow = p.C + b * p.bt.c_b + m * p.crs + n0 * p.ccs;
         const int nn = (int)min((int64_t)TN, p.N - n0);
         const bool vec = p.ccs == 1 && nn == TN && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
 #pragma unroll
@@ -311,8 +319,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
           double o[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int64_t n = min(n0 + jc + q, p.N - 1);
-            o[q] = fa * p.sb[n] * (fma(run[jc + q], 6.103515625e-05 /* 4 * 2^-16 */, um) + p.cprime * p.tb[n]);
+            const int64_t n = br + min(n0 + jc + q, p.N - 1);
+            o[q] = fa * p.sb[n] * (fma(run[jc + q], 6.103515625e-05 /* 4 * 2^-16 */, um) + p.cprime * tb[n]);
           }
           if (vec) {
             if (p.beta != 0.0) {
@@ -354,70 +362,90 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// row statistics: s_r = 2^e_r with |X[r,:]| < s_r (1 for an all-zero or padded row) and
-// t_r = sum_k X[r,k] / s_r (fixed summation order).  X[r*rs + k*ks]; one of rs, ks is 1.
+// row statistics: s_r = 2^e_r with |X[r,:]| < s_r (1 for an all-zero or padded row), t_r = sum_k X[r,k] / s_r
+// (fixed summation order) and, for a two-level contraction index k = (k1, k2), the partial sums per k1.
+// X[r*rs + k1*ks1 + k2*ks2]; stats = [scales (Rp) | row sums (Rp) | row sums per k1 (K1 x Rp) when K1 > 1]
+// with Rp the padded row count of the WHOLE plane set; the pointers passed here are offset to the chunk's first row.
 __device__ __forceinline__ double oz_scale_of(double mx) {
   int e = 0;
   if (mx > 0.0) frexp(mx, &e);          // mx = f 2^e, f in [0.5, 1)
   return mx > 0.0 ? ldexp(1.0, e) : 1.0;
 }
-__global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, int64_t K, int64_t rs, int64_t Rp,
-                                      double* __restrict__ scale, double* __restrict__ rsum) {
+// one warp per row (k2 contiguous)
+__global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, int64_t K1, int64_t K2, int64_t rs,
+                                      int64_t ks1, int64_t Rp_chunk, int64_t Rp, double* __restrict__ stats) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (r >= Rp) return;
-  double mx = 0.0, sm = 0.0;
-  if (r < R) {
-    const double* x = X + r * rs;
-    for (int64_t k = lane; k < K; k += 32) {
-      const double v = x[k];
-      mx = fmax(mx, fabs(v));
-      sm += v;
-    }
+  if (r >= Rp_chunk) return;
+  double mx = 0.0, tot = 0.0;
+  for (int64_t k1 = 0; k1 < K1; ++k1) {
+    double sm = 0.0;
+    if (r < R) {
+      const double* x = X + r * rs + k1 * ks1;
+      for (int64_t k = lane; k < K2; k += 32) {
+        const double v = x[k];
+        mx = fmax(mx, fabs(v));
+        sm += v;
+      }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
     }
+    tot += sm;
+    if (K1 > 1 && lane == 0) stats[(2 + k1) * Rp + r] = sm;     // scaled below
   }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) {
     const double s = oz_scale_of(mx);
-    scale[r] = s;
-    rsum[r] = sm / s;
+    stats[r] = s;
+    stats[Rp + r] = tot / s;
+    if (K1 > 1)
+      for (int64_t k1 = 0; k1 < K1; ++k1) stats[(2 + k1) * Rp + r] /= s;
   }
 }
-__global__ void ozaki_rowstat_rcontig(const double* __restrict__ X, int64_t R, int64_t K, int64_t ks, int64_t Rp,
-                                      double* __restrict__ scale, double* __restrict__ rsum) {
-  __shared__ double red[8][33], reds[8][33];
+// 32 rows x 8 k-lanes per block (rows contiguous)
+__global__ void ozaki_rowstat_rcontig(const double* __restrict__ X, int64_t R, int64_t K1, int64_t K2, int64_t ks1,
+                                      int64_t ks2, int64_t Rp_chunk, int64_t Rp, double* __restrict__ stats) {
+  __shared__ double red[8][33];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * 32 + lane;
-  double mx = 0.0, sm = 0.0;
-  if (r < R)
-    for (int64_t k = wy; k < K; k += 8) {
-      const double v = X[r + k * ks];
-      mx = fmax(mx, fabs(v));
-      sm += v;
-    }
-  red[wy][lane] = mx;
-  reds[wy][lane] = sm;
-  __syncthreads();
-  if (wy == 0 && r < Rp) {
+  double mx = 0.0, tot = 0.0;
+  for (int64_t k1 = 0; k1 < K1; ++k1) {
+    double sm = 0.0;
+    if (r < R)
+      for (int64_t k = wy; k < K2; k += 8) {
+        const double v = X[r + k1 * ks1 + k * ks2];
+        mx = fmax(mx, fabs(v));
+        sm += v;
+      }
+    red[wy][lane] = sm;
+    __syncthreads();
+    if (wy == 0) {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      mx = fmax(mx, red[i][lane]);
-      sm += reds[i][lane];
+      for (int i = 1; i < 8; ++i) sm += red[i][lane];
+      tot += sm;
+      if (K1 > 1 && r < Rp_chunk) stats[(2 + k1) * Rp + r] = sm;
     }
+    __syncthreads();
+  }
+  red[wy][lane] = mx;
+  __syncthreads();
+  if (wy == 0 && r < Rp_chunk) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmax(mx, red[i][lane]);
     const double s = oz_scale_of(mx);
-    scale[r] = s;
-    rsum[r] = sm / s;
+    stats[r] = s;
+    stats[Rp + r] = tot / s;
+    if (K1 > 1)
+      for (int64_t k1 = 0; k1 < K1; ++k1) stats[(2 + k1) * Rp + r] /= s;
   }
 }
 
-// cut X into NS digit planes (layout in the header comment).  Block = 128 rows x one k-block (32 k),
-// thread t: row t%128, 16-byte k-chunk t/128.
+// cut X into NS digit planes (layout in the header comment).  Block = 128 rows x one k-block (32 k2 of one k1),
+// thread t: row t%128, 16-byte k-chunk t/128.  k-block index = k1 * ceil(K2/32) + k2/32: k2 is padded per k1.
 template <int NS>
-__global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restrict__ X, int64_t R, int64_t K, int64_t rs,
-                                                          int64_t ks, int64_t Rp, int64_t row0,
+__global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restrict__ X, int64_t R, int64_t K2, int64_t rs,
+                                                          int64_t ks1, int64_t ks2, int64_t Rp, int64_t row0,
                                                           const double* __restrict__ scale,
                                                           int8_t* __restrict__ planes) {
   // X, scale: the chunk (local rows 0..R); planes: the whole set of Rp padded rows, chunk rows start at row0
@@ -425,12 +453,14 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
   const int64_t r = (int64_t)blockIdx.x * 128 + (t & 127);
   const int j = t >> 7;
   const int64_t kb = blockIdx.y;
-  const int64_t k0 = kb * OZ_BK + j * 16;
+  const int64_t nkb2 = (K2 + OZ_BK - 1) / OZ_BK;
+  const int64_t k1 = kb / nkb2;
+  const int64_t k0 = (kb - k1 * nkb2) * OZ_BK + j * 16;
   double y[16];          // (x/s + 1)/2 in [0,1]; negative = padding (all digits 0)
   if (r < R) {
     const double inv = 0.5 / scale[r];     // exact: a power of two
-    const double* src = X + r * rs + k0 * ks;
-    if (ks == 1 && k0 + 16 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    const double* src = X + r * rs + k1 * ks1 + k0 * ks2;
+    if (ks2 == 1 && k0 + 16 <= K2 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
         const double2 v = *reinterpret_cast<const double2*>(src + i);
@@ -439,7 +469,7 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) y[i] = (k0 + i < K) ? fma(src[i * ks], inv, 0.5) : -1.0;
+      for (int i = 0; i < 16; ++i) y[i] = (k0 + i < K2) ? fma(src[i * ks2], inv, 0.5) : -1.0;
     }
   } else {
 #pragma unroll
@@ -477,7 +507,7 @@ cudaError_t launch_gemm_ns(OzGemmParams p, cudaStream_t st, int sm_count) {
   double c = 0.0;
   for (int q = 1; q < NS; ++q) c += ldexp(1.0, -8 * q);
   p.cprime = c;
-  const int64_t tiles = ((p.M + OZ_TM - 1) / OZ_TM) * ((p.N + TN - 1) / TN);
+  const int64_t tiles = ((p.M + OZ_TM - 1) / OZ_TM) * ((p.N + TN - 1) / TN) * p.bt.batch;
   const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
   kern<<<grid, 192, Cfg::SMEM, st>>>(p);
   return cudaGetLastError();
@@ -493,47 +523,56 @@ int ozaki_tile_n(int ns) {
   return 64;
 }
 int64_t ozaki_padded_rows(int64_t R) { return (R + 127) / 128 * 128; }
-// + one B tile of slack: the last N-side tile of the last slab may start inside the padded rows and run past them
-int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns) {
-  return ozaki_padded_rows(R) * ((K + OZ_BK - 1) / OZ_BK * OZ_BK) * ns + 4096;
+int64_t ozaki_kblocks(int64_t K1, int64_t K2) { return K1 * ((K2 + OZ_BK - 1) / OZ_BK); }
+// + one tile of slack: the last tile of the last slab may start inside the padded rows and run past them
+int64_t ozaki_plane_bytes2(int64_t R, int64_t K1, int64_t K2, int ns) {
+  return ozaki_padded_rows(R) * ozaki_kblocks(K1, K2) * OZ_BK * ns + 4096;
 }
+int64_t ozaki_plane_bytes(int64_t R, int64_t K, int ns) { return ozaki_plane_bytes2(R, 1, K, ns); }
+int64_t ozaki_stat_elems(int64_t R, int64_t K1) { return (K1 > 1 ? 2 + K1 : 2) * ozaki_padded_rows(R); }
 
-cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, int8_t* planes,
-                               double* scale, cudaStream_t st, int64_t row0, int64_t total_rows) {
-  if (ns < 3 || ns > 8 || (rs != 1 && ks != 1) || (row0 & 127)) return cudaErrorInvalidValue;
+cudaError_t launch_ozaki_split2(const double* X, int64_t R, int64_t K1, int64_t K2, int64_t rs, int64_t ks1, int64_t ks2,
+                                int ns, int8_t* planes, double* stats, cudaStream_t st, int64_t row0, int64_t total_rows) {
+  if (ns < 3 || ns > 8 || (rs != 1 && ks2 != 1) || (row0 & 127) || K1 < 1) return cudaErrorInvalidValue;
   if (total_rows <= 0) total_rows = row0 + R;
   if (row0 + R > total_rows || (row0 + R < total_rows && (R & 127))) return cudaErrorInvalidValue;
   const int64_t Rp = ozaki_padded_rows(R);              // rows this launch writes (incl. zero padding)
   const int64_t Rp_total = ozaki_padded_rows(total_rows);
-  double* sc = scale + row0;                            // stats: [scales (Rp_total) | row sums (Rp_total)]
-  double* sm = scale + Rp_total + row0;
-  if (ks == 1) {
-    ozaki_rowstat_kcontig<<<(unsigned)((Rp + 7) / 8), 256, 0, st>>>(X, R, K, rs, Rp, sc, sm);
+  double* sc = stats + row0;
+  if (ks2 == 1) {
+    ozaki_rowstat_kcontig<<<(unsigned)((Rp + 7) / 8), 256, 0, st>>>(X, R, K1, K2, rs, ks1, Rp, Rp_total, sc);
   } else {
-    ozaki_rowstat_rcontig<<<(unsigned)((Rp + 31) / 32), 256, 0, st>>>(X, R, K, ks, Rp, sc, sm);
+    ozaki_rowstat_rcontig<<<(unsigned)((Rp + 31) / 32), 256, 0, st>>>(X, R, K1, K2, ks1, ks2, Rp, Rp_total, sc);
   }
-  const int64_t nkb = (K + OZ_BK - 1) / OZ_BK;
+  const int64_t nkb = ozaki_kblocks(K1, K2);
   if (nkb > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)(Rp / 128), (unsigned)nkb, 1);
   switch (ns) {
 #define ECW_OZ_SPLIT(NS_) \
-  case NS_: ozaki_split_kernel<NS_><<<grid, 256, 0, st>>>(X, R, K, rs, ks, Rp_total, row0, sc, planes); break;
+  case NS_: ozaki_split_kernel<NS_><<<grid, 256, 0, st>>>(X, R, K2, rs, ks1, ks2, Rp_total, row0, sc, planes); break;
     ECW_OZ_SPLIT(3) ECW_OZ_SPLIT(4) ECW_OZ_SPLIT(5) ECW_OZ_SPLIT(6) ECW_OZ_SPLIT(7) ECW_OZ_SPLIT(8)
 #undef ECW_OZ_SPLIT
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* pb, const double* sb, int64_t M, int64_t N,
-                              int64_t K, double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns,
-                              cudaStream_t st, int sm_count) {
+cudaError_t launch_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, int8_t* planes,
+                               double* scale, cudaStream_t st, int64_t row0, int64_t total_rows) {
+  return launch_ozaki_split2(X, R, 1, K, rs, 0, ks, ns, planes, scale, st, row0, total_rows);
+}
+
+cudaError_t launch_ozaki_gemm_batched(const int8_t* pa, const double* sa, int64_t a_rows, const int8_t* pb,
+                                      const double* sb, int64_t b_rows, int64_t M, int64_t N, int64_t K, double* C,
+                                      int64_t crs, int64_t ccs, double alpha, double beta, int ns, const OzBatch& bt,
+                                      cudaStream_t st, int sm_count) {
   OzGemmParams p{};
   p.pa = pa; p.pb = pb; p.sa = sa; p.sb = sb; p.C = C;
   p.M = M; p.N = N; p.K = K;
-  p.Mp = ozaki_padded_rows(M); p.Np = ozaki_padded_rows(N);
-  p.ta = sa + p.Mp; p.tb = sb + p.Np;                   // stats arrays: [scales | row sums]
+  p.Mp = ozaki_padded_rows(a_rows); p.Np = ozaki_padded_rows(b_rows);
   p.crs = crs; p.ccs = ccs; p.alpha = alpha; p.beta = beta;
   p.lbo = 128; p.sbo = 256;
+  p.bt = bt;
+  if (bt.batch < 1 || ((bt.a_row0 | bt.a_rowb | bt.b_row0 | bt.b_rowb) & 7)) return cudaErrorInvalidValue;
   if (sm_count <= 0) sm_count = 148;
   switch (ns) {
     case 3: return launch_gemm_ns<3>(p, st, sm_count);
@@ -544,6 +583,16 @@ cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* 
     case 8: return launch_gemm_ns<8>(p, st, sm_count);
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* pb, const double* sb, int64_t M, int64_t N,
+                              int64_t K, double* C, int64_t crs, int64_t ccs, double alpha, double beta, int ns,
+                              cudaStream_t st, int sm_count) {
+  OzBatch bt{};
+  bt.batch = 1;
+  bt.a_t0 = ozaki_padded_rows(M);        // whole-K row sums
+  bt.b_t0 = ozaki_padded_rows(N);
+  return launch_ozaki_gemm_batched(pa, sa, M, pb, sb, N, M, N, K, C, crs, ccs, alpha, beta, ns, bt, st, sm_count);
 }
 
 }  // namespace ecw

@@ -15,7 +15,7 @@ const char* slot_name(int s) {
   static const char* names[] = {
       "ws", "t1", "t2", "l1", "l2", "fsp", "fock", "out1", "out2", "rdm1", "scal",
       "oooo", "ooov", "oovv", "oovv_ph", "ovov_ph", "ovvv", "oooo_p", "oovv_p", "ovvv_p", "vvvv_p",
-      "vvvv_oz", "vvvv_ozs",
+      "vvvv_oz", "vvvv_ozs", "ovvv_oz1", "ovvv_oz1s", "ovvv_oz2", "ovvv_oz2s",
       "a0", "a1", "a2", "a3", "a4", "a5", "a6", "a7", "a8", "a9",
       "b0", "b1", "b2", "b3", "b4", "b5", "b6", "b7"};
   if (s < 0 || s >= S_COUNT) return "?";
@@ -583,21 +583,22 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
 
   // ---- INT8 tensor-core route (ozaki.cu): one unbatched GEMM, operands cut into digit planes
   {
-    const bool const_planes = vvvv_planes && (A.slot == S_VVVV_P || B.slot == S_VVVV_P);
+    const bool const_a = (vvvv_planes && A.slot == S_VVVV_P) || (ovvv_planes && A.slot == S_OVVV_P);
+    const bool const_b = (vvvv_planes && B.slot == S_VVVV_P) || (ovvv_planes && B.slot == S_OVVV_P);
+    const bool const_planes = const_a || const_b;
     const double fl = 2.0 * (double)Md * (double)Nd * (double)Kd;
     bool oz = oz_ns > 0 && ch.bcls == 0 && Kd >= 1 && (Kd + 31) / 32 <= 65535;
     if (oz && oz_min_flops >= 0.0) {
       // INT8 route (model in oz_time) + cutting the operands (8 B read + ns B written and re-read) against the
       // DMMA route at 30 TFLOP/s: skinny, few-tile or short-K products stay on the DMMA kernels
       MatView vcm = mat_view(C, sc, ch.om, ch.on);
-      const double cut = (8.0 + 2.0 * oz_ns) * ((const_planes && A.slot == S_VVVV_P ? 0.0 : (double)Md) +
-                                                (const_planes && B.slot == S_VVVV_P ? 0.0 : (double)Nd)) * (double)Kd / 5e12;
+      const double cut = (8.0 + 2.0 * oz_ns) * ((const_a ? 0.0 : (double)Md) + (const_b ? 0.0 : (double)Nd)) * (double)Kd / 5e12;
       const double t_oz = oz_time(oz_ns, sm_count, Md, Nd, Kd, vcm.any ? vcm.sr : Nd, vcm.any ? vcm.scol : 1, beta, nullptr) +
                           cut + 2e-5;
       oz = fl >= oz_min_flops && t_oz < 0.8 * fl / 3.0e13;
     }
     if (const_planes && !(oz_ns > 0 && ch.bcls == 0 && ch.a_dir && ch.b_dir))
-      throw PlanError("contract: vvvv_p is bound as digit planes but the contraction is not a plain GEMM: " + tag);
+      throw PlanError("contract: an operand is bound as digit planes but the contraction is not a plain GEMM: " + tag);
     if (oz || const_planes) {
       Tensor tA = A, tB = B;
       int64_t ars, aks, brs, bks;
@@ -736,12 +737,13 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
 }
 
 // ---------------------------------------------------------------- INT8-pipe GEMM
-// sizes mirror ozaki.cu (ozaki_padded_rows / ozaki_plane_bytes / ozaki_tile_n); this file stays CUDA-free
+// sizes mirror ozaki.cu (ozaki_padded_rows / ozaki_plane_bytes2 / ozaki_stat_elems / ozaki_tile_n); this file stays
+// CUDA-free
 static int64_t oz_pad_rows(int64_t r) { return (r + 127) / 128 * 128; }
-static int64_t oz_plane_elems(int64_t R, int64_t K, int ns) {
-  return (oz_pad_rows(R) * ((K + 31) / 32 * 32) * ns + 4096 + 7) / 8;
+static int64_t oz_plane_elems(int64_t R, int64_t K1, int64_t K2, int ns) {
+  return (oz_pad_rows(R) * K1 * ((K2 + 31) / 32 * 32) * ns + 4096 + 7) / 8;
 }
-static int64_t oz_stat_elems(int64_t R) { return 2 * oz_pad_rows(R); }   // [row scales | row sums]
+static int64_t oz_stat_elems(int64_t R, int64_t K1) { return (K1 > 1 ? 2 + K1 : 2) * oz_pad_rows(R); }
 static int oz_tile_n(int ns) { return ns <= 5 ? 96 : (ns == 6 ? 80 : 64); }
 
 // Seconds (model) of one INT8-route GEMM for both role assignments; tile = 128 rows of the first operand x TN rows
@@ -765,57 +767,137 @@ static double oz_time(int ns, int sm_count, int64_t M, int64_t N, int64_t K, int
   return best;
 }
 
-void Plan::emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, const Tensor& B, int64_t brs, int64_t bks,
-                   int64_t M, int64_t N, int64_t K, double beta, const Tensor& C, int64_t crs, int64_t ccs,
+OzSet Plan::oz_cut(const Tensor& X, int64_t R, int64_t rs, int64_t K1, int64_t ks1, int64_t K2, int64_t ks2,
                    const std::string& note) {
-  struct Side { Tensor planes, scales; bool owned; };
-  auto prepare = [&](const Tensor& X, int64_t R, int64_t rs, int64_t ks) {
-    Side s;
-    if (vvvv_planes && X.slot == S_VVVV_P) {
-      // the constant row shard of the packed vvvv: [R, K] with K contiguous, cut once at upload time
-      if (X.off != 0 || ks != 1 || rs != K) throw PlanError("vvvv_p digit planes: unexpected operand view in " + note);
-      s.planes = make_tensor(S_VVVV_OZ, 0, {oz_plane_elems(R, K, oz_ns)});
-      s.scales = make_tensor(S_VVVV_OZS, 0, {oz_stat_elems(R)});
-      s.owned = false;
-      return s;
-    }
-    s.planes = tmp({oz_plane_elems(R, K, oz_ns)});
-    s.scales = tmp({oz_stat_elems(R)});
-    s.owned = true;
-    Op sp;
-    sp.kind = OP_OZ_SPLIT;
-    sp.a = X;
-    sp.c = s.planes;
-    sp.d = s.scales;
-    sp.M = R; sp.K = K; sp.lda = rs; sp.ldb = ks;
-    sp.i0 = oz_ns;
-    sp.note = note;
-    ops.push_back(sp);
-    return s;
-  };
-  Side a = prepare(A, M, ars, aks), b = prepare(B, N, brs, bks);
+  if (oz_ns <= 0) throw PlanError("oz_cut: the INT8 engine is off");
+  OzSet s;
+  s.R = R; s.K1 = K1; s.K2 = K2;
+  s.owned = true;
+  s.planes = tmp({oz_plane_elems(R, K1, K2, oz_ns)});
+  s.stats = tmp({oz_stat_elems(R, K1)});
+  Op sp;
+  sp.kind = OP_OZ_SPLIT;
+  sp.a = X;
+  sp.c = s.planes;
+  sp.d = s.stats;
+  sp.M = R; sp.K = K2; sp.i1 = K1;
+  sp.lda = rs; sp.ldb = ks2; sp.ldc = ks1;
+  sp.i0 = oz_ns;
+  sp.note = note;
+  ops.push_back(sp);
+  return s;
+}
+
+void Plan::oz_release(const OzSet& s) {
+  if (!s.owned) return;
+  release(s.stats);
+  release(s.planes);
+}
+
+OzSet Plan::oz_const_vvvv(int64_t rows) const {
+  const int64_t pv = npair(nvir);
+  OzSet s;
+  s.R = rows; s.K1 = 1; s.K2 = pv;
+  s.planes = make_tensor(S_VVVV_OZ, 0, {oz_plane_elems(rows, 1, pv, oz_ns)});
+  s.stats = make_tensor(S_VVVV_OZS, 0, {oz_stat_elems(rows, 1)});
+  return s;
+}
+OzSet Plan::oz_const_ovvv1() const {
+  const int64_t pv = npair(nvir);
+  OzSet s;
+  s.R = nocc * nvir; s.K1 = 1; s.K2 = pv;
+  s.planes = make_tensor(S_OVVV_OZ1, 0, {oz_plane_elems(s.R, 1, pv, oz_ns)});
+  s.stats = make_tensor(S_OVVV_OZ1S, 0, {oz_stat_elems(s.R, 1)});
+  return s;
+}
+OzSet Plan::oz_const_ovvv2() const {
+  const int64_t pv = npair(nvir);
+  OzSet s;
+  s.R = pv; s.K1 = nocc; s.K2 = nvir;
+  s.planes = make_tensor(S_OVVV_OZ2, 0, {oz_plane_elems(pv, nocc, nvir, oz_ns)});
+  s.stats = make_tensor(S_OVVV_OZ2S, 0, {oz_stat_elems(pv, nocc)});
+  return s;
+}
+
+void Plan::oz_mm(double alpha, const OzSet& A, const OzSel& a, const OzSet& B, const OzSel& b, int64_t M, int64_t N,
+                 int64_t batch, double beta, const Tensor& C, int64_t crs, int64_t ccs, int64_t c_b,
+                 const std::string& note) {
+  const int64_t ank1 = a.nk1 > 0 ? a.nk1 : A.K1, bnk1 = b.nk1 > 0 ? b.nk1 : B.K1;
+  if (A.K2 != B.K2 || ank1 != bnk1) throw PlanError("oz_mm: contraction ranges differ in " + note);
+  if ((ank1 != A.K1 && ank1 != 1) || (bnk1 != B.K1 && bnk1 != 1))
+    throw PlanError("oz_mm: a partial k1 range must be a single k1 in " + note);
+  if (((a.row0 | a.rowb | b.row0 | b.rowb) & 7) != 0) throw PlanError("oz_mm: row offsets must be multiples of 8 in " + note);
+  const int64_t K = ank1 * A.K2;
   Op g;
   g.kind = OP_OZ_GEMM;
   g.alpha = alpha; g.beta = beta;
   g.c = C;
   g.K = K;
   g.i0 = oz_ns;
+  g.batch = batch;
+  g.sC = c_b;
   g.note = note;
-  // tile = 128 rows of the first operand x TN rows of the second: pick the cheaper role assignment
   bool swap = false;
   oz_time(oz_ns, sm_count, M, N, K, crs, ccs, beta, &swap);
-  if (!swap) {
-    g.a = a.planes; g.d = a.scales; g.b = b.planes; g.e = b.scales;
-    g.M = M; g.N = N; g.i1 = crs; g.i2 = ccs;
-  } else {
-    g.a = b.planes; g.d = b.scales; g.b = a.planes; g.e = a.scales;
-    g.M = N; g.N = M; g.i1 = ccs; g.i2 = crs;
-  }
+  const OzSet& X = swap ? B : A;
+  const OzSet& Y = swap ? A : B;
+  const OzSel& x = swap ? b : a;
+  const OzSel& y = swap ? a : b;
+  g.a = X.planes; g.d = X.stats; g.lda = X.R;
+  g.b = Y.planes; g.e = Y.stats; g.ldb = Y.R;
+  g.M = swap ? N : M; g.N = swap ? M : N;
+  g.i1 = swap ? ccs : crs; g.i2 = swap ? crs : ccs;
+  auto fill = [&](const OzSet& S, const OzSel& e, int64_t nk1, int64_t* row0, int64_t* rowb, int64_t* kb0, int64_t* kbb,
+                  int64_t* t0, int64_t* tb) {
+    *row0 = e.row0; *rowb = e.rowb;
+    *kb0 = e.k10 * S.nkb2(); *kbb = e.k1b * S.nkb2();
+    if (nk1 == S.K1) { *t0 = S.rp(); *tb = 0; }                          // whole-index row sums
+    else { *t0 = (2 + e.k10) * S.rp(); *tb = e.k1b * S.rp(); }          // sums of one k1
+  };
+  fill(X, x, ank1, &g.oz[0], &g.oz[1], &g.oz[4], &g.oz[5], &g.oz[8], &g.oz[9]);
+  fill(Y, y, ank1, &g.oz[2], &g.oz[3], &g.oz[6], &g.oz[7], &g.oz[10], &g.oz[11]);
+  g.oz[12] = ank1 * A.nkb2();
   ops.push_back(g);
-  gemm_flops += 2.0 * (double)M * N * K;
-  oz_flops += 2.0 * (double)M * N * K;
-  if (b.owned) { release(b.scales); release(b.planes); }
-  if (a.owned) { release(a.scales); release(a.planes); }
+  gemm_flops += 2.0 * (double)M * N * K * (double)batch;
+  oz_flops += 2.0 * (double)M * N * K * (double)batch;
+}
+
+void Plan::emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, const Tensor& B, int64_t brs, int64_t bks,
+                   int64_t M, int64_t N, int64_t K, double beta, const Tensor& C, int64_t crs, int64_t ccs,
+                   const std::string& note) {
+  const int64_t pv = npair(nvir);
+  // the (m, a) contraction index of the constant ovvv plane set OZ2 is two-level (a padded per m): the other
+  // operand of such a product is cut with the same structure
+  auto is_oz2 = [&](const Tensor& X, int64_t R, int64_t rs, int64_t ks) {
+    return ovvv_planes && X.slot == S_OVVV_P && X.off == 0 && rs == 1 && ks == pv && R == pv && K == nocc * nvir;
+  };
+  const bool two_level = is_oz2(A, M, ars, aks) || is_oz2(B, N, brs, bks);
+  const int64_t K1 = two_level ? nocc : 1, K2 = two_level ? nvir : K;
+  struct Side { OzSet set; OzSel sel; };
+  auto prepare = [&](const Tensor& X, int64_t R, int64_t rs, int64_t ks) {
+    Side s;
+    if (vvvv_planes && X.slot == S_VVVV_P) {
+      // the constant row shard of the packed vvvv: [R, K] with K contiguous, cut once at upload time
+      if (X.off != 0 || ks != 1 || rs != K || K != pv) throw PlanError("vvvv_p digit planes: unexpected operand view in " + note);
+      s.set = oz_const_vvvv(R);
+      return s;
+    }
+    if (ovvv_planes && X.slot == S_OVVV_P) {
+      if (is_oz2(X, R, rs, ks)) { s.set = oz_const_ovvv2(); return s; }
+      if (ks == 1 && rs == pv && K == pv && X.off % pv == 0 && (X.off / pv) % 8 == 0 && X.off / pv + R <= nocc * nvir) {
+        s.set = oz_const_ovvv1();
+        s.sel.row0 = X.off / pv;       // a range of (m,a) rows
+        return s;
+      }
+      throw PlanError("ovvv_p digit planes: unexpected operand view in " + note);
+    }
+    s.set = oz_cut(X, R, rs, K1, K2 * ks, K2, ks, note);
+    return s;
+  };
+  Side a = prepare(A, M, ars, aks), b = prepare(B, N, brs, bks);
+  oz_mm(alpha, a.set, a.sel, b.set, b.sel, M, N, 1, beta, C, crs, ccs, 0, note);
+  oz_release(b.set);
+  oz_release(a.set);
 }
 
 // ---------------------------------------------------------------- dump
@@ -850,7 +932,9 @@ std::string Plan::dump_json() const {
       << ",\"sA\":" << p.sA << ",\"sB\":" << p.sB << ",\"sC\":" << p.sC << ",\"batch\":" << p.batch
       << ",\"ta\":" << p.ta << ",\"tb\":" << p.tb << ",\"splitk\":" << p.splitk << ",\"kchunk\":" << p.kchunk
       << ",\"i0\":" << p.i0 << ",\"i1\":" << p.i1 << ",\"i2\":" << p.i2 << ",\"i3\":" << p.i3
-      << ",\"d0\":" << p.d0 << ",\"d1\":" << p.d1 << ",\"note\":\"" << p.note << "\"}";
+      << ",\"d0\":" << p.d0 << ",\"d1\":" << p.d1 << ",\"oz\":[";
+    for (int q = 0; q < 13; ++q) o << (q ? "," : "") << p.oz[q];
+    o << "],\"note\":\"" << p.note << "\"}";
   }
   o << "\n]}";
   return o.str();

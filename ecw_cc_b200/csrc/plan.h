@@ -31,6 +31,8 @@ enum Slot : int {
   // int8 digit planes + row scales of vvvv_p for the INT8-tensor-core GEMM (ozaki.cu); element
   // offsets into these two slots are in units of 8 bytes like everywhere else
   S_VVVV_OZ, S_VVVV_OZS,
+  // digit planes of ovvv_p in both orientations: OZ1 = rows (m,a), k = ef_p;  OZ2 = rows ef_p, k = (m, a)
+  S_OVVV_OZ1, S_OVVV_OZ1S, S_OVVV_OZ2, S_OVVV_OZ2S,
   // generic argument slots for the CCS entry points
   S_A0, S_A1, S_A2, S_A3, S_A4, S_A5, S_A6, S_A7, S_A8, S_A9,
   S_B0, S_B1, S_B2, S_B3, S_B4, S_B5, S_B6, S_B7,
@@ -70,8 +72,9 @@ enum OpKind : int {
   OP_RDM1,        // assemble the symmetrised rdm1 (CCSD.py:154-160)
   OP_EWISE,       // small CCS element-wise helpers (sub-kind in i0)
   OP_ALLGATHER,   // collective: every rank contributes `a` (i0 elements); `c` receives world*i0 (host runs it)
-  OP_OZ_SPLIT,    // a = X[R=M, K] (element strides lda, ldb) -> c = i0 int8 digit planes, d = row scales
-  OP_OZ_GEMM,     // C[m*i1 + n*i2] = alpha sum_k A[m,k] B[n,k] + beta C from planes a (scales d) and b (scales e)
+  OP_OZ_SPLIT,    // a = X[R=M, (K1=i1, K2=K)] (element strides lda, ldc, ldb) -> c = i0 int8 digit planes, d = statistics
+  OP_OZ_GEMM,     // C_b[m*i1 + n*i2] = alpha sum_k A_b[m,k] B_b[n,k] + beta C_b from plane sets a (stats d, lda rows)
+                  // and b (stats e, ldb rows); sub-blocks per batch in oz[] (OzBatch order), sC = C offset per batch
 };
 
 struct Op {
@@ -86,7 +89,22 @@ struct Op {
   // generic ints / doubles
   int64_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
   double d0 = 0.0, d1 = 0.0;
+  int64_t oz[13] = {0};       // OP_OZ_GEMM: a_row0,a_rowb,b_row0,b_rowb,a_kb0,a_kbb,b_kb0,b_kbb,a_t0,a_tb,b_t0,b_tb,nkb
   std::string note;
+};
+
+// A plane set: the int8 digits of an operand X[R, (K1, K2)] (ozaki.cu) plus its row statistics.
+struct OzSet {
+  Tensor planes, stats;
+  int64_t R = 0, K1 = 1, K2 = 0;
+  bool owned = false;          // lives in the workspace arena
+  int64_t rp() const { return (R + 127) / 128 * 128; }
+  int64_t nkb2() const { return (K2 + 31) / 32; }
+};
+// The part of a plane set one product of a batch reads: rows [row0 + b*rowb, +M|N), k1 values [k10 + b*k1b, +nk1)
+// (nk1 = K1: the whole contraction index; otherwise nk1 must be 1).
+struct OzSel {
+  int64_t row0 = 0, rowb = 0, k10 = 0, k1b = 0, nk1 = 0;   // nk1 = 0: all K1
 };
 
 struct Arena {
@@ -110,6 +128,8 @@ class Plan {
   int oz_ns = 0;
   double oz_min_flops = 0.0;
   bool vvvv_planes = false;    // vvvv_p is bound as digit planes (S_VVVV_OZ/S_VVVV_OZS), not as FP64
+  bool ovvv_planes = false;    // ovvv_p is bound as digit planes in both orientations (S_OVVV_OZ1/2)
+  int64_t nocc = 0, nvir = 0;  // needed to recognise the constant plane sets
   double oz_flops = 0.0;       // part of gemm_flops that runs on the INT8 pipe
   double gemm_flops = 0.0;     // sum of 2MNK over GEMM ops (executed flops)
   double perm_bytes = 0.0;     // bytes moved by engine-inserted permutes
@@ -153,6 +173,19 @@ class Plan {
   void rdm1(const Tensor& doo, const Tensor& dvoT, const Tensor& l1, const Tensor& dvv, const Tensor& out);
   void ewise(int sub, const Tensor& a, const Tensor& b, const Tensor& c, double alpha, double beta,
              int64_t i1 = 0, int64_t i2 = 0);
+
+  // ---- INT8-pipe primitives (ozaki.cu)
+  // cut X[R, (K1,K2)] (element strides rs, ks1, ks2) into oz_ns digit planes in the workspace
+  OzSet oz_cut(const Tensor& X, int64_t R, int64_t rs, int64_t K1, int64_t ks1, int64_t K2, int64_t ks2,
+               const std::string& note);
+  void oz_release(const OzSet& s);
+  OzSet oz_const_vvvv(int64_t rows) const;     // this rank's shard of vvvv_p: rows x P_v
+  OzSet oz_const_ovvv1() const;                // rows (m,a), k = ef_p
+  OzSet oz_const_ovvv2() const;                // rows ef_p, k = (m, a)
+  // batch of products C_b[m*crs + n*ccs] = alpha sum_k A_b[m,k] B_b[n,k] + beta C_b  (C_b = C + b*c_b);
+  // the role assignment (which operand feeds the 128-row side of the tile) is chosen here
+  void oz_mm(double alpha, const OzSet& A, const OzSel& a, const OzSet& B, const OzSel& b, int64_t M, int64_t N,
+             int64_t batch, double beta, const Tensor& C, int64_t crs, int64_t ccs, int64_t c_b, const std::string& note);
 
   int64_t workspace_elems() const { return arena.peak; }
   std::string dump_json() const;

@@ -61,7 +61,7 @@ class DeviceEris(object):
     """Owns the C context, the bound integral layouts and the workspace."""
 
     def __init__(self, nocc, nvir, device=None, rank=0, world=1, group=None, gemm=None, int8_digits=None,
-                 int8_min_flops=None, eri_max=1.0):
+                 int8_min_flops=None, eri_max=1.0, ovvv_planes=None):
         """rank/world/group: one process per GPU; `vvvv_p` is then row-sharded over the packed
         virtual pair index and the heavy contractions are distributed (include/ecw_b200.h).
         gemm: "int8" | "dmma"; int8_digits: None = chosen from eri_max = max |<pq||rs>| (module header)."""
@@ -77,6 +77,10 @@ class DeviceEris(object):
             raise EcwError("ecw_ctx_set_shard failed")
         self.int8_digits, self.int8_min_flops = _gemm_config(gemm, int8_digits, int8_min_flops, self.nvir, eri_max)
         self.check(lib.ecw_ctx_set_gemm(self._h, self.int8_digits, self.int8_min_flops), "ecw_ctx_set_gemm")
+        # constant digit planes of ovvv_p (both orientations): sub-blocks of a plane set start on 8-row groups
+        if ovvv_planes is None:
+            ovvv_planes = os.environ.get("ECW_OVVV_PLANES", "1") != "0"
+        self.use_ovvv_planes = bool(ovvv_planes and self.int8_digits and self.nocc % 8 == 0 and self.nvir % 8 == 0)
         self.buf = {}
         self._ws = None
         self._scal = torch.zeros(16, dtype=torch.float64, device=self.device)
@@ -151,7 +155,7 @@ class DeviceEris(object):
     # -- constructors ----------------------------------------------------------
     @classmethod
     def from_geris(cls, eris, device=None, rank=0, world=1, group=None, gemm=None, int8_digits=None,
-                   int8_min_flops=None):
+                   int8_min_flops=None, ovvv_planes=None):
         """Upload a reference-style container (numpy blocks, Eris.py:132-150)."""
         torch = _torch()
         fock = np.asarray(eris.fock)
@@ -159,7 +163,7 @@ class DeviceEris(object):
         eri_max = max(float(np.abs(np.asarray(getattr(eris, k))).max()) if np.asarray(getattr(eris, k)).size else 0.0
                       for k in ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv"))
         self = cls(nocc, fock.shape[0] - nocc, device, gemm=gemm, int8_digits=int8_digits,
-                   int8_min_flops=int8_min_flops, eri_max=eri_max)          # packed whole first, sharded below
+                   int8_min_flops=int8_min_flops, eri_max=eri_max, ovvv_planes=ovvv_planes)   # packed whole, sharded below
         self.set_fock(fock)
         for name in ("oooo", "ooov", "oovv", "ovvv"):
             t = torch.from_numpy(np.ascontiguousarray(getattr(eris, name), dtype=np.float64)).to(self.device)
@@ -188,6 +192,8 @@ class DeviceEris(object):
             # a dense upload is small: the FP64 shard stays (cc_Wvvvv / Linter getters read it), the
             # residual plans read the digit planes
             self._cut_vvvv_planes(lambda r0, nr: self.buf["vvvv_p"][r0 * self._pv(): (r0 + nr) * self._pv()])
+        if self.use_ovvv_planes:
+            self._cut_ovvv_planes(keep_fp64=True)
         for attr in ("mo_occ", "EHF", "orbspin"):
             if hasattr(eris, attr):
                 setattr(self, attr, getattr(eris, attr))
@@ -195,13 +201,13 @@ class DeviceEris(object):
 
     @classmethod
     def synthetic(cls, nocc, nvir, device=None, scale=0.01, rank=0, world=1, group=None, gemm=None,
-                  int8_digits=None, int8_min_flops=None, keep_fp64_vvvv=False):
+                  int8_digits=None, int8_min_flops=None, keep_fp64_vvvv=False, ovvv_planes=None):
         """Function-defined synthetic integrals generated in place on the device (each rank
         generates only its own rows of the packed vvvv).  With the INT8 engine the packed vvvv is
         generated in row chunks and kept as digit planes only (keep_fp64_vvvv: also the FP64 layout)."""
         torch = _torch()
         self = cls(nocc, nvir, device, rank=rank, world=world, group=group, gemm=gemm, int8_digits=int8_digits,
-                   int8_min_flops=int8_min_flops, eri_max=abs(float(scale)))
+                   int8_min_flops=int8_min_flops, eri_max=abs(float(scale)), ovvv_planes=ovvv_planes)
         planes_only = bool(self.int8_digits) and not keep_fp64_vvvv
         for name in _LAYOUTS:
             if name == "vvvv_p" and planes_only:
@@ -225,6 +231,8 @@ class DeviceEris(object):
                 del tmp
             else:
                 self._cut_vvvv_planes(lambda r0, nr: self.buf["vvvv_p"][r0 * self._pv(): (r0 + nr) * self._pv()])
+        if self.use_ovvv_planes:
+            self._cut_ovvv_planes(keep_fp64=keep_fp64_vvvv)
         n = self.nocc + self.nvir
         self.fock_dev = self.synth_tensor("fock", (n, n))
         self.fock = self.fock_dev.cpu().numpy()
@@ -262,6 +270,24 @@ class DeviceEris(object):
             if r0 >= nsh:
                 break
         torch.cuda.current_stream(self.device).synchronize()
+
+    def _cut_ovvv_planes(self, keep_fp64=False):
+        """ovvv_p -> int8 digit planes in both orientations (ecw_eris_ovvv_planes); the FP64 layout is then
+        dropped unless keep_fp64."""
+        torch = _torch()
+        for name in ("ovvv_oz1", "ovvv_oz1s", "ovvv_oz2", "ovvv_oz2s"):
+            n = lib.ecw_slot_elems(self._h, name.encode())
+            if n < 0:
+                self.check(-1, "ecw_slot_elems(%s)" % name)
+            planes = not name.endswith("s")
+            self.buf[name] = torch.empty(max(int(n), 1) * (8 if planes else 1),
+                                         dtype=torch.int8 if planes else torch.float64, device=self.device)
+            self._bind(name, self.buf[name])
+        self.check(lib.ecw_eris_ovvv_planes(self._h, self.stream()), "ecw_eris_ovvv_planes")
+        torch.cuda.current_stream(self.device).synchronize()
+        if not keep_fp64:
+            self.check(lib.ecw_bind(self._h, b"ovvv_p", None), "ecw_bind(ovvv_p)")
+            del self.buf["ovvv_p"]
 
     def synth_tensor(self, kind, shape, scale=0.01):
         """Synthetic fock / fsp / t1 / l1 / t2 / l2 on the device."""

@@ -68,7 +68,8 @@ int ecw_pending_collective(ecw_ctx* ctx, int64_t* desc6);
  *   "oooo" [o,o,o,o]  "ooov" [o,o,o,v]  "oovv" [o,o,v,v]  "ovvv" [o,v,v,v]
  *   "oovv_ph" [(m,e),(n,f)] = oovv[m,n,e,f]     "ovov_ph" [(i,a),(n,f)] = ovov[n,a,i,f]
  *   "oooo_p" [ij_p,kl_p]  "oovv_p" [ij_p,ab_p]  "ovvv_p" [m,a,ef_p]  "vvvv_p" [ab_p,cd_p]
- *   "vvvv_oz" / "vvvv_ozs": int8 digit planes / row scales of vvvv_p (ecw_eris_vvvv_planes)
+ *   "vvvv_oz" / "vvvv_ozs": int8 digit planes / row statistics of vvvv_p (ecw_eris_vvvv_planes)
+ *   "ovvv_oz1" / "ovvv_oz1s", "ovvv_oz2" / "ovvv_oz2s": the same for ovvv_p, both orientations (ecw_eris_ovvv_planes)
  * with the antisymmetric pair index p(x<y) = y(y-1)/2 + x.  Also bindable:
  * "scal" (16 doubles of device scratch for scalars). */
 int64_t ecw_slot_elems(ecw_ctx* ctx, const char* slot);
@@ -82,6 +83,11 @@ int ecw_eris_pack_from_dense(ecw_ctx* ctx, const double* ovov_dense, const doubl
  * shard ([nrows, P_v], row0 a multiple of 128, every chunk but the last a multiple of 128 rows) chunk by
  * chunk; after the last chunk the plans read the planes and "vvvv_p" need not be bound. */
 int ecw_eris_vvvv_planes(ecw_ctx* ctx, const double* rows, int64_t row0, int64_t nrows, void* stream);
+/* INT8 engine, optional (needs nocc % 8 == 0 and nvir % 8 == 0): cut the bound "ovvv_p" into digit planes in both
+ * orientations — bind "ovvv_oz1"/"ovvv_oz1s" (rows (m,a), k = ef_p) and "ovvv_oz2"/"ovvv_oz2s" (rows ef_p,
+ * k = (m,a)) first.  Afterwards "ovvv_p" need not stay bound; R4/R6/R9 (CCSD.py:602-605, 461-470, 396-402) skip
+ * their per-call cuts and the ovvv terms of CCSD.py:294, 311-312, 499, 585-600 run as batched INT8 products. */
+int ecw_eris_ovvv_planes(ecw_ctx* ctx, void* stream);
 /* Fill every bound integral layout with the function-defined synthetic
  * integrals (DESIGN.md "Synthetic inputs"); dense vvvv never exists. */
 int ecw_eris_synthetic(ecw_ctx* ctx, double scale, void* stream);
@@ -158,6 +164,7 @@ int64_t ecw_op_workspace_needed(ecw_ctx* ctx);
 /* Host-only test hook: plan as if ecw_eris_vvvv_planes had completed (so the lowering of the
  * digit-plane ladders can be dumped and replayed on a box without a GPU). */
 int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* ctx);
+int ecw_ctx_test_assume_ovvv_planes(ecw_ctx* ctx);
 /* JSON dump of the op list a call would launch (host only, no CUDA). */
 int64_t ecw_plan_dump(ecw_ctx* ctx, const char* func, int mode_flags, char* buf, int64_t buflen);
 /* executed GEMM flops (sum of 2MNK) and launches of a plan */
@@ -180,6 +187,18 @@ int64_t ecw_ozaki_stat_elems(int64_t R);
 int ecw_ozaki_tile_n(int ns);
 int ecw_ozaki_split(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes, double* scale,
                     void* stream);
+/* two-level contraction index k = (k1, k2) (element at X[r*rs + k1*ks1 + k2*ks2], k2 padded to 32 per k1; the
+ * statistics then also hold the row sums per k1) and batches of products over sub-blocks of two plane sets:
+ * bt15 = {batch, a_row0, a_rowb, b_row0, b_rowb, a_kb0, a_kbb, b_kb0, b_kbb, a_t0, a_tb, b_t0, b_tb, c_b, nkb}
+ * (csrc/kernels.h, struct OzBatch). */
+int64_t ecw_ozaki_plane_bytes2(int64_t R, int64_t K1, int64_t K2, int ns);
+int64_t ecw_ozaki_stat_elems2(int64_t R, int64_t K1);
+int ecw_ozaki_split2(const double* X, int64_t R, int64_t K1, int64_t K2, int64_t rs, int64_t ks1, int64_t ks2, int ns,
+                     void* planes, double* stats, void* stream);
+int ecw_ozaki_gemm_batched(const void* planes_a, const double* stats_a, int64_t a_rows, const void* planes_b,
+                           const double* stats_b, int64_t b_rows, int64_t M, int64_t N, int64_t K, double* C,
+                           int64_t crs, int64_t ccs, double alpha, double beta, int ns, const int64_t* bt15,
+                           void* stream);
 /* chunked cut: X holds rows [row0, row0+R) of an operand of total_rows rows (row0 and every chunk but the
  * last multiples of 128); planes/scale address the whole plane set */
 int ecw_ozaki_split_rows(const double* X, int64_t R, int64_t K, int64_t rs, int64_t ks, int ns, void* planes,

@@ -53,37 +53,43 @@ def oz_value(D, s, ns):
     return s[:, None] * (2.0 * Dv + oz_cprime(ns))
 
 
-def oz_to_planes(D):
-    """digits [ns][R][K] -> device order [kb][p][rg][j][ri][16], rows padded to 128, k to 32 (flat int8)."""
+def oz_to_planes(D, K1=1):
+    """digits [ns][R][K1*K2] -> device order [kb][p][rg][j][ri][16]: rows padded to 128, k2 to 32 per k1 (flat int8)."""
     ns, R, K = D.shape
-    Rp, Kp = (R + 127) // 128 * 128, (K + 31) // 32 * 32
-    P = np.zeros((ns, Rp, Kp), dtype=np.int8)
-    P[:, :R, :K] = D
-    return np.ascontiguousarray(P.reshape(ns, Rp // 8, 8, Kp // 32, 2, 16).transpose(3, 0, 1, 4, 2, 5)).reshape(-1)
+    K2 = K // K1
+    Rp, K2p = (R + 127) // 128 * 128, (K2 + 31) // 32 * 32
+    P = np.zeros((ns, Rp, K1, K2p), dtype=np.int8)
+    P[:, :R, :, :K2] = D.reshape(ns, R, K1, K2)
+    P = P.reshape(ns, Rp, K1 * K2p)
+    return np.ascontiguousarray(P.reshape(ns, Rp // 8, 8, K1 * K2p // 32, 2, 16).transpose(3, 0, 1, 4, 2, 5)).reshape(-1)
 
 
-def oz_from_planes(buf, ns, R, K):
-    Rp, Kp = (R + 127) // 128 * 128, (K + 31) // 32 * 32
-    P = buf[: ns * Rp * Kp].reshape(Kp // 32, ns, Rp // 8, 2, 8, 16).transpose(1, 2, 4, 0, 3, 5).reshape(ns, Rp, Kp)
-    return P[:, :R, :K]
+def oz_from_planes(buf, ns, Rp, nkb):
+    """flat int8 -> digits [ns][Rp][nkb*32] (padded rows and k kept)."""
+    return buf[: ns * Rp * nkb * 32].reshape(nkb, ns, Rp // 8, 2, 8, 16).transpose(1, 2, 4, 0, 3, 5).reshape(ns, Rp, nkb * 32)
 
 
-def oz_stats(X, s):
-    """device statistics array [row scales (padded to 128) | row sums / scale]."""
-    Rp = (X.shape[0] + 127) // 128 * 128
-    st = np.zeros(2 * Rp)
+def oz_stats(X, s, K1=1):
+    """device statistics array [row scales (padded to 128) | row sums / scale | the same per k1 (K1 > 1)]."""
+    R = X.shape[0]
+    Rp = (R + 127) // 128 * 128
+    st = np.zeros((2 + K1 if K1 > 1 else 2) * Rp)
     st[:Rp] = 1.0
-    st[: X.shape[0]] = s
-    st[Rp: Rp + X.shape[0]] = X.sum(axis=1) / s
+    st[:R] = s
+    st[Rp: Rp + R] = X.sum(axis=1) / s
+    if K1 > 1:
+        part = X.reshape(R, K1, -1).sum(axis=2) / s[:, None]
+        for k1 in range(K1):
+            st[(2 + k1) * Rp: (2 + k1) * Rp + R] = part[:, k1]
     return st
 
 
-def oz_const_slots(X, ns):
-    """(planes, stats) slot arrays for a constant operand X[R,K] (what ecw_eris_vvvv_planes leaves bound)."""
+def oz_const_slots(X, ns, K1=1):
+    """(planes, stats) slot arrays for a constant operand X[R,K] (what ecw_eris_*_planes leaves bound)."""
     D, s = oz_digits(X, ns)
-    pl = oz_to_planes(D)
+    pl = oz_to_planes(D, K1)
     pl = np.concatenate([pl, np.zeros(4096 + (-pl.size) % 8, np.int8)]).view(np.float64).copy()
-    return pl, oz_stats(X, s)
+    return pl, oz_stats(X, s, K1)
 
 
 def oz_product(DA, sa, ta, DB, sb, tb, K, ns):
@@ -189,30 +195,45 @@ class Interp(object):
 
     def op_oz_split(self, op):
         a = op["a"]
-        R, K, ns = op["M"], op["K"], op["i0"]
-        X = np.array(self._mat(a["slot"], a["off"], R, K, op["lda"], op["ldb"]))
+        R, K2, K1, ns = op["M"], op["K"], op["i1"], op["i0"]
+        base = self.slots[a["slot"]].reshape(-1)
+        X = np.array(as_strided(base[a["off"]:], shape=(R, K1, K2),
+                                strides=(8 * op["lda"], 8 * op["ldc"], 8 * op["ldb"]))).reshape(R, K1 * K2)
         assert not np.isnan(X).any(), op["note"]
         D, s = oz_digits(X, ns)
-        pl = oz_to_planes(D)
+        pl = oz_to_planes(D, K1)
         assert pl.size + 4096 <= 8 * op["c"]["dim"][0], op["note"]
         self._bytes(op["c"])[: pl.size] = pl
         st = self.view(op["d"])
-        assert st.shape[0] == 2 * ((R + 127) // 128 * 128)
-        st[...] = oz_stats(X, s)
+        want = oz_stats(X, s, K1)
+        assert st.shape[0] == want.size, op["note"]
+        st[...] = want
 
     def op_oz_gemm(self, op):
         M, N, K, ns = op["M"], op["N"], op["K"], op["i0"]
-        DA = oz_from_planes(self._bytes(op["a"]), ns, M, K)
-        DB = oz_from_planes(self._bytes(op["b"]), ns, N, K)
-        Mp, Np = (M + 127) // 128 * 128, (N + 127) // 128 * 128
+        a_row0, a_rowb, b_row0, b_rowb, a_kb0, a_kbb, b_kb0, b_kbb, a_t0, a_tb, b_t0, b_tb, nkb = op["oz"]
+        if nkb == 0:
+            nkb = (K + 31) // 32
+        Ap, Bp = (op["lda"] + 127) // 128 * 128, (op["ldb"] + 127) // 128 * 128
         sta, stb = self.view(op["d"]), self.view(op["e"])
-        assert not np.isnan(sta).any() and not np.isnan(stb).any(), op["note"]
+        ba, bb = self._bytes(op["a"]), self._bytes(op["b"])
+        nka, nkb_b = (8 * op["a"]["dim"][0] - 4096) // (ns * Ap * 32), (8 * op["b"]["dim"][0] - 4096) // (ns * Bp * 32)
+        DA, DB = oz_from_planes(ba, ns, Ap, nka), oz_from_planes(bb, ns, Bp, nkb_b)
         c = op["c"]
-        C = self._mat(c["slot"], c["off"], M, N, op["i1"], op["i2"])
-        res = op["alpha"] * oz_product(DA, sta[:M], sta[Mp:Mp + M], DB, stb[:N], stb[Np:Np + N], K, ns)
-        if op["beta"] != 0.0:
-            res = res + op["beta"] * C
-        C[...] = res
+        for b in range(op["batch"]):
+            ar, br = a_row0 + b * a_rowb, b_row0 + b * b_rowb
+            ka, kb = (a_kb0 + b * a_kbb) * 32, (b_kb0 + b * b_kbb) * 32
+            da = DA[:, ar:ar + M, ka:ka + nkb * 32]
+            db = DB[:, br:br + N, kb:kb + nkb * 32]
+            ta = sta[a_t0 + b * a_tb + ar: a_t0 + b * a_tb + ar + M]
+            tb = stb[b_t0 + b * b_tb + br: b_t0 + b * b_tb + br + N]
+            sa, sb = sta[ar:ar + M], stb[br:br + N]
+            assert not (np.isnan(sa).any() or np.isnan(sb).any() or np.isnan(ta).any() or np.isnan(tb).any()), op["note"]
+            C = self._mat(c["slot"], c["off"] + b * op["sC"], M, N, op["i1"], op["i2"])
+            res = op["alpha"] * oz_product(da, sa, ta, db, sb, tb, K, ns)
+            if op["beta"] != 0.0:
+                res = res + op["beta"] * C
+            C[...] = res
 
     def op_fill(self, op):
         self.view(op["c"])[...] = op["alpha"]

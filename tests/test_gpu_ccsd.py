@@ -90,7 +90,7 @@ def test_synthetic_tensors_bit_exact(ecw):
     assert np.array_equal(de.synth_tensor("l2", (o, o, v, v)).cpu().numpy(), l2)
 
 
-@pytest.mark.parametrize("ov", [(2, 3), (4, 6), (5, 7), (6, 11), (8, 20), (10, 33)])
+@pytest.mark.parametrize("ov", [(2, 3), (4, 6), (5, 7), (6, 11), (8, 20), (10, 33), (8, 16), (16, 24)])
 def test_ccsd_matches_oracle(ecw, ov, engine):
     from oracle import synth
     from oracle.ccsd_np import OracleGCC
@@ -169,7 +169,7 @@ def test_device_resident_and_synthetic_eris(ecw, engine):
     assert np.array_equal(cc.eris.oovv, synth.SynthEris(o, v).oovv)
 
 
-@pytest.mark.parametrize("ov", [(3, 4), (5, 9), (8, 21)])
+@pytest.mark.parametrize("ov", [(3, 4), (5, 9), (8, 21), (8, 16)])
 def test_general_path_unsymmetric_amplitudes(ecw, ov, engine):
     """t2/l2 without permutational symmetry (what the reference's L1 update produces, Q1):
     the host measures the antisymmetry defect on the device and runs the general path."""

@@ -6,7 +6,7 @@ is exercised, against the FP64 DMMA engine."""
 import numpy as np
 import pytest
 
-from plan_interp import oz_digits, oz_to_planes, oz_stats, oz_value
+from plan_interp import oz_digits, oz_to_planes, oz_stats, oz_value, oz_const_slots, oz_product
 
 pytestmark = pytest.mark.gpu
 
@@ -72,7 +72,7 @@ def test_chunked_plane_set_equals_whole(ecw):
     for r0 in range(0, R, 256):
         nr = min(256, R - r0)
         _split(ecw, X[r0:r0 + nr], ns, row0=r0, total=R, planes=planes, scale=scale)
-    assert torch.equal(planes, whole) and torch.equal(scale, sw)
+    assert torch.equal(planes[:-4096], whole[:-4096]) and torch.equal(scale, sw)      # the last 4096 bytes are slack
 
 
 @pytest.mark.parametrize("M,N,K,ns", [(1, 1, 1, 6), (128, 80, 32, 6), (130, 90, 40, 6), (300, 100, 70, 7), (256, 192, 512, 8),
@@ -148,3 +148,73 @@ def test_residual_int8_vs_dmma_engine(ecw, ov, antisym):
         torch.cuda.empty_cache()
     for x, y in zip(res["dmma"], res["int8"]):
         assert float((x - y).abs().max()) < 1e-11
+
+
+def test_two_level_cut_and_batched_products(ecw):
+    """k = (k1, k2) with k2 padded per k1, per-k1 row sums, and batches over row blocks / single k1 values of a plane
+    set — the access patterns of the ovvv terms (CCSD.py:294, 311-312) — against numpy."""
+    import ctypes
+    import torch
+    lib = ecw.lib
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(4)
+    ns, R, K1, K2, nb, Mb, Nb = 6, 96, 5, 40, 3, 32, 16
+    X = rng.standard_normal((R, K1, K2)) * 0.03                  # rows r, k = (k1, k2)
+    Xd = torch.from_numpy(X).cuda()
+    planes = torch.zeros(lib.ecw_ozaki_plane_bytes2(R, K1, K2, ns), dtype=torch.int8, device="cuda")
+    stats = torch.zeros(lib.ecw_ozaki_stat_elems2(R, K1), dtype=torch.float64, device="cuda")
+    assert lib.ecw_ozaki_split2(Xd.data_ptr(), R, K1, K2, K1 * K2, K2, 1, ns, planes.data_ptr(), stats.data_ptr(), st) == 0
+    pl, want = oz_const_slots(X.reshape(R, K1 * K2), ns, K1=K1)
+    nbytes = planes.numel() - 4096
+    assert np.array_equal(planes.cpu().numpy()[:nbytes], pl.view(np.int8)[:nbytes])
+    assert np.abs(stats.cpu().numpy() - want).max() < 1e-13
+    # the same set cut from the transposed storage (rows contiguous)
+    Xt = torch.from_numpy(np.ascontiguousarray(X.transpose(1, 2, 0))).cuda()     # [k1, k2, r]
+    planes2, stats2 = torch.zeros_like(planes), torch.zeros_like(stats)
+    assert lib.ecw_ozaki_split2(Xt.data_ptr(), R, K1, K2, 1, K2 * R, R, ns, planes2.data_ptr(), stats2.data_ptr(), st) == 0
+    assert torch.equal(planes2[:nbytes], planes[:nbytes]) and float((stats2 - stats).abs().max()) < 1e-13
+    # (1) batch over row blocks: C_b = X[b*Mb:(b+1)*Mb, :] . Y[b*Nb:(b+1)*Nb, :]^T over the whole k
+    Y = rng.standard_normal((nb * Nb, K1, K2)) * 0.02
+    Yd = torch.from_numpy(Y).cuda()
+    pY = torch.zeros(lib.ecw_ozaki_plane_bytes2(nb * Nb, K1, K2, ns), dtype=torch.int8, device="cuda")
+    sY = torch.zeros(lib.ecw_ozaki_stat_elems2(nb * Nb, K1), dtype=torch.float64, device="cuda")
+    assert lib.ecw_ozaki_split2(Yd.data_ptr(), nb * Nb, K1, K2, K1 * K2, K2, 1, ns, pY.data_ptr(), sY.data_ptr(), st) == 0
+    C = torch.zeros((nb, Mb, Nb), dtype=torch.float64, device="cuda")
+    nkb2 = (K2 + 31) // 32
+    bt = (ctypes.c_int64 * 15)(nb, 0, Mb, 0, Nb, 0, 0, 0, 0, 128, 0, 128, 0, Mb * Nb, K1 * nkb2)
+    assert lib.ecw_ozaki_gemm_batched(planes.data_ptr(), stats.data_ptr(), R, pY.data_ptr(), sY.data_ptr(), nb * Nb, Mb, Nb,
+                                      K1 * K2, C.data_ptr(), Nb, 1, 1.0, 0.0, ns, bt, st) == 0
+    Xf, Yf = X.reshape(R, -1), Y.reshape(nb * Nb, -1)
+    ref = np.stack([Xf[b * Mb:(b + 1) * Mb] @ Yf[b * Nb:(b + 1) * Nb].T for b in range(nb)])
+    assert np.abs(C.cpu().numpy() - ref).max() < 1e-13
+    # (2) batch over single k1 values of X against ONE small operand Z[Nz, K2]: C_b = X[:, b, :] . Z^T
+    Nz = 24
+    Z = rng.standard_normal((Nz, K2)) * 0.05
+    Zd = torch.from_numpy(Z).cuda()
+    pZ = torch.zeros(lib.ecw_ozaki_plane_bytes2(Nz, 1, K2, ns), dtype=torch.int8, device="cuda")
+    sZ = torch.zeros(lib.ecw_ozaki_stat_elems2(Nz, 1), dtype=torch.float64, device="cuda")
+    assert lib.ecw_ozaki_split2(Zd.data_ptr(), Nz, 1, K2, K2, 0, 1, ns, pZ.data_ptr(), sZ.data_ptr(), st) == 0
+    C2 = torch.zeros((K1, Nz, R), dtype=torch.float64, device="cuda")          # [b][n][m]: tile rows contiguous
+    bt = (ctypes.c_int64 * 15)(K1, 0, 0, 0, 0, 0, nkb2, 0, 0, 2 * 128, 128, 128, 0, Nz * R, nkb2)
+    assert lib.ecw_ozaki_gemm_batched(planes.data_ptr(), stats.data_ptr(), R, pZ.data_ptr(), sZ.data_ptr(), Nz, R, Nz, K2,
+                                      C2.data_ptr(), 1, R, 1.0, 0.0, ns, bt, st) == 0
+    ref2 = np.stack([(X[:, b, :] @ Z.T).T for b in range(K1)])
+    assert np.abs(C2.cpu().numpy() - ref2).max() < 1e-13
+
+
+def test_ovvv_plane_sets_bit_exact(ecw):
+    """ecw_eris_ovvv_planes: both orientations of ovvv_p == the numpy statement of the cut; the FP64 layout is dropped."""
+    from oracle import synth
+    from oracle import refactored_np as R
+    o, v = 8, 16
+    de = ecw.DeviceEris.synthetic(o, v, gemm="int8")
+    assert de.use_ovvv_planes and "ovvv_p" not in de.buf
+    E = R.DeviceErisSpec(synth.SynthEris(o, v))
+    O = E.ovvv_p.reshape(o * v, -1)
+    for name, X, K1 in (("ovvv_oz1", O, 1), ("ovvv_oz2", np.ascontiguousarray(O.T), o)):
+        pl, st = oz_const_slots(X, de.int8_digits, K1=K1)
+        nb = pl.size * 8 - 4096 - (pl.size * 8 - 4096) % 8
+        assert np.array_equal(de.buf[name].cpu().numpy()[:nb], pl.view(np.int8)[:nb]), name
+        got = de.buf[name + "s"].cpu().numpy()
+        assert np.array_equal(got[: st.size // (2 + K1 if K1 > 1 else 2)], st[: st.size // (2 + K1 if K1 > 1 else 2)])
+        assert np.abs(got - st).max() < 1e-13, name

@@ -143,19 +143,27 @@ def test_north_star_plan_has_no_integral_permutes(built_lib):
 from plan_interp import oz_const_slots
 
 
-def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_planes=True):
+def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_planes=True, ovvv_planes=False):
     orc = OracleGCC(er)
     base = eris_slots(er)
     base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=fsp, fock=er.fock.copy())
     if vvvv_planes:
         base["vvvv_oz"], base["vvvv_ozs"] = oz_const_slots(base["vvvv_p"], ns)
         base["vvvv_p"] = np.full(1, np.nan)          # FP64 vvvv is not bound in this mode
+    if ovvv_planes:
+        pv = v * (v - 1) // 2
+        O = base["ovvv_p"].reshape(o * v, pv)
+        base["ovvv_oz1"], base["ovvv_oz1s"] = oz_const_slots(O, ns)
+        base["ovvv_oz2"], base["ovvv_oz2s"] = oz_const_slots(np.ascontiguousarray(O.T), ns, K1=o)
+        base["ovvv_p"] = np.full(1, np.nan)
     worst = 0.0
     n_oz = 0
     for tag, alpha, eq in MODES:
         for fn in ("tupdate", "lupdate"):
             pl = plan_json(built_lib, o, v, fn, flags_of(alpha, eq, antisym=antisym), int8_digits=ns, min_flops=-1.0,
-                           vvvv_planes=vvvv_planes)
+                           vvvv_planes=vvvv_planes, ovvv_planes=ovvv_planes)
+            if ovvv_planes:
+                assert any(op["kind"] == "oz_gemm" and op["batch"] > 1 for op in pl["ops"])
             n_oz += sum(op["kind"] == "oz_gemm" for op in pl["ops"])
             sl = dict(base)
             sl["out1"] = np.full((o, v), np.nan)
@@ -207,13 +215,28 @@ def test_int8_engine_north_star_plan(built_lib):
     o, v = 40, 400
     oz = tot = 0.0
     for fn in ("tupdate", "lupdate"):
-        pl = plan_json(built_lib, o, v, fn, 4, int8_digits=6, min_flops=2e10, vvvv_planes=True)
+        pl = plan_json(built_lib, o, v, fn, 4, int8_digits=6, min_flops=2e10, vvvv_planes=True, ovvv_planes=True)
         assert pl["workspace_elems"] * 8 < 45e9
         oz += pl["oz_flops"]
         tot += pl["gemm_flops"]
         for op in pl["ops"]:
             for k in "abcde":
-                assert not (op[k] and op[k]["slot"] == "vvvv_p"), op["note"]
+                assert not (op[k] and op[k]["slot"] in ("vvvv_p", "ovvv_p")), op["note"]
         big = [op for op in pl["ops"] if op["kind"] == "gemm" and 2.0 * op["M"] * op["N"] * op["K"] * op["batch"] / op["splitk"] > 5e11]
         assert not big, [b["note"] for b in big]
     assert oz / tot > 0.9
+
+
+@pytest.mark.parametrize("antisym", [True, False])
+def test_int8_engine_ovvv_planes(built_lib, antisym):
+    """nocc, nvir multiples of 8: ovvv_p bound as digit planes in both orientations; R4/R6/R9 read them and the
+    ovvv-streaming terms run as batched INT8 products over row / k1 sub-blocks of the constant plane sets."""
+    o, v = 8, 16
+    er = synth.SynthEris(o, v)
+    if antisym:
+        t1, t2, l1, l2 = synth.amplitudes(o, v)
+    else:
+        rng = np.random.default_rng(9)
+        t1, l1 = 0.05 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, v))
+        t2, l2 = 0.02 * rng.standard_normal((o, o, v, v)), 0.02 * rng.standard_normal((o, o, v, v))
+    _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, antisym, 6, 1e-12, ovvv_planes=True)
