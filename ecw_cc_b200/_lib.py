@@ -73,6 +73,7 @@ class _Lib(object):
             "ecw_resume": (c_i, [c_p, c_p]),
             "ecw_ctx_set_gemm": (c_i, [c_p, c_i, c_d]),
             "ecw_ctx_get_gemm": (c_i, [c_p]),
+            "ecw_ctx_set_int8_splitk": (c_i, [c_p, c_l]),
             "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),
             "ecw_ctx_test_assume_ovvv_planes": (c_i, [c_p]),
             "ecw_eris_ovvv_planes": (c_i, [c_p, c_p]),

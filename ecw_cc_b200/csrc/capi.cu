@@ -347,6 +347,13 @@ int ecw_ctx_set_gemm(ecw_ctx* c, int int8_digits, double min_flops) {
 
 int ecw_ctx_get_gemm(ecw_ctx* c) { return c ? c->z.oz_ns : -1; }
 
+int ecw_ctx_set_int8_splitk(ecw_ctx* c, int64_t min_k) {
+  if (!c) return -1;
+  c->z.oz_splitk_min_k = min_k;
+  c->plans.clear();
+  return 0;
+}
+
 int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* c) {
   if (!c || c->z.oz_ns <= 0) return -1;
   c->z.vvvv_planes = true;
@@ -695,6 +702,7 @@ int ecw_op_contract(ecw_ctx* c, double alpha, const ecw_tensor* A, const char* s
     require_device();
     Plan P;
     P.oz_ns = c->z.oz_ns; P.oz_min_flops = c->z.oz_min_flops; P.nocc = c->z.nocc; P.nvir = c->z.nvir;
+    P.oz_splitk_min_k = c->z.oz_splitk_min_k;
     c->ptr[S_A0] = (double*)A->ptr; c->ptr[S_A1] = (double*)B->ptr; c->ptr[S_B0] = (double*)C->ptr;
     P.contract(alpha, from_desc(A, S_A0), sa, from_desc(B, S_A1), sb, beta, from_desc(C, S_B0), sc, "op");
     c->op_plan = std::move(P);

@@ -12,6 +12,7 @@ struct Sizes {
   // vvvv shard is bound as digit planes ("vvvv_oz"/"vvvv_ozs") instead of FP64 ("vvvv_p")
   int oz_ns = 0;
   double oz_min_flops = 2e10;
+  int64_t oz_splitk_min_k = 65536;
   bool vvvv_planes = false;
   // ovvv_p is bound as digit planes in both orientations ("ovvv_oz1/2" + statistics) instead of FP64: R4/R6/R9 skip
   // their per-call cuts and the ovvv-streaming terms with a contracted or free antisymmetric pair run on the INT8
@@ -20,7 +21,8 @@ struct Sizes {
   void apply(Plan& P) const {
     P.rank = rank; P.world = world;
     P.nocc = nocc; P.nvir = nvir;
-    P.oz_ns = oz_ns; P.oz_min_flops = oz_min_flops; P.vvvv_planes = vvvv_planes && oz_ns > 0;
+    P.oz_ns = oz_ns; P.oz_min_flops = oz_min_flops; P.oz_splitk_min_k = oz_splitk_min_k;
+    P.vvvv_planes = vvvv_planes && oz_ns > 0;
     P.ovvv_planes = ovvv_planes && oz_ns > 0;
   }
 };

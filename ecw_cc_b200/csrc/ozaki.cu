@@ -6,10 +6,10 @@
 // digits (Ozaki scheme I) and multiplying the digit planes on the INT8 tensor pipe (4.5 POP/s nominal):
 //
 //   row r of an operand X[R,K]:  s_r = 2^e_r with |X[r,:]| < s_r;  y = (X[r,k]/s_r + 1)/2 in [0,1) is
-//   written in base 256,  y = sum_{p=1..NS} u_p 256^-p,  u_p in [0,255] (last digit rounded to nearest),
-//   and stored as the int8 digit  d_p = u_p - 128.  The offsets cancel the "-1" almost exactly:
+//   written in base 256,  y ~ Y 256^-NS,  Y = min(rint(y 256^NS), 256^NS - 1) = sum_{p=1..NS} u_p 256^(NS-p),
+//   u_p in [0,255], and stored as the int8 digit  d_p = u_p - 128.  The offsets cancel the "-1" almost exactly:
 //       X[r,k] = s_r (2 D + c) + delta,   D = sum_p d_p 256^-p,  c = sum_{p=1..NS-1} 256^-p,
-//       |delta| <= s_r 256^-NS (2 s_r 256^-NS when the rounded last digit is clamped at 255).
+//       |delta| <= s_r 256^-NS (2 s_r 256^-NS in the one clamped case y = 1).
 //       (8 bits per int8 digit: NS = 6 digits carry 48 bits.)
 //   C[m,n] = sA_m sB_n sum_k (2 Da + c)(2 Db + c) = sA_m sB_n ( 4 P[m,n] + c (tA_m + tB_n) - c^2 K ),
 //       P = sum_k Da Db  ~  sum_{p+q <= NS+1} 256^-(p+q) (A_p . B_q^T)      (triangular truncation),
@@ -382,11 +382,19 @@ __global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, i
     double sm = 0.0;
     if (r < R) {
       const double* x = X + r * rs + k1 * ks1;
-      for (int64_t k = lane; k < K2; k += 32) {
+      double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int64_t k = lane;
+      for (; k + 96 < K2; k += 128) {                         // four independent loads in flight per lane
+        const double v0 = x[k], v1 = x[k + 32], v2 = x[k + 64], v3 = x[k + 96];
+        mx = fmax(fmax(mx, fabs(v0)), fmax(fabs(v1), fmax(fabs(v2), fabs(v3))));
+        sm += v0; s1 += v1; s2 += v2; s3 += v3;
+      }
+      for (; k < K2; k += 32) {
         const double v = x[k];
         mx = fmax(mx, fabs(v));
         sm += v;
       }
+      sm += s1 + s2 + s3;
 #pragma unroll
       for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
     }
@@ -403,46 +411,70 @@ __global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, i
       for (int64_t k1 = 0; k1 < K1; ++k1) stats[(2 + k1) * Rp + r] /= s;
   }
 }
-// 32 rows x 8 k-lanes per block (rows contiguous)
+// rows contiguous: 32 rows x 8 k-lanes per block, grid.y = K1 * C2 (k2 cut into C2 chunks so that operands with few
+// rows and a long contraction index still fill the machine).  Row maxima are combined with atomicMax on the bit
+// pattern (non-negative doubles order like integers; order independent), partial sums go to `part` and are added in
+// a fixed order by ozaki_rowstat_finish.
 __global__ void ozaki_rowstat_rcontig(const double* __restrict__ X, int64_t R, int64_t K1, int64_t K2, int64_t ks1,
-                                      int64_t ks2, int64_t Rp_chunk, int64_t Rp, double* __restrict__ stats) {
-  __shared__ double red[8][33];
+                                      int64_t ks2, int64_t C2, int64_t Rp_chunk, int64_t Rp, double* __restrict__ stats,
+                                      double* __restrict__ part) {
+  __shared__ double red[8][33], reds[8][33];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * 32 + lane;
-  double mx = 0.0, tot = 0.0;
-  for (int64_t k1 = 0; k1 < K1; ++k1) {
-    double sm = 0.0;
-    if (r < R)
-      for (int64_t k = wy; k < K2; k += 8) {
-        const double v = X[r + k1 * ks1 + k * ks2];
-        mx = fmax(mx, fabs(v));
-        sm += v;
-      }
-    red[wy][lane] = sm;
-    __syncthreads();
-    if (wy == 0) {
-#pragma unroll
-      for (int i = 1; i < 8; ++i) sm += red[i][lane];
-      tot += sm;
-      if (K1 > 1 && r < Rp_chunk) stats[(2 + k1) * Rp + r] = sm;
+  const int64_t k1 = blockIdx.y / C2, c = blockIdx.y - k1 * C2;
+  const int64_t len = (K2 + C2 - 1) / C2, kbeg = c * len, kend = min(K2, kbeg + len);
+  double mx = 0.0, sm = 0.0;
+  if (r < R) {
+    const double* x = X + r + k1 * ks1;
+    double s1 = 0.0;
+    int64_t k = kbeg + wy;
+    for (; k + 8 < kend; k += 16) {
+      const double v0 = x[k * ks2], v1 = x[(k + 8) * ks2];
+      mx = fmax(mx, fmax(fabs(v0), fabs(v1)));
+      sm += v0; s1 += v1;
     }
-    __syncthreads();
+    for (; k < kend; k += 8) {
+      const double v = x[k * ks2];
+      mx = fmax(mx, fabs(v));
+      sm += v;
+    }
+    sm += s1;
   }
   red[wy][lane] = mx;
+  reds[wy][lane] = sm;
   __syncthreads();
   if (wy == 0 && r < Rp_chunk) {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) mx = fmax(mx, red[i][lane]);
-    const double s = oz_scale_of(mx);
-    stats[r] = s;
-    stats[Rp + r] = tot / s;
-    if (K1 > 1)
-      for (int64_t k1 = 0; k1 < K1; ++k1) stats[(2 + k1) * Rp + r] /= s;
+    for (int i = 1; i < 8; ++i) {
+      mx = fmax(mx, red[i][lane]);
+      sm += reds[i][lane];
+    }
+    atomicMax(reinterpret_cast<unsigned long long*>(stats + r), (unsigned long long)__double_as_longlong(mx));
+    part[(k1 * C2 + c) * Rp + r] = sm;
   }
+}
+// stats[r] holds the row maximum (bit pattern); part[(k1*C2 + c)*Rp + r] the partial sums
+__global__ void ozaki_rowstat_finish(int64_t K1, int64_t C2, int64_t Rp_chunk, int64_t Rp, double* __restrict__ stats,
+                                     const double* __restrict__ part) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rp_chunk) return;
+  const double s = oz_scale_of(stats[r]);
+  double tot = 0.0;
+  for (int64_t k1 = 0; k1 < K1; ++k1) {
+    double sm = 0.0;
+    for (int64_t c = 0; c < C2; ++c) sm += part[(k1 * C2 + c) * Rp + r];
+    tot += sm;
+    if (K1 > 1) stats[(2 + k1) * Rp + r] = sm / s;
+  }
+  stats[r] = s;
+  stats[Rp + r] = tot / s;
 }
 
 // cut X into NS digit planes (layout in the header comment).  Block = 128 rows x one k-block (32 k2 of one k1),
 // thread t: row t%128, 16-byte k-chunk t/128.  k-block index = k1 * ceil(K2/32) + k2/32: k2 is padded per k1.
+// Digits: Y = min(rint(y 2^(8 NS)), 2^(8 NS) - 1) as an integer; digit p is byte NS-1-p of Y, stored with the top
+// bit flipped (u - 128 as int8).  One FP64 fma, one multiply and one conversion per element; the rest is byte
+// permutes, so the kernel runs at memory speed.  Padding carries 0x80 bytes in Y so that it is stored as d = 0.
 template <int NS>
 __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restrict__ X, int64_t R, int64_t K2, int64_t rs,
                                                           int64_t ks1, int64_t ks2, int64_t Rp, int64_t row0,
@@ -456,42 +488,58 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
   const int64_t nkb2 = (K2 + OZ_BK - 1) / OZ_BK;
   const int64_t k1 = kb / nkb2;
   const int64_t k0 = (kb - k1 * nkb2) * OZ_BK + j * 16;
-  double y[16];          // (x/s + 1)/2 in [0,1]; negative = padding (all digits 0)
+  constexpr unsigned long long PAD = 0x8080808080808080ull;
+  constexpr unsigned long long YMAX = NS >= 8 ? ~0ull : ((1ull << (8 * (NS & 7))) - 1ull);
+  constexpr double two = NS >= 4 ? (double)(1ull << 32) * (double)(1ull << (NS >= 4 ? 8 * NS - 32 : 0))
+                                 : (double)(1ull << (NS >= 4 ? 0 : 8 * NS));                // 2^(8 NS)
+  uint32_t lo[16], hi[16];
+  auto digits_of = [&](double x, double inv, int i) {
+    const double y = fma(x, inv, 0.5);                       // (x/s + 1)/2 in [0, 1]
+    unsigned long long Y = __double2ull_rn(y * two);         // exact scaling, one rounding; saturates at 2^64-1
+    Y = Y < YMAX ? Y : YMAX;
+    lo[i] = (uint32_t)Y;
+    hi[i] = (uint32_t)(Y >> 32);
+  };
   if (r < R) {
     const double inv = 0.5 / scale[r];     // exact: a power of two
     const double* src = X + r * rs + k1 * ks1 + k0 * ks2;
     if (ks2 == 1 && k0 + 16 <= K2 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      double2 v[8];
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(src + i);
-        y[i] = fma(v.x, inv, 0.5);
-        y[i + 1] = fma(v.y, inv, 0.5);
+      for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const double2*>(src + 2 * i);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        digits_of(v[i].x, inv, 2 * i);
+        digits_of(v[i].y, inv, 2 * i + 1);
       }
     } else {
+      double v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) y[i] = (k0 + i < K2) ? fma(src[i * ks2], inv, 0.5) : -1.0;
+      for (int i = 0; i < 16; ++i) v[i] = (k0 + i < K2) ? src[i * ks2] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (k0 + i < K2) digits_of(v[i], inv, i);
+        else { lo[i] = (uint32_t)PAD; hi[i] = (uint32_t)(PAD >> 32); }
+      }
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = -1.0;
+    for (int i = 0; i < 16; ++i) { lo[i] = (uint32_t)PAD; hi[i] = (uint32_t)(PAD >> 32); }
   }
   const int64_t slab = Rp * OZ_BK;
   const int64_t rg = row0 + r;
   int8_t* dst = planes + (kb * NS) * slab + (rg >> 3) * 256 + j * 128 + (rg & 7) * 16;
 #pragma unroll
   for (int p = 0; p < NS; ++p) {
-    uint32_t w[4] = {0, 0, 0, 0};
+    constexpr uint32_t FLIP = 0x80808080u;
+    const int b = NS - 1 - p;                                // byte of Y that holds digit p
+    const uint32_t sel = (uint32_t)((b & 3) | (((b & 3) + 4) << 4));          // byte b of two words -> low half
+    uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int d = 0;
-      if (y[i] >= 0.0) {
-        const double z = y[i] * 256.0;                               // exact
-        double u = (p == NS - 1) ? floor(z + 0.5) : floor(z);        // last digit: to nearest
-        u = fmin(u, 255.0);
-        y[i] = fmax(z - u, 0.0);                                     // exact; in [0,1] ((.,1] only after a clamp)
-        d = (int)u - 128;
-      }
-      w[i >> 2] |= ((uint32_t)d & 0xffu) << ((i & 3) * 8);
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t* s4 = (b < 4 ? lo : hi) + 4 * q;
+      const uint32_t t01 = __byte_perm(s4[0], s4[1], sel), t23 = __byte_perm(s4[2], s4[3], sel);
+      w[q] = __byte_perm(t01, t23, 0x5410) ^ FLIP;
     }
     *reinterpret_cast<uint4*>(dst + p * slab) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -542,7 +590,19 @@ cudaError_t launch_ozaki_split2(const double* X, int64_t R, int64_t K1, int64_t 
   if (ks2 == 1) {
     ozaki_rowstat_kcontig<<<(unsigned)((Rp + 7) / 8), 256, 0, st>>>(X, R, K1, K2, rs, ks1, Rp, Rp_total, sc);
   } else {
-    ozaki_rowstat_rcontig<<<(unsigned)((Rp + 31) / 32), 256, 0, st>>>(X, R, K1, K2, ks1, ks2, Rp, Rp_total, sc);
+    // partial sums: in the statistics array itself when k2 is not chunked (K1 > 1: the per-k1 slots; K1 == 1: the
+    // row-sum slot), else in the (not yet written) plane buffer — only for a plane set cut in one piece
+    const int64_t rb = (Rp + 31) / 32;
+    int64_t C2 = 1;
+    if (row0 == 0 && Rp == Rp_total)
+      while (rb * K1 * C2 < 1024 && K2 / (C2 * 2) >= 512 && C2 < 256) C2 *= 2;
+    if (K1 * C2 > 65535) return cudaErrorInvalidValue;
+    double* part = C2 > 1 ? reinterpret_cast<double*>(planes) : (K1 > 1 ? stats + 2 * Rp_total + row0 : stats + Rp_total + row0);
+    cudaError_t e = cudaMemsetAsync(sc, 0, (size_t)Rp * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    ozaki_rowstat_rcontig<<<dim3((unsigned)rb, (unsigned)(K1 * C2)), 256, 0, st>>>(X, R, K1, K2, ks1, ks2, C2, Rp, Rp_total, sc,
+                                                                                  part);
+    ozaki_rowstat_finish<<<(unsigned)((Rp + 255) / 256), 256, 0, st>>>(K1, C2, Rp, Rp_total, sc, part);
   }
   const int64_t nkb = ozaki_kblocks(K1, K2);
   if (nkb > 65535) return cudaErrorInvalidValue;

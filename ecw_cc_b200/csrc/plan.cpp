@@ -3,6 +3,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <sstream>
@@ -382,7 +383,8 @@ void Plan::ewise(int sub, const Tensor& a, const Tensor& b, const Tensor& c, dou
 
 // ---------------------------------------------------------------- contraction engine
 static double oz_time(int ns, int sm_count, int64_t M, int64_t N, int64_t K, int64_t crs, int64_t ccs, double beta,
-                      bool* swap_out);
+                      bool* swap_out, int64_t splits = 1);
+static int64_t oz_pick_splits(int ns, int sm_count, int64_t M, int64_t N, int64_t K, int64_t min_k);
 
 namespace {
 
@@ -588,14 +590,16 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
     const bool const_planes = const_a || const_b;
     const double fl = 2.0 * (double)Md * (double)Nd * (double)Kd;
     bool oz = oz_ns > 0 && ch.bcls == 0 && Kd >= 1 && (Kd + 31) / 32 <= 65535;
+    const int64_t S = (oz && !const_planes) ? oz_pick_splits(oz_ns, sm_count, Md, Nd, Kd, oz_splitk_min_k) : 1;
     if (oz && oz_min_flops >= 0.0) {
       // INT8 route (model in oz_time) + cutting the operands (8 B read + ns B written and re-read) against the
       // DMMA route at 30 TFLOP/s: skinny, few-tile or short-K products stay on the DMMA kernels
       MatView vcm = mat_view(C, sc, ch.om, ch.on);
       const double cut = (8.0 + 2.0 * oz_ns) * ((const_a ? 0.0 : (double)Md) + (const_b ? 0.0 : (double)Nd)) * (double)Kd / 5e12;
-      const double t_oz = oz_time(oz_ns, sm_count, Md, Nd, Kd, vcm.any ? vcm.sr : Nd, vcm.any ? vcm.scol : 1, beta, nullptr) +
+      const double t_oz = oz_time(oz_ns, sm_count, Md, Nd, Kd, vcm.any ? vcm.sr : Nd, vcm.any ? vcm.scol : 1, beta, nullptr, S) +
                           cut + 2e-5;
-      oz = fl >= oz_min_flops && t_oz < 0.8 * fl / 3.0e13;
+      // the DMMA kernels reach ~30 TFLOP/s on large plain GEMMs, ~18 on split-K / few-tile shapes
+      oz = fl >= oz_min_flops && t_oz < 0.8 * fl / (S > 1 ? 1.8e13 : 3.0e13);
     }
     if (const_planes && !(oz_ns > 0 && ch.bcls == 0 && ch.a_dir && ch.b_dir))
       throw PlanError("contract: an operand is bound as digit planes but the contraction is not a plain GEMM: " + tag);
@@ -620,7 +624,36 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
       }
       MatView vc = mat_view(C, sc, ch.om, ch.on);
       const std::string nt = std::string(note) + " [" + tag + "]";
-      if (vc.any) {
+      if (S > 1) {
+        // split-K: S products over the chunks of a two-level index, partial results summed in a fixed order
+        OzSet a = oz_cut(tA, Md, ars, S, (Kd / S) * aks, Kd / S, aks, nt);
+        OzSet b = oz_cut(tB, Nd, brs, S, (Kd / S) * bks, Kd / S, bks, nt);
+        Tensor part = tmp({S, Md, Nd});
+        OzSel sel;
+        sel.k1b = 1; sel.nk1 = 1;
+        oz_mm(alpha, a, sel, b, sel, Md, Nd, S, 0.0, part, Nd, 1, Md * Nd, nt + " [split-K]");
+        oz_release(b);
+        oz_release(a);
+        Op r;
+        r.kind = OP_REDUCE;
+        r.a = part;
+        r.i0 = S;
+        r.M = Md; r.N = Nd;
+        r.alpha = 1.0;
+        r.note = nt;
+        if (vc.any) {
+          r.c = C; r.beta = beta; r.i1 = Md == 1 ? 0 : vc.sr; r.i2 = Nd == 1 ? 0 : vc.scol;
+          ops.push_back(r);
+        } else {
+          std::string lay = ch.om + ch.on;
+          Tensor tC = tmpv(dimvec(lay));
+          r.c = tC; r.beta = 0.0; r.i1 = Nd; r.i2 = 1;
+          ops.push_back(r);
+          permute(1.0, tC, lay.c_str(), beta, C, sc, "engine:C");
+          release(tC);
+        }
+        release(part);
+      } else if (vc.any) {
         emit_oz(alpha, tA, ars, aks, tB, brs, bks, Md, Nd, Kd, beta, C, Md == 1 ? 0 : vc.sr, Nd == 1 ? 0 : vc.scol, nt);
       } else {
         std::string lay = ch.om + ch.on;
@@ -751,18 +784,37 @@ static int oz_tile_n(int ns) { return ns <= 5 ? 96 : (ns == 6 ? 80 : 64); }
 // count), derated when fewer tiles than SMs; epilogue: the C tile is written (and read when beta != 0) by one thread
 // per tile row — coalesced when the tile rows are contiguous in C, 16-byte pieces otherwise.
 static double oz_time(int ns, int sm_count, int64_t M, int64_t N, int64_t K, int64_t crs, int64_t ccs, double beta,
-                      bool* swap_out) {
+                      bool* swap_out, int64_t splits) {
   auto pad = [](int64_t x, int64_t g) { return (x + g - 1) / g * g; };
   const int TN = oz_tile_n(ns);
   const double rate = 1.0e14 * 28.0 / (0.5 * ns * (ns + 1));
   double best = 1e300;
   for (int sw = 0; sw < 2; ++sw) {
     const int64_t m = sw ? N : M, n = sw ? M : N, rs = sw ? ccs : crs;
-    const double tiles = (double)(pad(m, 128) / 128) * (double)(pad(n, TN) / TN);
-    const double eff = std::min(1.0, tiles / (double)sm_count);
+    const double tiles = (double)(pad(m, 128) / 128) * (double)(pad(n, TN) / TN) * (double)splits;
+    const double waves = std::ceil(tiles / (double)sm_count);
+    const double eff = tiles / (waves * (double)sm_count);
     const double main = 2.0 * (double)K * (double)pad(m, 128) * (double)pad(n, TN) / (rate * eff);
     const double epi = 8.0 * (double)M * (double)N * (beta != 0.0 ? 2.0 : 1.0) / (rs == 1 ? 3.0e12 : 0.5e12);
     if (main + epi < best) { best = main + epi; if (swap_out) *swap_out = sw != 0; }
+  }
+  return best;
+}
+
+// Few output tiles and a long contraction index: cut K into S equal chunks (a two-level index, one product per
+// chunk, partial results summed by a reduce op).  S = the divisor of K/32 up to 64 that fills the SMs best.
+static int64_t oz_pick_splits(int ns, int sm_count, int64_t M, int64_t N, int64_t K, int64_t min_k) {
+  auto pad = [](int64_t x, int64_t g) { return (x + g - 1) / g * g; };
+  const int TN = oz_tile_n(ns);
+  const int64_t tiles = std::min((pad(M, 128) / 128) * (pad(N, TN) / TN), (pad(N, 128) / 128) * (pad(M, TN) / TN));
+  if (min_k <= 0 || K < min_k || K % 32 != 0 || tiles * 2 > sm_count) return 1;
+  int64_t best = 1;
+  double best_eff = (double)tiles / (double)sm_count;
+  for (int64_t S = 2; S <= 64; ++S) {
+    if ((K / 32) % S != 0) continue;
+    const double items = (double)(tiles * S);
+    const double eff = items / (std::ceil(items / (double)sm_count) * (double)sm_count);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = S; }
   }
   return best;
 }

@@ -127,6 +127,7 @@ class Plan {
   // oz_ns > 0 and 2MNK >= oz_min_flops; oz_ns = number of 7-bit digits (7: FP64-level accuracy).
   int oz_ns = 0;
   double oz_min_flops = 0.0;
+  int64_t oz_splitk_min_k = 65536;   // INT8 products with few output tiles and K >= this are cut into K chunks
   bool vvvv_planes = false;    // vvvv_p is bound as digit planes (S_VVVV_OZ/S_VVVV_OZS), not as FP64
   bool ovvv_planes = false;    // ovvv_p is bound as digit planes in both orientations (S_OVVV_OZ1/2)
   int64_t nocc = 0, nvir = 0;  // needed to recognise the constant plane sets

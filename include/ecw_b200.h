@@ -61,6 +61,9 @@ int ecw_resume(ecw_ctx* ctx, void* stream);
  * (CCSD.py:25).  A context starts with int8_digits = 0. */
 int ecw_ctx_set_gemm(ecw_ctx* ctx, int int8_digits, double min_flops);
 int ecw_ctx_get_gemm(ecw_ctx* ctx);
+/* INT8 products with fewer output tiles than SMs and a contraction length >= min_k (a multiple of 32) are cut into
+ * equal K chunks, one product each, summed in a fixed order (default 65536; <= 0: never). */
+int ecw_ctx_set_int8_splitk(ecw_ctx* ctx, int64_t min_k);
 int ecw_pending_collective(ecw_ctx* ctx, int64_t* desc6);
 
 /* ---- integral container (consumed type `Eris.geris`, Eris.py:132-154) ---- */

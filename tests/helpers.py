@@ -14,7 +14,7 @@ def load_golden(name):
 
 
 def plan_json(lib, o, v, func, flags, rank=0, world=1, int8_digits=0, min_flops=-1.0, vvvv_planes=False,
-              ovvv_planes=False):
+              ovvv_planes=False, splitk_min_k=None):
     """Plan of one call.  int8_digits > 0: INT8 tensor-core engine for every unbatched GEMM with
     2MNK >= min_flops; vvvv_planes: the packed vvvv is bound as digit planes (needs a device for the
     real entry point, so the flag is flipped through the test hook ecw_ctx_test_assume_vvvv_planes)."""
@@ -24,6 +24,8 @@ def plan_json(lib, o, v, func, flags, rank=0, world=1, int8_digits=0, min_flops=
         assert lib.ecw_ctx_set_shard(h, rank, world) == 0
     if int8_digits:
         assert lib.ecw_ctx_set_gemm(h, int8_digits, float(min_flops)) == 0
+        if splitk_min_k is not None:
+            assert lib.ecw_ctx_set_int8_splitk(h, splitk_min_k) == 0
         if vvvv_planes:
             assert lib.ecw_ctx_test_assume_vvvv_planes(h) == 0
         if ovvv_planes:

@@ -34,16 +34,16 @@ def oz_cprime(ns):
 
 
 def oz_digits(X, ns):
-    """X[r,k] = s_r (2 sum_p d_p 256^-(p+1) + c) + delta: int8 digits [ns][R][K] and the scales."""
+    """X[r,k] = s_r (2 sum_p d_p 256^-(p+1) + c) + delta: int8 digits [ns][R][K] and the scales.
+    Y = min(rint(y 256^ns), 256^ns - 1) with y = (x/s + 1)/2; digit p is byte ns-1-p of Y, minus 128."""
     s = oz_scale(X)
     y = X * (0.5 / s)[:, None] + 0.5                 # one rounding, as the device fma
-    out = []
-    for p in range(ns):
-        z = y * 256.0
-        u = np.floor(z + 0.5) if p == ns - 1 else np.floor(z)
-        u = np.minimum(u, 255.0)
-        y = np.maximum(z - u, 0.0)
-        out.append((u - 128.0).astype(np.int8))
+    z = np.rint(y * 2.0 ** (8 * ns))                 # exact scaling; ties to even like cvt.rn
+    top = 2.0 ** (8 * ns)
+    Y = np.where(z >= top, 0.0, z).astype(np.uint64)
+    Y = np.where(z >= top, np.uint64(2 ** (8 * ns) - 1), Y)
+    out = [(((Y >> np.uint64(8 * (ns - 1 - p))) & np.uint64(255)).astype(np.int64) - 128).astype(np.int8)
+           for p in range(ns)]
     return np.stack(out), s
 
 

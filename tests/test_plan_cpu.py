@@ -143,7 +143,8 @@ def test_north_star_plan_has_no_integral_permutes(built_lib):
 from plan_interp import oz_const_slots
 
 
-def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_planes=True, ovvv_planes=False):
+def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_planes=True, ovvv_planes=False,
+               splitk_min_k=None):
     orc = OracleGCC(er)
     base = eris_slots(er)
     base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=fsp, fock=er.fock.copy())
@@ -161,7 +162,9 @@ def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_
     for tag, alpha, eq in MODES:
         for fn in ("tupdate", "lupdate"):
             pl = plan_json(built_lib, o, v, fn, flags_of(alpha, eq, antisym=antisym), int8_digits=ns, min_flops=-1.0,
-                           vvvv_planes=vvvv_planes, ovvv_planes=ovvv_planes)
+                           vvvv_planes=vvvv_planes, ovvv_planes=ovvv_planes, splitk_min_k=splitk_min_k)
+            if splitk_min_k:
+                assert any(op["kind"] == "oz_gemm" and "split-K" in op["note"] for op in pl["ops"]), fn
             if ovvv_planes:
                 assert any(op["kind"] == "oz_gemm" and op["batch"] > 1 for op in pl["ops"])
             n_oz += sum(op["kind"] == "oz_gemm" for op in pl["ops"])
@@ -240,3 +243,12 @@ def test_int8_engine_ovvv_planes(built_lib, antisym):
         t1, l1 = 0.05 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, v))
         t2, l2 = 0.02 * rng.standard_normal((o, o, v, v)), 0.02 * rng.standard_normal((o, o, v, v))
     _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, antisym, 6, 1e-12, ovvv_planes=True)
+
+
+def test_int8_engine_split_k(built_lib):
+    """Few-tile products with a long contraction index are cut into K chunks (two-level index, per-chunk row sums,
+    one product per chunk, fixed-order sum)."""
+    o, v = 8, 16
+    er = synth.SynthEris(o, v)
+    t1, t2, l1, l2 = synth.amplitudes(o, v)
+    _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, True, 6, 1e-12, splitk_min_k=64)
