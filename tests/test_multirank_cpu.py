@@ -42,6 +42,11 @@ def _worker(rank, world, port, o, v, antisym, q, int8=0):
         if int8:      # INT8 engine: the rank's shard is bound as digit planes, every unbatched GEMM on that route
             base["vvvv_oz"], base["vvvv_ozs"] = oz_const_slots(base["vvvv_p"], int8)
             base["vvvv_p"] = np.full(1, np.nan)
+            if o % 8 == 0 and v % 8 == 0:          # ovvv_p as digit planes too (R4/R6/R9 read row ranges of them)
+                O = base["ovvv_p"].reshape(o * v, pv)
+                base["ovvv_oz1"], base["ovvv_oz1s"] = oz_const_slots(O, int8)
+                base["ovvv_oz2"], base["ovvv_oz2s"] = oz_const_slots(np.ascontiguousarray(O.T), int8, K1=o)
+                base["ovvv_p"] = np.full(1, np.nan)
 
         def allgather(send, recv):
             out = torch.from_numpy(recv)
@@ -53,7 +58,7 @@ def _worker(rank, world, port, o, v, antisym, q, int8=0):
         for alpha, eq in ((None, False), (1e-3, True)):
             for fn in ("tupdate", "lupdate"):
                 pl = plan_json(lib, o, v, fn, flags_of(alpha, eq, antisym), rank=rank, world=world, int8_digits=int8,
-                               vvvv_planes=bool(int8))
+                               vvvv_planes=bool(int8), ovvv_planes=bool(int8) and o % 8 == 0 and v % 8 == 0)
                 ncoll += sum(1 for op in pl["ops"] if op["kind"] == "allgather")
                 sl = dict(base)
                 sl["out1"] = np.full((o, v), np.nan)
@@ -68,7 +73,7 @@ def _worker(rank, world, port, o, v, antisym, q, int8=0):
 
 
 @pytest.mark.parametrize("antisym", [True, False])
-@pytest.mark.parametrize("world,ov,int8", [(2, (4, 6), 0), (2, (5, 7), 0), (3, (5, 7), 0), (2, (5, 7), 7)])
+@pytest.mark.parametrize("world,ov,int8", [(2, (4, 6), 0), (2, (5, 7), 0), (3, (5, 7), 0), (2, (5, 7), 7), (2, (8, 16), 6)])
 def test_sharded_plans_match_oracle(built_lib, world, ov, antisym, int8):
     o, v = ov
     ctx = mp.get_context("spawn")

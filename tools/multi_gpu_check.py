@@ -16,7 +16,7 @@ rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 worst = 0.0
-for (o, v) in [(5, 9), (8, 20), (10, 33)]:
+for (o, v) in [(5, 9), (8, 20), (10, 33), (8, 16), (16, 24)]:     # the last two: ovvv digit planes (nocc, nvir % 8 == 0)
     er = synth.SynthEris(o, v)
     fsp = synth.fsp(o, v)
     orc = OracleGCC(er)
