@@ -930,7 +930,9 @@ void Plan::emit_oz(double alpha, const Tensor& A, int64_t ars, int64_t aks, cons
     Side s;
     if (vvvv_planes && X.slot == S_VVVV_P) {
       // the constant row shard of the packed vvvv: [R, K] with K contiguous, cut once at upload time
-      if (X.off != 0 || ks != 1 || rs != K || K != pv) throw PlanError("vvvv_p digit planes: unexpected operand view in " + note);
+      // (a one-row shard has no meaningful row stride, and the engine may read it as a column)
+      if (X.off != 0 || K != pv || (R > 1 && (ks != 1 || rs != K)))
+        throw PlanError("vvvv_p digit planes: unexpected operand view in " + note);
       s.set = oz_const_vvvv(R);
       return s;
     }

@@ -29,7 +29,7 @@ def test_dgemm_all_layouts(ecw, cfg, ta, tb):
     import torch
     rng = np.random.default_rng(10 * ta + tb + 100)
     for (M, N, K) in [(1, 1, 1), (7, 5, 3), (33, 17, 129), (130, 131, 67), (256, 128, 64), (45, 300, 1000),
-                      (300, 258, 520), (112, 128, 48)]:
+                      (300, 258, 520), (112, 128, 48), (2100, 517, 40)]:
         A = rng.standard_normal((K, M) if ta else (M, K))
         B = rng.standard_normal((N, K) if tb else (K, N))
         C0 = rng.standard_normal((M, N))
@@ -55,6 +55,33 @@ def test_dgemm_strided_views(ecw):
                            dC.data_ptr() + 8, N + 7, -1, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     assert np.abs(dC.cpu().numpy() - ref).max() < 1e-11
+
+
+@pytest.mark.parametrize("engine_env", ["dmma", "int8"])
+def test_occupied_index_contractions_at_size(ecw, engine_env, monkeypatch):
+    """The K = nocc contractions of the residual (CCSD.py:290-291, 307, 407-410, 593-597) at a size where the engine
+    batches / permutes them as it does at the benchmark shape — against numpy einsum with the reference's index
+    strings."""
+    from ecw_cc_b200.devops import DevOps
+    monkeypatch.setenv("ECW_GEMM", engine_env)
+    o, v = 24, 72
+    ops = DevOps(ecw.DeviceEris.synthetic(4, 6))
+    rng = np.random.default_rng(8)
+    t1 = rng.standard_normal((o, v))
+    cases = [("ma,jbmi->iajb", (o, v), (o, v, o, o)), ("nb,mnje->mejb", (o, v), (o, o, o, v)),
+             ("nb,mnej->mejb", (o, v), (o, o, v, o)), ("lc,ljkb->kcjb", (o, v), (o, o, o, v)),
+             ("ma,ijmb->ijab", (o, v), (o, o, o, v)), ("mj,imab->ijab", (o, o), (o, o, v, v)),
+             ("ka,ijkb->ijab", (o, v), (o, o, o, v)), ("qk,kprs->pqrs", (o, o), (o, o, v, v)),
+             ("pk,kqrs->pqrs", (o, o), (o, o, v, v)), ("mnie,je->mnij", (o, o, o, v), (o, v))]
+    for spec, sha, shb in cases:
+        A, B = rng.standard_normal(sha), rng.standard_normal(shb)
+        ref = np.einsum(spec, A, B)
+        C0 = rng.standard_normal(ref.shape)
+        out = ops.to_dev(C0)
+        ops.contract(spec, ops.to_dev(A), ops.to_dev(B), alpha=-0.5, out=out, beta=1.0)
+        assert np.abs(out.cpu().numpy() - (C0 - 0.5 * ref)).max() < 1e-11, spec
+        got = ops.contract(spec, ops.to_dev(A), ops.to_dev(B))
+        assert np.abs(got.cpu().numpy() - ref).max() < 1e-11, spec
 
 
 def test_synthetic_tensors_bit_exact(ecw):

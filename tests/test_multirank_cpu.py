@@ -73,7 +73,7 @@ def _worker(rank, world, port, o, v, antisym, q, int8=0):
 
 
 @pytest.mark.parametrize("antisym", [True, False])
-@pytest.mark.parametrize("world,ov,int8", [(2, (4, 6), 0), (2, (5, 7), 0), (3, (5, 7), 0), (2, (5, 7), 7), (2, (8, 16), 6)])
+@pytest.mark.parametrize("world,ov,int8", [(2, (4, 6), 0), (2, (5, 7), 0), (3, (5, 7), 0), (2, (5, 7), 7), (2, (8, 16), 6), (8, (5, 9), 6)])
 def test_sharded_plans_match_oracle(built_lib, world, ov, antisym, int8):
     o, v = ov
     ctx = mp.get_context("spawn")
