@@ -6,6 +6,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace ecw {
 
@@ -32,24 +33,52 @@ struct PermK {
 };
 
 // Same contiguous axis on both sides (or no unit stride at all): plain strided copy,
-// dims ordered so the last one is the fast axis.
+// dims ordered so the last one is the fast axis.  IT = index type of the element counter (32-bit divisions when the
+// tensor has fewer than 2^31 elements), VEC = 2: the fast axis has unit stride on both sides and even extent, so a
+// thread moves 16 bytes per access.  Four independent elements per thread and iteration keep enough loads in flight
+// to reach HBM speed (the one-element version sat at ~2 TB/s, latency bound).
+template <typename IT, int VEC>
 __global__ void __launch_bounds__(EW_THREADS) permute_linear_kernel(PermK p) {
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < p.total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t rem = idx, oi = 0, oo = 0;
+  using V = typename std::conditional<VEC == 2, double2, double>::type;
+  const IT total = (IT)(p.total / VEC), stride = (IT)gridDim.x * (IT)blockDim.x;
+  for (IT base = (IT)blockIdx.x * (IT)blockDim.x + (IT)threadIdx.x; base < total; base += 4 * stride) {
+    int64_t oi[4], oo[4];
+    bool ok[4];
+    V vi[4], vo[4];
 #pragma unroll
-    for (int d = KMAXD - 1; d >= 0; --d) {
-      if (d < p.nd) {
-        int64_t q = rem / p.dim[d];
-        int64_t c = rem - q * p.dim[d];
-        rem = q;
-        oi += c * p.sin[d];
-        oo += c * p.sout[d];
+    for (int u = 0; u < 4; ++u) {
+      IT rem = base + (IT)u * stride;
+      ok[u] = rem < total;
+      int64_t a = 0, b = 0;
+#pragma unroll
+      for (int d = KMAXD - 1; d >= 0; --d) {
+        if (d < p.nd) {
+          const IT dd = (IT)p.dim[d];
+          const IT q = rem / dd, c = rem - q * dd;
+          rem = q;
+          a += (int64_t)c * p.sin[d];
+          b += (int64_t)c * p.sout[d];
+        }
+      }
+      oi[u] = a; oo[u] = b;
+      if (ok[u]) {
+        vi[u] = *reinterpret_cast<const V*>(p.in + a);
+        if (p.beta != 0.0) vo[u] = *reinterpret_cast<const V*>(p.out + b);
       }
     }
-    double v = p.alpha * p.in[oi];
-    if (p.beta != 0.0) v += p.beta * p.out[oo];
-    p.out[oo] = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      if constexpr (VEC == 2) {
+        double2 r = make_double2(p.alpha * vi[u].x, p.alpha * vi[u].y);
+        if (p.beta != 0.0) { r.x += p.beta * vo[u].x; r.y += p.beta * vo[u].y; }
+        *reinterpret_cast<double2*>(p.out + oo[u]) = r;
+      } else {
+        double r = p.alpha * vi[u];
+        if (p.beta != 0.0) r += p.beta * vo[u];
+        p.out[oo[u]] = r;
+      }
+    }
   }
 }
 
@@ -135,17 +164,29 @@ reduce_kernel(const double* __restrict__ part, int64_t nz, int64_t M, int64_t N,
   }
 }
 
+// two consecutive b per thread (v even) or one; the (i,j) pair comes from blockIdx.y so that only one 32-bit
+// division per thread remains
+template <int VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 tau_kernel(const double* __restrict__ t2, const double* __restrict__ t1, double* __restrict__ out, int o, int v,
            double c1, double c2) {
-  const int64_t vv = (int64_t)v * v, total = (int64_t)o * o * vv;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t ij = idx / vv, ab = idx - ij * vv;
-    int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
-    int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
-    double x = c1 * (t1[i * v + a] * t1[j * v + b]) - c2 * (t1[i * v + b] * t1[j * v + a]);
-    out[idx] = t2[idx] + x;
+  const uint32_t vv = (uint32_t)v * (uint32_t)v;
+  const int i = blockIdx.y / o, j = blockIdx.y - i * o;
+  const double* __restrict__ ti = t1 + (int64_t)i * v;
+  const double* __restrict__ tj = t1 + (int64_t)j * v;
+  const int64_t row = (int64_t)blockIdx.y * vv;
+  for (uint32_t ab = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; ab < vv; ab += gridDim.x * blockDim.x * VEC) {
+    const uint32_t a = ab / (uint32_t)v, b = ab - a * (uint32_t)v;
+    if constexpr (VEC == 2) {
+      const double2 t = *reinterpret_cast<const double2*>(t2 + row + ab);
+      const double ia = ti[a], ja = tj[a];
+      double2 r;
+      r.x = t.x + (c1 * (ia * tj[b]) - c2 * (ti[b] * ja));
+      r.y = t.y + (c1 * (ia * tj[b + 1]) - c2 * (ti[b + 1] * ja));
+      *reinterpret_cast<double2*>(out + row + ab) = r;
+    } else {
+      out[row + ab] = t2[row + ab] + (c1 * (ti[a] * tj[b]) - c2 * (ti[b] * tj[a]));
+    }
   }
 }
 
@@ -183,60 +224,81 @@ __device__ __forceinline__ void pair_decode(int64_t k, int64_t& lo, int64_t& hi)
   lo = k - h * (h - 1) / 2;
 }
 
+// blockIdx.y enumerates the rows (first pair, decoded once per block), threads the columns with 32-bit arithmetic
 __global__ void __launch_bounds__(EW_THREADS) pack_kernel(PackArgs p, int64_t rows, int64_t cols) {
-  const int64_t total = rows * cols;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = idx / cols, c = idx - r * cols;
-    int64_t i0, i1, i2, i3;
+  const uint32_t ncols = (uint32_t)cols, d3 = (uint32_t)p.d3;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    int64_t i0, i1;
     if (p.flags & 1) pair_decode(r, i0, i1);
     else { i0 = r / p.d1; i1 = r - i0 * p.d1; }
-    if (p.flags & 2) pair_decode(c, i2, i3);
-    else { i2 = c / p.d3; i3 = c - i2 * p.d3; }
-    const double* s = p.src + i0 * p.s0 + i1 * p.s1;
-    double val = s[i2 * p.s2 + i3 * p.s3];
-    if (p.flags & 4) val -= s[i3 * p.s2 + i2 * p.s3];
-    if (p.flags & 8) {
-      const double* s2 = p.src + i1 * p.s0 + i0 * p.s1;
-      double w = s2[i2 * p.s2 + i3 * p.s3];
-      if (p.flags & 4) w -= s2[i3 * p.s2 + i2 * p.s3];
-      val -= w;
+    const double* __restrict__ s = p.src + i0 * p.s0 + i1 * p.s1;
+    const double* __restrict__ s2 = p.src + i1 * p.s0 + i0 * p.s1;
+    double* drow = p.dst + r * p.ld;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) {
+      int64_t i2, i3;
+      if (p.flags & 2) pair_decode((int64_t)c, i2, i3);
+      else { const uint32_t q = c / d3; i2 = q; i3 = c - q * d3; }
+      double val = s[i2 * p.s2 + i3 * p.s3];
+      if (p.flags & 4) val -= s[i3 * p.s2 + i2 * p.s3];
+      if (p.flags & 8) {
+        double w = s2[i2 * p.s2 + i3 * p.s3];
+        if (p.flags & 4) w -= s2[i3 * p.s2 + i2 * p.s3];
+        val -= w;
+      }
+      double out = p.alpha * val;
+      if (p.beta != 0.0) out += p.beta * drow[c];
+      drow[c] = out;
     }
-    double* d = p.dst + r * p.ld + c;
-    double out = p.alpha * val;
-    if (p.beta != 0.0) out += p.beta * *d;
-    *d = out;
   }
 }
 
-__global__ void __launch_bounds__(EW_THREADS) unpack_kernel(PackArgs p, int64_t total) {
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t rem = idx;
-    int64_t i3 = rem % p.d3; rem /= p.d3;
-    int64_t i2 = rem % p.d2; rem /= p.d2;
-    int64_t i1 = rem % p.d1;
-    int64_t i0 = rem / p.d1;
-    double sign = 1.0;
-    bool zero = false;
-    int64_t r, c;
-    if (p.flags & 1) {
-      if (i0 == i1) zero = true;
-      int64_t lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
-      if (i0 > i1) sign = -sign;
-      r = hi * (hi - 1) / 2 + lo;
-    } else r = i0 * p.d1 + i1;
+// blockIdx.y enumerates the first pair (i0,i1), threads the second pair (i2,i3) with 32-bit arithmetic, two
+// consecutive i3 per thread and 16-byte accesses to the destination when its last axis is contiguous (VEC = 2)
+template <int VEC>
+__global__ void __launch_bounds__(EW_THREADS) unpack_kernel(PackArgs p) {
+  const uint32_t d3 = (uint32_t)p.d3, n23 = (uint32_t)p.d2 * d3;
+  for (int64_t row = blockIdx.y; row < p.d0 * p.d1; row += gridDim.y) {
+  const int64_t i0 = row / p.d1, i1 = row - i0 * p.d1;
+  double sign0 = 1.0;
+  bool zero0 = false;
+  int64_t r;
+  if (p.flags & 1) {
+    zero0 = i0 == i1;
+    const int64_t lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+    if (i0 > i1) sign0 = -1.0;
+    r = hi * (hi - 1) / 2 + lo;
+  } else r = i0 * p.d1 + i1;
+  const double* __restrict__ src = p.src + r * p.ld;
+  double* dst = p.dst + i0 * p.s0 + i1 * p.s1;
+  auto value = [&](uint32_t i2, uint32_t i3) {
+    double sign = sign0;
+    bool zero = zero0;
+    int64_t c;
     if (p.flags & 2) {
-      if (i2 == i3) zero = true;
-      int64_t lo = i2 < i3 ? i2 : i3, hi = i2 < i3 ? i3 : i2;
+      zero = zero || i2 == i3;
+      const uint32_t lo = i2 < i3 ? i2 : i3, hi = i2 < i3 ? i3 : i2;
       if (i2 > i3) sign = -sign;
-      c = hi * (hi - 1) / 2 + lo;
-    } else c = i2 * p.d3 + i3;
-    double val = zero ? 0.0 : sign * p.src[r * p.ld + c];
-    double* d = p.dst + i0 * p.s0 + i1 * p.s1 + i2 * p.s2 + i3 * p.s3;
-    double out = p.alpha * val;
-    if (p.beta != 0.0) out += p.beta * *d;
-    *d = out;
+      c = (int64_t)hi * (hi - 1) / 2 + lo;
+    } else c = (int64_t)i2 * d3 + i3;
+    return zero ? 0.0 : p.alpha * (sign * src[c]);
+  };
+  for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; e < n23; e += gridDim.x * blockDim.x * VEC) {
+    const uint32_t i2 = e / d3, i3 = e - i2 * d3;
+    double* d = dst + (int64_t)i2 * p.s2 + (int64_t)i3 * p.s3;
+    if constexpr (VEC == 2) {
+      double2 out = make_double2(value(i2, i3), value(i2, i3 + 1));
+      if (p.beta != 0.0) {
+        const double2 old = *reinterpret_cast<const double2*>(d);
+        out.x += p.beta * old.x;
+        out.y += p.beta * old.y;
+      }
+      *reinterpret_cast<double2*>(d) = out;
+    } else {
+      double out = value(i2, i3);
+      if (p.beta != 0.0) out += p.beta * *d;
+      *d = out;
+    }
+  }
   }
 }
 
@@ -254,6 +316,7 @@ subdiff_kernel(const double* __restrict__ e, const double* __restrict__ v, doubl
     out[i] = subdiff(e[i], v[i], alpha);
 }
 
+// rank 4: blockIdx.y enumerates (i,j), threads (a,b) with 32-bit arithmetic; rank 2: one row of blocks
 __global__ void __launch_bounds__(EW_THREADS)
 finish_kernel(const double* r, const double* __restrict__ amp, const double* __restrict__ fock, int64_t ldf,
               double* out, int o, int v, int rank, int has_alpha, int equation, double alpha, double shift,
@@ -262,30 +325,31 @@ finish_kernel(const double* r, const double* __restrict__ amp, const double* __r
   const int n = o + v;
   for (int i = threadIdx.x; i < n; i += blockDim.x) eps[i] = fock[(int64_t)i * ldf + i];
   __syncthreads();
-  const int64_t vv = (int64_t)v * v;
-  const int64_t total = rank == 2 ? (int64_t)o * v : (int64_t)o * o * vv;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    double d;
-    if (rank == 2) {
-      int i = (int)(idx / v), a = (int)(idx - (int64_t)i * v);
-      d = shift + (eps[i] - eps[o + a]);
-    } else {
-      int64_t ij = idx / vv, ab = idx - ij * vv;
-      int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
-      int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
-      d = (eps[i] - eps[o + a]) + (eps[j] - eps[o + b]);
-      if (shift != 0.0) d += shift;
+  const uint32_t uv = (uint32_t)v;
+  const uint32_t per = rank == 2 ? (uint32_t)o * uv : uv * uv;
+  const int64_t nrow = rank == 2 ? 1 : (int64_t)o * o;
+  for (int64_t row = blockIdx.y; row < nrow; row += gridDim.y) {
+    const int i = (int)(row / o), j = (int)(row - (int64_t)i * o);
+    const int64_t base = row * (int64_t)per;
+    for (uint32_t e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < per; e0 += gridDim.x * blockDim.x) {
+      const uint32_t a = e0 / uv, b = e0 - a * uv;
+      double d;
+      if (rank == 2) d = shift + (eps[a] - eps[o + b]);            // here (a, b) = (i, a)
+      else {
+        d = (eps[i] - eps[o + a]) + (eps[j] - eps[o + b]);
+        if (shift != 0.0) d += shift;
+      }
+      const int64_t idx = base + e0;
+      double e = r[idx], res;
+      if (has_alpha) {
+        double t = amp[idx];
+        double w = (rank == 4 || sub_singles) ? subdiff(e, t, alpha) : e;   // CCSD: L1 only on doubles (Q3)
+        res = equation ? w : (w + t * d) / d;
+      } else {
+        res = equation ? e : e / d;
+      }
+      out[idx] = res;
     }
-    double e = r[idx], res;
-    if (has_alpha) {
-      double t = amp[idx];
-      double w = (rank == 4 || sub_singles) ? subdiff(e, t, alpha) : e;   // CCSD: L1 only on doubles (Q3)
-      res = equation ? w : (w + t * d) / d;
-    } else {
-      res = equation ? e : e / d;
-    }
-    out[idx] = res;
   }
 }
 
@@ -390,7 +454,17 @@ cudaError_t launch_permute(const PermArgs& a, cudaStream_t st) {
       if (d != fo) { k.dim[n] = dim[d]; k.sin[n] = si[d]; k.sout[n] = so[d]; ++n; }
     k.dim[n] = dim[fo]; k.sin[n] = si[fo]; k.sout[n] = so[fo]; ++n;
     k.nd = n;
-    permute_linear_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(k);
+    const bool small = total + 4LL * 148 * 32 * EW_THREADS < (1LL << 31);
+    auto even = [](int64_t x) { return (x & 1) == 0; };
+    bool vec = k.sin[n - 1] == 1 && k.sout[n - 1] == 1 && even(k.dim[n - 1]) &&
+               (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    for (int d = 0; d + 1 < n; ++d) vec = vec && even(k.sin[d]) && even(k.sout[d]);
+    if (vec) { k.dim[n - 1] /= 2; k.sin[n - 1] = 2; k.sout[n - 1] = 2; }
+    const unsigned grid = grid_for(total / (vec ? 2 : 1), EW_THREADS * 4);
+    if (vec && small) permute_linear_kernel<uint32_t, 2><<<grid, EW_THREADS, 0, st>>>(k);
+    else if (vec) permute_linear_kernel<int64_t, 2><<<grid, EW_THREADS, 0, st>>>(k);
+    else if (small) permute_linear_kernel<uint32_t, 1><<<grid, EW_THREADS, 0, st>>>(k);
+    else permute_linear_kernel<int64_t, 1><<<grid, EW_THREADS, 0, st>>>(k);
   } else {
     int n = 0;
     int64_t rest = 1;
@@ -431,7 +505,12 @@ cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, i
                        cudaStream_t st) {
   int64_t total = (int64_t)o * o * v * v;
   if (total <= 0) return cudaSuccess;
-  tau_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
+  if ((int64_t)o * o > 65535) return cudaErrorInvalidValue;
+  const bool vec = (v % 2 == 0) && (reinterpret_cast<uintptr_t>(t2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int64_t per = (int64_t)v * v / (vec ? 2 : 1);
+  dim3 grid((unsigned)std::min<int64_t>((per + EW_THREADS - 1) / EW_THREADS, 64), (unsigned)(o * o));
+  if (vec) tau_kernel<2><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
+  else tau_kernel<1><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
   return cudaGetLastError();
 }
 
@@ -445,17 +524,27 @@ cudaError_t launch_antisym_defect(const double* x, int o, int v, double* out, cu
 }
 
 cudaError_t launch_pack(const PackArgs& a, cudaStream_t st) {
-  int64_t rows = (a.flags & 1) ? a.d0 * (a.d0 - 1) / 2 : a.d0 * a.d1;
-  int64_t cols = (a.flags & 2) ? a.d2 * (a.d2 - 1) / 2 : a.d2 * a.d3;
+  const int64_t rows = (a.flags & 1) ? a.d0 * (a.d0 - 1) / 2 : a.d0 * a.d1;
+  const int64_t cols = (a.flags & 2) ? a.d2 * (a.d2 - 1) / 2 : a.d2 * a.d3;
   if (rows * cols <= 0) return cudaSuccess;
-  pack_kernel<<<grid_for(rows * cols, EW_THREADS * 2), EW_THREADS, 0, st>>>(a, rows, cols);
+  if (cols >= (1LL << 31)) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)std::min<int64_t>((cols + EW_THREADS - 1) / EW_THREADS, 64), (unsigned)std::min<int64_t>(rows, 65535));
+  pack_kernel<<<grid, EW_THREADS, 0, st>>>(a, rows, cols);
   return cudaGetLastError();
 }
 
 cudaError_t launch_unpack(const PackArgs& a, cudaStream_t st) {
-  int64_t total = a.d0 * a.d1 * a.d2 * a.d3;
+  const int64_t total = a.d0 * a.d1 * a.d2 * a.d3;
   if (total <= 0) return cudaSuccess;
-  unpack_kernel<<<grid_for(total, EW_THREADS * 2), EW_THREADS, 0, st>>>(a, total);
+  if (a.d2 * a.d3 >= (1LL << 31)) return cudaErrorInvalidValue;
+  auto even = [](int64_t x) { return (x & 1) == 0; };
+  const bool vec = a.s3 == 1 && even(a.d3) && even(a.s0) && even(a.s1) && even(a.s2) &&
+                   (reinterpret_cast<uintptr_t>(a.dst) & 15) == 0;
+  const int64_t per = a.d2 * a.d3 / (vec ? 2 : 1);
+  dim3 grid((unsigned)std::min<int64_t>((per + EW_THREADS - 1) / EW_THREADS, 64),
+            (unsigned)std::min<int64_t>(a.d0 * a.d1, 65535));
+  if (vec) unpack_kernel<2><<<grid, EW_THREADS, 0, st>>>(a);
+  else unpack_kernel<1><<<grid, EW_THREADS, 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -465,9 +554,12 @@ cudaError_t launch_finish(const double* r, const double* amp, const double* fock
   int64_t total = rank == 2 ? (int64_t)o * v : (int64_t)o * o * v * v;
   if (total <= 0) return cudaSuccess;
   size_t sm = sizeof(double) * (size_t)(o + v);
-  finish_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, sm, st>>>(r, amp, fock, ldf, out, o, v, rank,
-                                                                        has_alpha, equation, alpha, shift,
-                                                                        sub_singles);
+  const int64_t per = rank == 2 ? (int64_t)o * v : (int64_t)v * v, rows = rank == 2 ? 1 : (int64_t)o * o;
+  if (per >= (1LL << 31)) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)std::min<int64_t>((per + EW_THREADS - 1) / EW_THREADS, rank == 2 ? 1024 : 64),
+            (unsigned)std::min<int64_t>(rows, 65535));
+  finish_kernel<<<grid, EW_THREADS, sm, st>>>(r, amp, fock, ldf, out, o, v, rank, has_alpha, equation, alpha, shift,
+                                              sub_singles);
   return cudaGetLastError();
 }
 
