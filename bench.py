@@ -182,12 +182,13 @@ def measure_fp64_peak(torch, n=8192, reps=5):
 def ncu_traffic():
     """dram bytes read+written by the dominant launch, from the committed ncu --set full capture."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_int8_ladder_ncu_summary.json")))
-        rd, wr = d["dram__bytes_read.sum"].split(), d["dram__bytes_write.sum"].split()
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_int8_oz_tupdate_ncu.json")))
+        rec = [r for r in d["launches"] if "pp ladder" in r.get("launch", "")][0]
+        rd, wr = rec["dram__bytes_read.sum"].split(), rec["dram__bytes_write.sum"].split()
         unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         return {"bytes_per_launch": float(rd[0]) * unit[rd[1]] + float(wr[0]) * unit[wr[1]],
                 "algorithmic_bytes_per_launch": 3.86e10 + 0.5e9,
-                "source": "profiles/r1_int8_ladder_ncu_summary.json (ncu --set full, same launch)"}
+                "source": "profiles/r1_int8_oz_tupdate_ncu.json (ncu --set full, same launch, 1 GPU)"}
     except Exception:
         return None
 

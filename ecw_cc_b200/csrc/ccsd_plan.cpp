@@ -496,7 +496,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   P.release(ring);
   P.contract(1.0, l1, "ka", s.ooov, "ijkb", 0.0, y, "ijab");
   P.contract(-1.0, l2, "ijac", v1, "cb", 1.0, y, "ijab");
-  P.contract(1.0, x_vv, "ca", s.oovv, "ijcb", 1.0, y, "ijab");
+  P.contract(-1.0, s.oovv, "ijbc", x_vv, "ca", 1.0, y, "ijab");     // oovv[ijcb] = -oovv[ijbc] (Eris.py:128)
   P.axpby(-1.0, y, 1.0, r2);
   P.permute(1.0, y, "ijba", 1.0, r2, "ijab");
   if (ovvv_fast(P)) {
@@ -868,7 +868,7 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.release(ring);
   P.contract(1.0, l1, "ka", s.ooov, "ijkb", 0.0, y, "ijab");
   P.contract(1.0, l2, "ijca", v1, "cb", 1.0, y, "ijab");
-  P.contract(1.0, x_vv, "ca", s.oovv, "ijcb", 1.0, y, "ijab");
+  P.contract(-1.0, s.oovv, "ijbc", x_vv, "ca", 1.0, y, "ijab");     // oovv[ijcb] = -oovv[ijbc] (Eris.py:128)
   P.axpby(-1.0, y, 1.0, r2);
   P.permute(1.0, y, "ijba", 1.0, r2, "ijab");
   if (ovvv_fast(P)) {

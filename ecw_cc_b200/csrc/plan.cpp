@@ -511,7 +511,7 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
     if (bi || bj) cands.push_back(std::string{x, y});
   }
 
-  Choice best;
+  Choice best, best0;          // best0: best lowering without a batch index (the only form the INT8 route takes)
   for (auto& bt : cands) {
     int bcls = 0;
     if (!bt.empty()) bcls = I.find(bt[0]) != std::string::npos ? 1 : (J.find(bt[0]) != std::string::npos ? 2 : 3);
@@ -562,10 +562,29 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
           ch.sC = (bcls == 1 || bcls == 2) ? gC.str : 0;
           ch.cost = cost;
           if (cost < best.cost) best = ch;
+          if (bcls == 0 && cost < best0.cost) best0 = ch;
         }
   }
   if (best.cost >= 1e299) throw PlanError("contract: no lowering for " + tag);
 
+  // A batched DMMA lowering that avoids a permute may still lose against ONE large INT8 product plus that permute
+  // (e.g. 'ijbc,ca->ijab': 1600 products of 400^3 at 18 TFLOP/s vs one 640000 x 400 x 400 product and a transposed
+  // accumulate of the result): compare the two with the same cost models as below.
+  if (oz_ns > 0 && oz_min_flops >= 0.0 && best.bcls != 0 && best0.cost < 1e299) {
+    const int64_t M0 = dims_of(best0.om, dm), N0 = dims_of(best0.on, dm), K0 = dims_of(best0.ok, dm);
+    const double fl0 = 2.0 * (double)M0 * (double)N0 * (double)K0;
+    const bool plain = (K0 + 31) / 32 <= 65535 && A.slot != S_VVVV_P && B.slot != S_VVVV_P && A.slot != S_OVVV_P &&
+                       B.slot != S_OVVV_P;
+    if (plain && fl0 >= oz_min_flops) {
+      MatView vc0 = mat_view(C, sc, best0.om, best0.on);
+      const double perm0 = 8.0 * best0.cost / 2.5e12, perm1 = 8.0 * best.cost / 2.5e12;
+      const double cut = (8.0 + 2.0 * oz_ns) * ((double)M0 + (double)N0) * (double)K0 / 5e12;
+      const double t_oz = oz_time(oz_ns, sm_count, M0, N0, K0, vc0.any ? vc0.sr : N0, vc0.any ? vc0.scol : 1,
+                                  vc0.any ? beta : 0.0, nullptr) + cut + perm0 + 2e-5;
+      const double t_dmma = fl0 / 1.8e13 + perm1;
+      if (t_oz < 0.7 * t_dmma) best = best0;
+    }
+  }
   const Choice& ch = best;
   const int64_t nb = ch.bt.empty() ? 1 : dims_of(ch.bt, dm);
   const int64_t Md = dims_of(ch.om, dm), Nd = dims_of(ch.on, dm), Kd = dims_of(ch.ok, dm);
