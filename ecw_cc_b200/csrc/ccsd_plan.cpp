@@ -88,10 +88,12 @@ void emit_wovvo_rows(Plan& P, const Slots& s, const Tensor& t1, const Tensor& t2
   Tensor Wl = slice0(Wph, m0, nm);
   P.contract(c2, slice0(s.oovv_ph, m0, nm), "menf", t2x, "nfjb", 0.0, Wl, "mejb", "R1 Wovvo");
   P.contract(1.0, slice0(s.ovvv, m0, nm), "mbef", t1, "jf", 1.0, Wl, "mejb");
-  P.contract(1.0, t1, "nb", slice0(s.ooov, m0, nm), "mnje", 1.0, Wl, "mejb");
-  Tensor U = P.tmp({nm, o, v, o});
-  P.contract(1.0, slice0(s.oovv, m0, nm), "mnef", t1, "jf", 0.0, U, "mnej");
-  P.contract(-1.0, t1, "nb", U, "mnej", 1.0, Wl, "mejb");
+  // -t1[nb] (oovv[mnef] t1[jf] - ooov[mnje]) (CCSD.py:409-410 and the t1.ooov term): the two o^3v operands are
+  // combined first, so that the o^2v^2 result is updated by ONE K = nocc product instead of two
+  Tensor U = P.tmp({nm, o, o, v});
+  P.axpby(-1.0, slice0(s.ooov, m0, nm), 0.0, U);
+  P.contract(1.0, slice0(s.oovv, m0, nm), "mnef", t1, "jf", 1.0, U, "mnje");
+  P.contract(-1.0, t1, "nb", U, "mnje", 1.0, Wl, "mejb");
   P.release(U);
   P.axpby(-1.0, slice0(s.ovov_ph, m0, nm), 1.0, Wl);
 }
@@ -416,13 +418,14 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   Tensor lt_p = P.tmp({po, po});
   P.contract(2.0, l2_p, "if", tau_p, "kf", 0.0, lt_p, "ik", "l2.tau");
 
-  Tensor S = P.tmp({o, o, v, o});
-  P.contract(1.0, s.oovv, "ljbd", t1, "kd", 0.0, S, "ljbk");
+  // t1[lc] (oovv[ljbd] t1[kd] - ooov[ljkb]) (CCSD.py:593-597): operands combined first, one K = nocc update of wph
+  Tensor S = P.tmp({o, o, o, v});
+  P.axpby(-1.0, s.ooov, 0.0, S);
+  P.contract(1.0, s.oovv, "ljbd", t1, "kd", 1.0, S, "ljkb");
   Tensor wph = P.tmp({o, v, o, v});    // wovvo as [(kc),(jb)]
   P.axpby(1.0, v4ph, 0.0, wph);
-  P.contract(1.0, t1, "lc", S, "ljbk", 1.0, wph, "kcjb");
+  P.contract(1.0, t1, "lc", S, "ljkb", 1.0, wph, "kcjb");
   P.release(S);
-  P.contract(-1.0, t1, "lc", s.ooov, "ljkb", 1.0, wph, "kcjb");
   if (P.world == 1) {
     P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
   } else {
@@ -779,13 +782,13 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
   P.release(y4);
   P.contract(0.5, s.oovv_p, "if", tau_q, "kf", 1.0, woo_p, "ik", "v3");
 
-  Tensor S = P.tmp({o, o, v, o});
-  P.contract(1.0, s.oovv, "ljbd", t1, "kd", 0.0, S, "ljbk");
+  Tensor S = P.tmp({o, o, o, v});
+  P.axpby(-1.0, s.ooov, 0.0, S);
+  P.contract(1.0, s.oovv, "ljbd", t1, "kd", 1.0, S, "ljkb");
   Tensor wph = P.tmp({o, v, o, v});
   P.axpby(1.0, v4ph, 0.0, wph);
-  P.contract(1.0, t1, "lc", S, "ljbk", 1.0, wph, "kcjb");
+  P.contract(1.0, t1, "lc", S, "ljkb", 1.0, wph, "kcjb");
   P.release(S);
-  P.contract(-1.0, t1, "lc", s.ooov, "ljkb", 1.0, wph, "kcjb");
   if (P.world == 1) {
     P.contract(1.0, s.ovvv, "jcbd", t1, "kd", 1.0, wph, "kcjb");
   } else {
