@@ -29,9 +29,9 @@ def _is_num(x):
 
 
 class Gccs(object):
-    def __init__(self, eris, fock=None, M_tot=None, device=None):
+    def __init__(self, eris, fock=None, M_tot=None, device=None, gemm=None):
         if not isinstance(eris, DeviceEris):
-            eris = DeviceEris.from_geris(eris, device=device)
+            eris = DeviceEris.from_geris(eris, device=device, gemm=gemm)
         self.M_tot = 1 if M_tot is None else M_tot                   # CCS.py:207-210
         self.eris = eris
         self.fock = np.asarray(eris.fock) if fock is None else fock  # CCS.py:212-215

@@ -25,14 +25,17 @@ def _flags(alpha, equation, antisym=False):
 
 
 class GCC(object):
-    def __init__(self, eris, fock=None, device=None, assume_antisym=None, rank=0, world=1, group=None):
+    def __init__(self, eris, fock=None, device=None, assume_antisym=None, rank=0, world=1, group=None, gemm=None,
+                 int8_digits=None):
         """:param eris: a `DeviceEris`, or any object with the reference's
         `Eris.geris` attribute surface (uploaded once).
+        :param gemm, int8_digits: GEMM engine of the uploaded container ("int8" default / "dmma"; eris.py)
         :param assume_antisym: None (default) = measure the antisymmetry of the doubles amplitudes
         on the device at every call and pick the packed or the general path; True/False = force."""
         self.assume_antisym = assume_antisym
         if not isinstance(eris, DeviceEris):
-            eris = DeviceEris.from_geris(eris, device=device, rank=rank, world=world, group=group)
+            eris = DeviceEris.from_geris(eris, device=device, rank=rank, world=world, group=group, gemm=gemm,
+                                         int8_digits=int8_digits)
         self.eris = eris
         self.nocc = eris.nocc
         if fock is None:                       # CCSD.py:196-198

@@ -45,11 +45,15 @@ def clock():
     return out.strip()
 
 
-for name, env in [("grid74", {"ECW_OZ_GRID": "74"}), ("grid74_15prod", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "16"}),
+# ECW_OZ_DEBUG bits: 1 no loads, 2 A planes only, 4 B planes only, 16 only 15 of the 21 products
+for name, env in [("normal", {}), ("noload", {"ECW_OZ_DEBUG": "1"}), ("grid74", {"ECW_OZ_GRID": "74"}),
+                  ("grid74_noload", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "1"}),
+                  ("grid74_Aonly", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "2"}),
+                  ("grid74_Bonly", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "4"}),
+                  ("grid74_15prod", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "16"}),
                   ("grid74_15prod_noload", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "17"}),
-                  ("grid74_15prod_Aonly", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "18"}),
-                  ("grid74_noload", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "1"})]:
-    for k in ("ECW_OZ_DEBUG", "ECW_OZ_GRID", "ECW_OZ_PF"):
+                  ("grid74_15prod_Aonly", {"ECW_OZ_GRID": "74", "ECW_OZ_DEBUG": "18"})]:
+    for k in ("ECW_OZ_DEBUG", "ECW_OZ_GRID"):
         os.environ.pop(k, None)
     os.environ.update(env)
     run(1)
