@@ -288,6 +288,23 @@ def run_ours(args):
     h2d = cc.h2d_bytes // (e2e_steps + 1)
     d2h = cc.d2h_bytes // (e2e_steps + 1)
 
+    # ---- the solver loop itself, device resident (ecw_cc_b200.Solver_CCSD mirrors Solver_GS.Solver_CCSD.SCF): per
+    # iteration gamma -> Vexp('mat') on the host (n x n) -> energy -> tupdate -> lupdate -> convergence vector
+    import numpy as np
+    from ecw_cc_b200.exp_pot import Exp
+    rng = np.random.default_rng(7)
+    pert = 0.02 * rng.standard_normal((n, n))
+    target = np.diag(np.concatenate([np.ones(o), np.zeros(v)])) + 0.5 * (pert + pert.T)
+    solver = ecw.Solver_CCSD(cc, Exp(0.05, [[["mat", target]]]), conv_thres=0.0, maxiter=1,
+                             tsini=t1, lsini=l1, tdini=t2, ldini=l2)
+    solver_calls = max(1, min(args.steps, 3) // 2 + 1)
+
+    def solver_run():
+        return solver.SCF(0.05, alpha=alpha, return_device=True)        # maxiter=1: exactly two iterations
+
+    ms_solver, sout = timed(solver_run, solver_calls, 1)
+    solver_iters = 2 * solver_calls
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -353,6 +370,10 @@ def run_ours(args):
                    "tflops_alg": f_alg(o, v) * evals_per_s / 1e12, "tflops_executed": exec_flops * evals_per_s / 1e12},
         "clocks": clocks,
         "e2e": {"value": e2e_per_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "solver_loop": {"value": solver_iters / (ms_solver / 1e3), "unit": "iterations/s",
+                        "h2d_bytes_per_iteration": n * n * 8, "d2h_bytes_per_iteration": n * n * 8 + 16,
+                        "what": "ecw_cc_b200.Solver_CCSD.SCF (mirror of Solver_GS.Solver_CCSD.SCF): the same iteration "
+                                "with the amplitudes resident on the GPU; only rdm1 / dressed Fock cross PCIe"},
         "gpu_launches": int(launches * args.steps),
         "roofline": roofline,
     }

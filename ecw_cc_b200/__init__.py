@@ -11,5 +11,7 @@ from .CCSD import GCC, gamma_CCSD  # noqa: F401
 from .CCS import Gccs  # noqa: F401
 from .devops import DevOps  # noqa: F401
 from .utilities import subdiff  # noqa: F401
+from .Solver_GS import Solver_CCSD  # noqa: F401
+from . import exp_pot  # noqa: F401
 
-__all__ = ["GCC", "Gccs", "DevOps", "DeviceEris", "subdiff", "gamma_CCSD", "build", "lib", "EcwError"]
+__all__ = ["GCC", "Gccs", "Solver_CCSD", "DevOps", "DeviceEris", "subdiff", "gamma_CCSD", "build", "lib", "EcwError"]

@@ -804,6 +804,15 @@ int ecw_op_dot(ecw_ctx* c, double alpha, const ecw_tensor* A, const ecw_tensor* 
   });
 }
 
+int ecw_conv_check(const double* a, const double* b, const double* prev, double* conv, int64_t n, double* scratch1024,
+                   double* sumsq, int accumulate, void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    ck(launch_conv(a, b, prev, conv, n, scratch1024, 1024, sumsq, accumulate ? 1.0 : 0.0, static_cast<cudaStream_t>(stream)),
+       "conv_check");
+  });
+}
+
 int ecw_profile_enable(ecw_ctx* c, int on) {
   if (!c) return -1;
   c->profile = on != 0;

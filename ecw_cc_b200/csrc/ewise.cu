@@ -368,6 +368,30 @@ dot_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, i
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// convergence vector of the solver loop (Solver_GS.py:598-612): conv = |a| + |b| (b == nullptr: conv = a) and the
+// per-block partial sums of (conv - prev)^2 (prev == nullptr: skipped); fixed two-stage reduction order
+__global__ void __launch_bounds__(EW_THREADS)
+conv_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ prev,
+                    double* __restrict__ conv, int64_t n, double* partial) {
+  __shared__ double sh[EW_THREADS];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double c = b ? fabs(a[i]) + fabs(b[i]) : a[i];
+    if (prev) {
+      const double d = c - prev[i];
+      s += d * d;
+    }
+    conv[i] = c;
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = EW_THREADS / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
 __global__ void __launch_bounds__(EW_THREADS)
 dot_final_kernel(const double* partial, int nb, double* scal, double alpha, double beta) {
   __shared__ double sh[EW_THREADS];
@@ -566,6 +590,15 @@ cudaError_t launch_finish(const double* r, const double* amp, const double* fock
 cudaError_t launch_subdiff(const double* e, const double* v, double alpha, double* out, int64_t n, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   subdiff_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, st>>>(e, v, alpha, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv(const double* a, const double* b, const double* prev, double* conv, int64_t n, double* partial,
+                        int nblocks, double* scal, double beta, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  int nb = (int)std::min<int64_t>(nblocks, std::max<int64_t>(1, (n + EW_THREADS - 1) / EW_THREADS));
+  conv_partial_kernel<<<nb, EW_THREADS, 0, st>>>(a, b, prev, conv, n, partial);
+  dot_final_kernel<<<1, EW_THREADS, 0, st>>>(partial, nb, scal, 1.0, beta);
   return cudaGetLastError();
 }
 

@@ -114,6 +114,9 @@ cudaError_t launch_finish(const double* r, const double* amp, const double* fock
                           int o, int v, int rank, int has_alpha, int equation, double alpha, double shift,
                           int sub_singles, cudaStream_t st);
 cudaError_t launch_subdiff(const double* e, const double* v, double alpha, double* out, int64_t n, cudaStream_t st);
+// conv = |a| + |b| (b null: a); scal = beta*scal + sum (conv - prev)^2 (prev null: + 0); partial: nblocks doubles
+cudaError_t launch_conv(const double* a, const double* b, const double* prev, double* conv, int64_t n, double* partial,
+                        int nblocks, double* scal, double beta, cudaStream_t st);
 cudaError_t launch_dot(const double* a, const double* b, int64_t n, double* partial, int nblocks, double* scal,
                        double alpha, double beta, cudaStream_t st);
 cudaError_t launch_scale_dev(double* c, int64_t n, const double* scal, double d0, double d1, cudaStream_t st);

@@ -123,6 +123,14 @@ int ecw_antisym_defect(const double* x, int nocc, int nvir, double* out, void* s
 /* utilities.subdiff(eq,var,alpha) — utilities.py:26-73 (element-wise, any shape). */
 int ecw_subdiff(const double* eq, const double* var, double alpha, double* out, int64_t n, void* stream);
 
+/* ---- solver loop (Solver_GS.Solver_CCSD.SCF, Solver_GS.py:621-742) ------------------------------------------
+ * Convergence vector of one amplitude pair and its squared distance to the previous iteration's
+ * (tl_check / l_check, Solver_GS.py:598-612): conv[i] = |a[i]| + |b[i]| (b == NULL: conv[i] = a[i]);
+ * sumsq[0] = (accumulate ? sumsq[0] : 0) + sum_i (conv[i] - prev[i])^2 (prev == NULL: + 0).  conv may not alias prev;
+ * scratch1024: 1024 device doubles.  Deterministic (fixed two-stage reduction). */
+int ecw_conv_check(const double* a, const double* b, const double* prev, double* conv, int64_t n, double* scratch1024,
+                   double* sumsq, int accumulate, void* stream);
+
 /* ---- primitive device ops ---------------------------------------------------------
  * The CCS class (CCS.py:197-1518: T1inter/tsupdate/L1inter/lsupdate/R1inter/rsupdate/es_L1inter/
  * es_lsupdate/R0inter/L0inter/*_fromE/gamma_*) and the GCC intermediate getters (cc_Fvv, cc_Woooo,

@@ -1,0 +1,59 @@
+"""Converged L1-ECW-CCSD ground states (BASELINE.json north_star: "the converged energies and rdm1 must also match"):
+the device-resident solver mirror `ecw_cc_b200.Solver_CCSD` (amplitudes stay on the GPU; per iteration only the rdm1 and
+the dressed Fock cross PCIe) against runs of the UNMODIFIED reference solver + CCSD.GCC + exp_pot.Exp
+(tests/golden/solver_ccsd_*.npz, oracle/make_golden_solver.py), under every GEMM engine."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle import synth
+from oracle.make_golden_solver import CASES, target_rdm1
+from oracle.solver_np import ExpMat
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.mark.parametrize("name", ["solver_ccsd_o4v6.npz", "solver_ccsd_o8v16.npz"])
+def test_solver_matches_reference_runs(built_lib, name, engine):
+    import ecw_cc_b200 as ecw
+    g = load_golden(name)
+    o, v = int(g["nocc"]), int(g["nvir"])
+    er = synth.SynthEris(o, v)
+    for tag, L, alpha, maxiter in CASES:
+        mycc = ecw.GCC(er)
+        solver = ecw.Solver_CCSD(mycc, ExpMat(L, target_rdm1(o, v)), conv="tl", conv_thres=float(g["conv_thres"]),
+                                 maxiter=maxiter)
+        text, ep, delta, conv, rdm1, amps = solver.SCF(L, alpha=alpha)
+        assert text == str(g[tag + "_text"]), tag
+        assert ep.shape == g[tag + "_Ep"].shape and np.abs(ep - g[tag + "_Ep"]).max() < TOL, tag
+        assert np.abs(delta - g[tag + "_Delta"]).max() < TOL, tag
+        assert np.allclose(conv, g[tag + "_conv"], rtol=1e-4, atol=1e-11), tag
+        assert np.abs(rdm1 - g[tag + "_rdm1"]).max() < TOL, tag
+        for k, a in zip(("ts", "ls", "td", "ld"), amps):
+            assert np.abs(a - g[tag + "_" + k]).max() < TOL, (tag, k)
+
+
+def test_solver_numpy_api_and_device_api_agree(built_lib):
+    """The reference loop written against the numpy API of GCC (what the unchanged reference solver does) and the
+    device-resident mirror walk through the same iterates; other convergence measures and start vectors work."""
+    import ecw_cc_b200 as ecw
+    from oracle.solver_np import scf_loop
+    o, v = 6, 10
+    er = synth.SynthEris(o, v)
+    L, alpha = 0.05, None
+    ref = scf_loop(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), L, alpha=alpha, conv_thres=1e-8, maxiter=30)
+    for conv in ("tl", "l", "Ep"):
+        r2 = scf_loop(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), L, alpha=alpha, conv_thres=1e-8, maxiter=30, conv=conv)
+        s = ecw.Solver_CCSD(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), conv=conv, conv_thres=1e-8, maxiter=30)
+        out = s.SCF(L, alpha=alpha)
+        assert out[0] == r2[0] and np.abs(out[1] - r2[1]).max() < 1e-12
+        assert np.allclose(out[3], r2[3], rtol=1e-6, atol=1e-13)
+        for a, b in zip(out[5], r2[5]):
+            assert np.abs(a - b).max() < 1e-12
+    # restart from converged amplitudes: one more pass stays converged
+    s = ecw.Solver_CCSD(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), conv_thres=1e-8, maxiter=30)
+    out = s.SCF(L, ref[5][0], ref[5][1], ref[5][2], ref[5][3])
+    assert abs(out[1][-1] - ref[1][-1]) < 1e-9
+    with pytest.raises(NotImplementedError):
+        ecw.Solver_CCSD(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), diis='tl')
