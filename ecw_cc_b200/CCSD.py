@@ -12,7 +12,7 @@ from ._lib import lib, EcwError, ECW_HAS_ALPHA, ECW_EQUATION, ECW_ANTISYM
 from .eris import DeviceEris
 
 
-# Amplitudes whose antisymmetry defect max|x[ijab]+x[jiab]|, |x[ijab]+x[ijba]| is below this run
+# Amplitudes whose antisymmetry defect max|x[ijab]+x[jiab]|, |x[ijab]+x[ijba]| is below this (times max(1, max|x|)) run
 # the fully packed path (the defect only enters the result multiplied by O(1) integrals/amplitudes,
 # far below the 1e-10 parity bar); anything larger — e.g. after an L1-regularised update, which
 # breaks antisymmetry in the reference (utilities.py:59-67) — runs the general path.
@@ -89,19 +89,28 @@ class GCC(object):
         outs = [h.numpy() for h in outs]
         return outs[0] if len(outs) == 1 else tuple(outs)
 
-    def antisym_defect(self, d_x):
-        """max |x[ijab]+x[jiab]|, |x[ijab]+x[ijba]| of a device doubles amplitude."""
+    def antisym_stats(self, d_x):
+        """(max |x[ijab]+x[jiab]|, |x[ijab]+x[ijba]|, max |x|) of a device doubles amplitude."""
         torch = self._torch()
         e = self.eris
-        out = torch.zeros(1, dtype=torch.float64, device=e.device)
+        out = torch.zeros(2, dtype=torch.float64, device=e.device)
         if lib.ecw_antisym_defect(d_x.data_ptr(), self.nocc, self.nvir, out.data_ptr(), e.stream()) != 0:
             raise EcwError("ecw_antisym_defect failed")
-        return float(out.cpu()[0])
+        h = out.cpu()
+        return float(h[0]), float(h[1])
+
+    def antisym_defect(self, d_x):
+        return self.antisym_stats(d_x)[0]
 
     def _is_antisym(self, *amps):
+        """Packed path when every amplitude is antisymmetric to ANTISYM_TOL relative to max(1, max|x|)."""
         if self.assume_antisym is not None:
             return bool(self.assume_antisym)
-        return all(self.antisym_defect(a) <= ANTISYM_TOL for a in amps)
+        for a in amps:
+            defect, amax = self.antisym_stats(a)
+            if not defect <= ANTISYM_TOL * max(1.0, amax):
+                return False
+        return True
 
     def _fsp(self, fsp):
         n = self.nocc + self.nvir

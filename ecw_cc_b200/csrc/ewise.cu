@@ -190,29 +190,37 @@ tau_kernel(const double* __restrict__ t2, const double* __restrict__ t1, double*
   }
 }
 
-// max asymmetry of a doubles amplitude; non-negative doubles order like their bit patterns
+// out[0] = max asymmetry of a doubles amplitude, out[1] = max |x| (non-negative doubles order like their bit patterns)
 __global__ void __launch_bounds__(EW_THREADS)
 defect_kernel(const double* __restrict__ x, int o, int v, double* out) {
-  __shared__ double sh[EW_THREADS];
-  const int64_t vv = (int64_t)v * v, total = (int64_t)o * o * vv;
-  double m = 0.0;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t ij = idx / vv, ab = idx - ij * vv;
-    int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
-    int a = (int)(ab / v), b = (int)(ab - (int64_t)a * v);
-    double val = x[idx];
-    m = fmax(m, fabs(val + x[((int64_t)j * o + i) * vv + ab]));
-    m = fmax(m, fabs(val + x[ij * vv + (int64_t)b * v + a]));
+  __shared__ double sh[EW_THREADS], sa[EW_THREADS];
+  const uint32_t uv = (uint32_t)v, vv = uv * uv;
+  double m = 0.0, am = 0.0;
+  for (int64_t row = blockIdx.y; row < (int64_t)o * o; row += gridDim.y) {
+    const int i = (int)(row / o), j = (int)(row - (int64_t)i * o);
+    const double* __restrict__ xr = x + row * vv;
+    const double* __restrict__ xt = x + ((int64_t)j * o + i) * vv;
+    for (uint32_t ab = blockIdx.x * blockDim.x + threadIdx.x; ab < vv; ab += gridDim.x * blockDim.x) {
+      const uint32_t a = ab / uv, b = ab - a * uv;
+      const double val = xr[ab];
+      am = fmax(am, fabs(val));
+      m = fmax(m, fmax(fabs(val + xt[ab]), fabs(val + xr[b * uv + a])));
+    }
   }
   sh[threadIdx.x] = m;
+  sa[threadIdx.x] = am;
   __syncthreads();
   for (int w = EW_THREADS / 2; w > 0; w >>= 1) {
-    if (threadIdx.x < w) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
+    if (threadIdx.x < w) {
+      sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
+      sa[threadIdx.x] = fmax(sa[threadIdx.x], sa[threadIdx.x + w]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(sh[0]));
+    atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)__double_as_longlong(sa[0]));
+  }
 }
 
 // packed pair index k = hi(hi-1)/2 + lo  (lo < hi)
@@ -539,11 +547,13 @@ cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, i
 }
 
 cudaError_t launch_antisym_defect(const double* x, int o, int v, double* out, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), st);
+  cudaError_t e = cudaMemsetAsync(out, 0, 2 * sizeof(double), st);
   if (e != cudaSuccess) return e;
   int64_t total = (int64_t)o * o * v * v;
   if (total <= 0) return cudaSuccess;
-  defect_kernel<<<grid_for(total, EW_THREADS * 4), EW_THREADS, 0, st>>>(x, o, v, out);
+  dim3 grid((unsigned)std::min<int64_t>(((int64_t)v * v + EW_THREADS - 1) / EW_THREADS, 16),
+            (unsigned)std::min<int64_t>((int64_t)o * o, 65535));
+  defect_kernel<<<grid, EW_THREADS, 0, st>>>(x, o, v, out);
   return cudaGetLastError();
 }
 

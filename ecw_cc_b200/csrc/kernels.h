@@ -92,7 +92,7 @@ cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, 
 // out[ijab] = t2[ijab] + c1*t1[ia]t1[jb] - c2*t1[ib]t1[ja]
 cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double c1, double c2,
                        cudaStream_t st);
-// out[0] = max(|x[ijab]+x[jiab]|, |x[ijab]+x[ijba]|)  (0 for exactly antisymmetric doubles amplitudes)
+// out[0] = max(|x[ijab]+x[jiab]|, |x[ijab]+x[ijba]|)  (0 for exactly antisymmetric doubles amplitudes), out[1] = max|x|
 cudaError_t launch_antisym_defect(const double* x, int o, int v, double* out, cudaStream_t st);
 
 struct PackArgs {

@@ -118,7 +118,7 @@ int ecw_ccsd_gamma(ecw_ctx* ctx, const double* t1, const double* t2, const doubl
 /* GCC.energy(t1,t2,fsp) — CCSD.py:224-242.  e_out: one device double. */
 int ecw_ccsd_energy(ecw_ctx* ctx, const double* t1, const double* t2, const double* fsp, double* e_out,
                     void* stream);
-/* out[0] = max |x[ijab]+x[jiab]|, |x[ijab]+x[ijba]| over a doubles amplitude (device scalar). */
+/* out[0] = max |x[ijab]+x[jiab]|, |x[ijab]+x[ijba]| over a doubles amplitude, out[1] = max |x| (two device doubles). */
 int ecw_antisym_defect(const double* x, int nocc, int nvir, double* out, void* stream);
 /* utilities.subdiff(eq,var,alpha) — utilities.py:26-73 (element-wise, any shape). */
 int ecw_subdiff(const double* eq, const double* var, double alpha, double* out, int64_t n, void* stream);
