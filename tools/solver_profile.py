@@ -48,4 +48,4 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 out = s.SCF(0.05, return_device=True)
 torch.cuda.synchronize(); tot = (time.perf_counter() - t0) * 1e3
 print("SCF total %.1f ms for %d iterations; inside calls: %s; other %.1f" % (tot, len(out[1]), {k: round(x, 1) for k, x in acc.items()}, tot - sum(x for k, x in acc.items() if k != "antisym_defect")))
-print("defects", cc.antisym_defect(out[5][2]), cc.antisym_defect(out[5][3]))
+print("final (defect, max|x|): t2", cc.antisym_stats(out[5][2]), "l2", cc.antisym_stats(out[5][3]), "Ep", out[1])
