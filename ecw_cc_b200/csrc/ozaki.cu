@@ -37,12 +37,12 @@
 //                    an accumulator and all NS digits of A and B are loaded once per k-block.  Digits
 //                    q = 0..NS-1-p of B are contiguous in shared memory, so they are issued as one MMA of
 //                    N = TN (NS-p) columns (split at 256);
-//   Measured limiter (tools/oz_experiment.py, profiles/r1_oz_limiter.md): a stage is 39.9 KB and 840 clk of MMA
-//   (47 B/clk); an SM ingests ~32.6 B/clk from L2 whatever the path (bulk TMA, cp.async, both), so the main loop
-//   runs at 1224 clk per stage = 69 % of the pipe; without loads it reaches 87 %.  TMEM (NS accumulators x TN
-//   columns <= 512) is what keeps the tile, and with it the bytes per MAC, from growing.
 //   warps 2-5      : epilogue — tcgen05.ld the NS accumulators, Horner in FP64, rank-one terms, scales,
 //                    alpha/beta, store (coalesced across lanes when the tile rows are contiguous in C).
+// Measured limiter (tools/oz_experiment.py, profiles/r1_oz_limiter.md): a stage is 39.9 KB and 840 clk of MMA
+// (47 B/clk); an SM ingests ~32.6 B/clk from L2 whatever the path (bulk TMA, cp.async, both), so the main loop
+// runs at 1224 clk per stage = 69 % of the pipe; without loads it reaches 87 %.  TMEM (NS accumulators x TN
+// columns <= 512) is what keeps the tile, and with it the bytes per MAC, from growing.
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
