@@ -3,7 +3,7 @@ CUDA path (vvvv_p row shard + distributed GEMMs + NCCL all-gathers) and compares
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import numpy as np
 import torch
 import torch.distributed as dist
