@@ -98,6 +98,7 @@ class _Lib(object):
             "ecw_subdiff": (c_i, [c_p, c_p, c_d, c_p, c_l, c_p]),
             "ecw_antisym_defect": (c_i, [c_p, c_i, c_i, c_p, c_p]),
             "ecw_plan_dump": (c_l, [c_p, c_s, c_i, c_p, c_l]),
+            "ecw_plan_dump_contract": (c_l, [c_p, c_d, c_p, c_s, c_p, c_s, c_d, c_p, c_s, c_p, c_l]),
             "ecw_plan_flops": (c_d, [c_p, c_s, c_i]),
             "ecw_plan_launches": (c_l, [c_p, c_s, c_i]),
             "ecw_dgemm": (c_i, [c_i, c_i, c_l, c_l, c_l, c_d, c_p, c_l, c_p, c_l, c_d, c_p, c_l, c_i, c_p]),

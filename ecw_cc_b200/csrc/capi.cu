@@ -576,6 +576,33 @@ int64_t ecw_plan_dump(ecw_ctx* c, const char* func, int flags, char* buf, int64_
   return r;
 }
 
+int64_t ecw_plan_dump_contract(ecw_ctx* c, double alpha, const ecw_tensor* A, const char* sa, const ecw_tensor* B,
+                               const char* sb, double beta, const ecw_tensor* C, const char* sc, char* buf,
+                               int64_t buflen) {
+  int64_t r = -1;
+  guarded(c, [&] {
+    // host only: the lowering ecw_op_contract would launch (operands named a0, a1, b0; ptr fields are ignored)
+    auto desc = [](const ecw_tensor* t, int slot) {
+      Tensor x;
+      if (t->nd < 0 || t->nd > MAXD) throw Fail("ecw_tensor: rank out of range");
+      x.slot = slot;
+      x.nd = t->nd;
+      for (int i = 0; i < t->nd; ++i) { x.dim[i] = t->dim[i]; x.str[i] = t->str[i]; }
+      if (x.nd == 0) { x.nd = 1; x.dim[0] = 1; x.str[0] = 1; }
+      return x;
+    };
+    Plan P;
+    P.oz_ns = c->z.oz_ns; P.oz_min_flops = c->z.oz_min_flops; P.nocc = c->z.nocc; P.nvir = c->z.nvir;
+    P.oz_splitk_min_k = c->z.oz_splitk_min_k;
+    P.contract(alpha, desc(A, S_A0), sa, desc(B, S_A1), sb, beta, desc(C, S_B0), sc, "op");
+    std::string s = P.dump_json();
+    if ((int64_t)s.size() + 1 > buflen) { r = -(int64_t)(s.size() + 1); return; }
+    memcpy(buf, s.c_str(), s.size() + 1);
+    r = (int64_t)s.size();
+  });
+  return r;
+}
+
 double ecw_plan_flops(ecw_ctx* c, const char* func, int flags) {
   double r = -1.0;
   guarded(c, [&] { r = get_plan(c, func, flags).gemm_flops; });

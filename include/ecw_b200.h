@@ -178,6 +178,10 @@ int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* ctx);
 int ecw_ctx_test_assume_ovvv_planes(ecw_ctx* ctx);
 /* JSON dump of the op list a call would launch (host only, no CUDA). */
 int64_t ecw_plan_dump(ecw_ctx* ctx, const char* func, int mode_flags, char* buf, int64_t buflen);
+/* the same for one ecw_op_contract call (operands appear as slots "a0", "a1", "b0"; host only, pointers unused) */
+int64_t ecw_plan_dump_contract(ecw_ctx* ctx, double alpha, const ecw_tensor* A, const char* sa, const ecw_tensor* B,
+                               const char* sb, double beta, const ecw_tensor* C, const char* sc, char* buf,
+                               int64_t buflen);
 /* executed GEMM flops (sum of 2MNK) and launches of a plan */
 double ecw_plan_flops(ecw_ctx* ctx, const char* func, int mode_flags);
 int64_t ecw_plan_launches(ecw_ctx* ctx, const char* func, int mode_flags);
