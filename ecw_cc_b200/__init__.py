@@ -13,5 +13,6 @@ from .devops import DevOps  # noqa: F401
 from .utilities import subdiff  # noqa: F401
 from .Solver_GS import Solver_CCSD  # noqa: F401
 from . import exp_pot  # noqa: F401
+from . import molint  # noqa: F401
 
 __all__ = ["GCC", "Gccs", "Solver_CCSD", "DevOps", "DeviceEris", "subdiff", "gamma_CCSD", "build", "lib", "EcwError"]

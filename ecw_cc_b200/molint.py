@@ -1,0 +1,265 @@
+"""Integral source without PySCF: Gaussian one- and two-electron integrals over s and p shells
+(McMurchie-Davidson), restricted Hartree-Fock, and the spin-orbital antisymmetrised MO integrals of the reference's
+`Eris.geris` container (Eris.py:24-154: `<pq||rs> = <pq|rs> - <pq|sr>`, blocks `oooo ... vvvv`, `fock = diag(mo_energy)`),
+built the way `Main.ECW.__init__` does (Main.py:151-217: RHF -> GHF spin orbitals in `[a, b, a, b, ...]` order).
+
+Host-side numpy on purpose: this is the producer of the path's inputs (a 13-function basis for config 1, H2O/6-31G),
+not the path.  Basis sets embedded: 6-31G for H, C, N, O.  Anchor: E_HF(H2O/6-31G) = -75.9839 (ECW_CC/__init__.py:39).
+"""
+import numpy as np
+from scipy.special import hyp1f1
+
+ANGSTROM = 1.0 / 0.52917721092                 # bohr per Angstrom (the value PySCF uses)
+
+# 6-31G: per element a list of (kind, exponents, s coefficients, p coefficients)
+BASIS_631G = {
+    1: [("S", [18.7311370, 2.8253937, 0.6401217], [0.03349460, 0.23472695, 0.81375733], None),
+        ("S", [0.1612778], [1.0], None)],
+    6: [("S", [3047.5249, 457.36952, 103.94869, 29.210155, 9.2866630, 3.1639270],
+         [0.0018347, 0.0140373, 0.0688426, 0.2321844, 0.4679413, 0.3623120], None),
+        ("SP", [7.8682724, 1.8812885, 0.5442493], [-0.1193324, -0.1608542, 1.1434564], [0.0689991, 0.3164240, 0.7443083]),
+        ("SP", [0.1687144], [1.0], [1.0])],
+    7: [("S", [4173.5110, 627.45790, 142.90210, 40.234330, 12.820210, 4.3904370],
+         [0.0018348, 0.0139950, 0.0685870, 0.2322410, 0.4690700, 0.3604550], None),
+        ("SP", [11.626358, 2.7162800, 0.7722180], [-0.1149610, -0.1691180, 1.1458520], [0.0675800, 0.3239070, 0.7408950]),
+        ("SP", [0.2120313], [1.0], [1.0])],
+    8: [("S", [5484.6717, 825.23495, 188.04696, 52.964500, 16.897570, 5.7996353],
+         [0.0018311, 0.0139501, 0.0684451, 0.2327143, 0.4701930, 0.3585209], None),
+        ("SP", [15.539616, 3.5999336, 1.0137618], [-0.1107775, -0.1480263, 1.1307670], [0.0708743, 0.3397528, 0.7271586]),
+        ("SP", [0.2700058], [1.0], [1.0])],
+}
+
+
+class Molecule(object):
+    """atoms: [(Z, (x, y, z)), ...] in Angstrom (Main.py:104-109 style); basis: '6-31g'."""
+
+    def __init__(self, atoms, basis="6-31g", charge=0):
+        if basis.lower().replace("-", "") != "631g":
+            raise NotImplementedError("embedded basis sets: 6-31G (s and p shells)")
+        self.Z = np.array([a[0] for a in atoms], dtype=np.float64)
+        self.R = np.array([a[1] for a in atoms], dtype=np.float64) * ANGSTROM
+        self.nelec = int(self.Z.sum()) - charge
+        if self.nelec % 2:
+            raise NotImplementedError("closed shells only (RHF)")
+        # primitive Cartesian Gaussians: centre, exponent, (lx,ly,lz), coefficient incl. normalisation, AO index
+        cen, ex, lmn, coef, ao = [], [], [], [], []
+        nao = 0
+        for z, r in zip(self.Z, self.R):
+            for kind, exps, cs, cp in BASIS_631G[int(z)]:
+                for ang, cc in ((0, cs),) + (((1, cp),) if kind == "SP" else ()):
+                    for l3 in ([(0, 0, 0)] if ang == 0 else [(1, 0, 0), (0, 1, 0), (0, 0, 1)]):
+                        for a, c in zip(exps, cc):
+                            norm = (2 * a / np.pi) ** 0.75 * (2 * np.sqrt(a)) ** ang      # primitive s / p norm
+                            cen.append(r); ex.append(a); lmn.append(l3); coef.append(c * norm); ao.append(nao)
+                        nao += 1
+        self.cen, self.ex = np.array(cen), np.array(ex)
+        self.lmn, self.coef, self.ao = np.array(lmn), np.array(coef), np.array(ao)
+        self.nao = nao
+        d = self.R[:, None, :] - self.R[None, :, :]
+        rr = np.sqrt((d ** 2).sum(-1))
+        iu = np.triu_indices(len(self.Z), 1)
+        self.e_nuc = float((self.Z[:, None] * self.Z[None, :])[iu].dot(1.0 / rr[iu]))
+
+
+def _boys(nmax, x):
+    """F_n(x), n = 0..nmax, for an array x."""
+    return np.stack([hyp1f1(n + 0.5, n + 1.5, -x) / (2 * n + 1) for n in range(nmax + 1)])
+
+
+def _hermite_E(imax, jmax, p, XPA, XPB, mu, XAB):
+    """1-D Hermite expansion coefficients E[i][j][t] (arrays over pairs), i <= imax, j <= jmax."""
+    E = [[None] * (jmax + 1) for _ in range(imax + 1)]
+    tmax = imax + jmax
+    z = np.zeros_like(p)
+    E[0][0] = [np.exp(-mu * XAB ** 2)] + [z] * (tmax + 1)
+    for i in range(imax + 1):
+        for j in range(jmax + 1):
+            if i == 0 and j == 0:
+                continue
+            if i > 0:
+                src, X = E[i - 1][j], XPA
+            else:
+                src, X = E[i][j - 1], XPB
+            E[i][j] = [(src[t - 1] / (2 * p) if t > 0 else 0) + X * src[t] + (t + 1) * src[t + 1]
+                       for t in range(tmax + 1)] + [z]
+    return E
+
+
+def _hermite_R(L, alpha, D):
+    """Hermite Coulomb integrals R[t][u][v] (t+u+v <= L) for exponent alpha and distance vectors D[..., 3]."""
+    r2 = (D ** 2).sum(-1)
+    F = _boys(L, alpha * r2)
+    Rn = {(0, 0, 0, n): (-2 * alpha) ** n * F[n] for n in range(L + 1)}
+    X, Y, Z = D[..., 0], D[..., 1], D[..., 2]
+
+    def get(t, u, v, n):
+        key = (t, u, v, n)
+        if key in Rn:
+            return Rn[key]
+        if t > 0:
+            val = X * get(t - 1, u, v, n + 1) + ((t - 1) * get(t - 2, u, v, n + 1) if t > 1 else 0)
+        elif u > 0:
+            val = Y * get(t, u - 1, v, n + 1) + ((u - 1) * get(t, u - 2, v, n + 1) if u > 1 else 0)
+        else:
+            val = Z * get(t, u, v - 1, n + 1) + ((v - 1) * get(t, u, v - 2, n + 1) if v > 1 else 0)
+        Rn[key] = val
+        return val
+    return {(t, u, v): get(t, u, v, 0) for t in range(L + 1) for u in range(L + 1 - t) for v in range(L + 1 - t - u)}
+
+
+def integrals(mol):
+    """Overlap, kinetic, nuclear-attraction [nao, nao] and electron-repulsion (mu nu|la si) [nao]*4, AO basis."""
+    npr = len(mol.ex)
+    I, J = np.meshgrid(np.arange(npr), np.arange(npr), indexing="ij")
+    I, J = I.ravel(), J.ravel()
+    a, b = mol.ex[I], mol.ex[J]
+    p = a + b
+    mu = a * b / p
+    A, B = mol.cen[I], mol.cen[J]
+    P = (a[:, None] * A + b[:, None] * B) / p[:, None]
+    la, lb = mol.lmn[I], mol.lmn[J]
+    cc = mol.coef[I] * mol.coef[J]
+    # 1-D coefficients with j up to l_b + 2 (kinetic energy)
+    Ed = [_hermite_E(1, 3, p, P[:, d] - A[:, d], P[:, d] - B[:, d], mu, A[:, d] - B[:, d]) for d in range(3)]
+
+    def pick(d, dj, t):
+        """E^{la_d, lb_d + dj}_t per pair (lb_d + dj may be -1 or -2: zero)."""
+        out = np.zeros(len(p))
+        for i in (0, 1):
+            for j in range(0, 4):
+                m = (la[:, d] == i) & (lb[:, d] + dj == j)
+                if m.any():
+                    out[m] = Ed[d][i][j][t][m]
+        return out
+    S1 = [pick(d, 0, 0) * np.sqrt(np.pi / p) for d in range(3)]
+    T1 = []
+    for d in range(3):
+        j = lb[:, d]
+        T1.append((-2 * b ** 2 * pick(d, 2, 0) + b * (2 * j + 1) * pick(d, 0, 0) - 0.5 * j * (j - 1) * pick(d, -2, 0))
+                  * np.sqrt(np.pi / p))
+    Sp = S1[0] * S1[1] * S1[2]
+    Tp = T1[0] * S1[1] * S1[2] + S1[0] * T1[1] * S1[2] + S1[0] * S1[1] * T1[2]
+    # Hermite tensor of every pair: Eab[pair, t, u, v], t,u,v <= 2
+    Eab = np.zeros((len(p), 3, 3, 3))
+    for t in range(3):
+        for u in range(3):
+            for v in range(3):
+                if t + u + v <= 2:
+                    Eab[:, t, u, v] = pick(0, 0, t) * pick(1, 0, u) * pick(2, 0, v)
+    Vp = np.zeros(len(p))
+    for Zc, C in zip(mol.Z, mol.R):
+        R = _hermite_R(2, p, P - C)
+        acc = np.zeros(len(p))
+        for (t, u, v), r in R.items():
+            acc += Eab[:, t, u, v] * r
+        Vp -= Zc * 2 * np.pi / p * acc
+    # contraction to AOs
+    nao = mol.nao
+    pair_ao = mol.ao[I] * nao + mol.ao[J]
+
+    def contract1(x):
+        out = np.zeros(nao * nao)
+        np.add.at(out, pair_ao, cc * x)
+        return out.reshape(nao, nao)
+    S, T, V = contract1(Sp), contract1(Tp), contract1(Vp)
+    # electron repulsion: (ab|cd) = 2 pi^2.5 / (p q sqrt(p+q)) sum E_ab(tuv) (-1)^(t'+u'+v') E_cd(t'u'v') R(t+t',u+u',v+v')
+    sign = np.array([[[(-1.0) ** (t + u + v) for v in range(3)] for u in range(3)] for t in range(3)])
+    Ecd = Eab * sign[None]
+    eri = np.zeros((nao * nao, nao * nao))
+    idx = [(t, u, v) for t in range(3) for u in range(3) for v in range(3) if t + u + v <= 2]
+    chunk = 64
+    for s0 in range(0, len(p), chunk):
+        sl = slice(s0, min(len(p), s0 + chunk))
+        pq = p[sl, None] + p[None, :]
+        alpha = p[sl, None] * p[None, :] / pq
+        R = _hermite_R(4, alpha, P[sl, None, :] - P[None, :, :])
+        acc = np.zeros_like(alpha)
+        for (t, u, v) in idx:
+            ea = Eab[sl, t, u, v]
+            if not ea.any():
+                continue
+            for (t2, u2, v2) in idx:
+                ec = Ecd[:, t2, u2, v2]
+                if not ec.any():
+                    continue
+                acc += ea[:, None] * ec[None, :] * R[(t + t2, u + u2, v + v2)]
+        val = 2 * np.pi ** 2.5 / (p[sl, None] * p[None, :] * np.sqrt(pq)) * acc * cc[sl, None] * cc[None, :]
+        # scatter rows to AO pairs
+        for k, row in zip(pair_ao[sl], val):
+            np.add.at(eri[k], pair_ao, row)
+    return S, T, V, eri.reshape(nao, nao, nao, nao)
+
+
+def rhf(mol, ints=None, conv=1e-11, maxiter=100):
+    """Closed-shell SCF with DIIS.  Returns (E_HF, mo_energy, mo_coeff, ints)."""
+    S, T, V, eri = ints if ints is not None else integrals(mol)
+    h = T + V
+    nocc = mol.nelec // 2
+    s, U = np.linalg.eigh(S)
+    X = U / np.sqrt(s)
+    e, C = np.linalg.eigh(X.T @ h @ X)
+    C = X @ C
+    D = 2 * C[:, :nocc] @ C[:, :nocc].T
+    fs, es = [], []
+    E_old = 0.0
+    for it in range(maxiter):
+        F = h + np.einsum("mnls,ls->mn", eri, D) - 0.5 * np.einsum("mlns,ls->mn", eri, D)
+        E = 0.5 * np.sum(D * (h + F)) + mol.e_nuc
+        err = X.T @ (F @ D @ S - S @ D @ F) @ X
+        fs.append(F); es.append(err)
+        fs, es = fs[-8:], es[-8:]
+        if len(fs) > 1:
+            n = len(fs)
+            Bm = -np.ones((n + 1, n + 1)); Bm[n, n] = 0.0
+            for i in range(n):
+                for j in range(n):
+                    Bm[i, j] = np.sum(es[i] * es[j])
+            rhs = np.zeros(n + 1); rhs[n] = -1.0
+            try:
+                c = np.linalg.solve(Bm, rhs)[:n]
+                F = sum(ci * fi for ci, fi in zip(c, fs))
+            except np.linalg.LinAlgError:
+                pass
+        e, C = np.linalg.eigh(X.T @ F @ X)
+        C = X @ C
+        D = 2 * C[:, :nocc] @ C[:, :nocc].T
+        if abs(E - E_old) < conv and np.abs(err).max() < 1e-8:
+            break
+        E_old = E
+    F = h + np.einsum("mnls,ls->mn", eri, D) - 0.5 * np.einsum("mlns,ls->mn", eri, D)
+    E = 0.5 * np.sum(D * (h + F)) + mol.e_nuc
+    e, C = np.linalg.eigh(X.T @ F @ X)
+    return float(E), e, X @ C, (S, T, V, eri)
+
+
+class geris(object):
+    """The attribute surface of the reference's `Eris.geris` (Eris.py:132-154) from an RHF solution:
+    spin orbitals in [alpha, beta, alpha, beta, ...] order (orbspin = 0,1,0,1,...), `fock = diag(mo_energy)`,
+    `<pq||rs> = (pr|qs) - (ps|qr)` with the spin selection rules, all sixteen o/v blocks."""
+
+    def __init__(self, mol, scf_result=None):
+        ehf, e, C, (S, T, V, eri) = scf_result if scf_result is not None else rhf(mol)
+        nmo = C.shape[1]
+        mo = np.einsum("mp,mnls->pnls", C, eri)
+        mo = np.einsum("nq,pnls->pqls", C, mo)
+        mo = np.einsum("lr,pqls->pqrs", C, mo)
+        mo = np.einsum("st,pqrs->pqrt", C, mo)                  # (pq|rs), spatial MOs, chemists' notation
+        n = 2 * nmo
+        sp = np.arange(n) // 2                                   # spatial index of spin orbital
+        spin = np.arange(n) % 2
+        g = mo[np.ix_(sp, sp, sp, sp)] * (spin[:, None, None, None] == spin[None, :, None, None]) \
+            * (spin[None, None, :, None] == spin[None, None, None, :])       # (pq|rs) spin orbitals
+        phys = g.transpose(0, 2, 1, 3)                           # <pq|rs> = (pr|qs)
+        anti = phys - phys.transpose(0, 1, 3, 2)
+        o = mol.nelec
+        self.nocc = o
+        self.fock = np.diag(np.repeat(e, 2))
+        self.mo_energy = np.repeat(e, 2)
+        self.mo_occ = np.concatenate([np.ones(o), np.zeros(n - o)])
+        self.orbspin = spin
+        self.mo_coeff = C
+        self.EHF = self.e_hf = ehf
+        sl = {"o": slice(0, o), "v": slice(o, n)}
+        for name in ("oooo", "ooov", "oovv", "ovov", "ovvo", "ovvv", "vvvv", "vooo", "vovo", "oovo", "vovv", "vvoo", "vvvo",
+                     "voov", "ovoo"):
+            setattr(self, name, np.ascontiguousarray(anti[sl[name[0]], sl[name[1]], sl[name[2]], sl[name[3]]]))

@@ -1,0 +1,62 @@
+"""The PySCF-free integral source (ecw_cc_b200/molint.py): anchors and structure of what it hands to the
+path, and config 1 (H2O/6-31G) through the oracle against runs of the unmodified reference solver."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle.ccsd_np import OracleGCC
+from oracle.make_golden_h2o import CASES, H2O
+from oracle.make_golden_solver import target_rdm1
+from oracle.solver_np import ExpMat, scf_loop
+
+
+@pytest.fixture(scope="module")
+def water():
+    from ecw_cc_b200 import molint
+    mol = molint.Molecule(H2O, "6-31g")
+    scf = molint.rhf(mol)
+    return molint, mol, scf
+
+
+def test_rhf_anchor_and_integral_symmetries(water):
+    molint, mol, (ehf, e, C, (S, T, V, eri)) = water
+    assert mol.nao == 13 and mol.nelec == 10
+    assert abs(ehf - (-75.9839)) < 5e-5                 # ECW_CC/__init__.py:39 (EHF = -7.59839e+01)
+    assert abs(ehf - (-75.98394849810545)) < 1e-8       # value of this implementation (PySCF: -75.983948...)
+    assert np.abs(np.diag(S) - 1).max() < 1e-6 and np.abs(S - S.T).max() < 1e-14
+    assert np.abs(T - T.T).max() < 1e-12 and np.abs(V - V.T).max() < 1e-12
+    for perm in ((1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1)):
+        assert np.abs(eri - eri.transpose(perm)).max() < 1e-12
+    assert np.abs(C.T @ S @ C - np.eye(13)).max() < 1e-10
+    assert e[0] < -20.5 and e[4] < 0 < e[5]             # O 1s core, 5 occupied orbitals
+
+
+def test_geris_surface(water):
+    molint, mol, scf = water
+    er = molint.geris(mol, scf)
+    o, n = er.nocc, er.fock.shape[0]
+    assert (o, n - o) == (10, 16) and np.array_equal(er.fock, np.diag(np.diagonal(er.fock)))
+    assert np.abs(er.oovv + er.oovv.transpose(1, 0, 2, 3)).max() < 1e-12
+    assert np.abs(er.oovv + er.oovv.transpose(0, 1, 3, 2)).max() < 1e-12
+    assert np.abs(er.vvvv - er.vvvv.transpose(2, 3, 0, 1)).max() < 1e-12
+    assert np.abs(er.ovvo + er.ovov.transpose(0, 1, 3, 2)).max() < 1e-12          # ovvo[iabj] = -ovov[iajb]
+    assert np.abs(er.voov + er.ovov.transpose(1, 0, 2, 3)).max() < 1e-12          # voov[akic] = -ovov[kaic]
+    # Brillouin: the HF determinant's singles vanish, the MP2 energy is negative and of the known size
+    e = np.diagonal(er.fock)
+    d = e[:o, None, None, None] + e[None, :o, None, None] - e[None, None, o:, None] - e[None, None, None, o:]
+    emp2 = 0.25 * np.sum(er.oovv ** 2 / d)
+    assert -0.14 < emp2 < -0.12
+
+
+def test_config1_oracle_reproduces_reference_runs(water):
+    """H2O/6-31G ECW-CCSD ground states: oracle loop vs the unmodified reference solver (tests/golden/h2o_631g.npz)."""
+    molint, mol, _ = water
+    g = load_golden("h2o_631g.npz")
+    ints = molint.integrals(mol)
+    er = molint.geris(mol, (float(g["EHF"]), g["mo_energy"], g["mo_coeff"], ints))
+    assert abs(float(g["L0_Ep"][-1]) - (-0.1353978855)) < 1e-9      # CCSD correlation energy of water in 6-31G
+    tag, L, alpha, maxiter = CASES[1]
+    out = scf_loop(OracleGCC(er), ExpMat(L, target_rdm1(10, 16)), L, alpha=alpha, conv_thres=float(g["conv_thres"]),
+                   maxiter=maxiter)
+    assert out[0] == str(g[tag + "_text"])
+    assert np.abs(out[1] - g[tag + "_Ep"]).max() < 1e-11 and np.abs(out[4] - g[tag + "_rdm1"]).max() < 1e-10
