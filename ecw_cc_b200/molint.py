@@ -31,12 +31,13 @@ BASIS_631G = {
 
 
 class Molecule(object):
-    """atoms: [(Z, (x, y, z)), ...] in Angstrom (Main.py:104-109 style); basis: '6-31g'."""
+    """atoms: [(Z or element symbol, (x, y, z)), ...] in Angstrom (Main.py:104-109 style); basis: '6-31g'."""
+    SYMBOLS = {"H": 1, "C": 6, "N": 7, "O": 8}
 
     def __init__(self, atoms, basis="6-31g", charge=0):
         if basis.lower().replace("-", "") != "631g":
             raise NotImplementedError("embedded basis sets: 6-31G (s and p shells)")
-        self.Z = np.array([a[0] for a in atoms], dtype=np.float64)
+        self.Z = np.array([self.SYMBOLS[a[0].capitalize()] if isinstance(a[0], str) else a[0] for a in atoms], dtype=np.float64)
         self.R = np.array([a[1] for a in atoms], dtype=np.float64) * ANGSTROM
         self.nelec = int(self.Z.sum()) - charge
         if self.nelec % 2:
