@@ -6,12 +6,15 @@ object (`exp_pot.Exp`, exp_pot.py:131-345) turns it into Vexp, and the dressed F
 and its norm are formed on the device (`ecw_conv_check`).
 
 The reference loop driven through the numpy API of `GCC` moves 16 GB over PCIe per iteration at (40,400); this loop
-moves 3 MB.  DIIS (`pyscf.lib.diis`, not part of the reference tree: parity unpinned) is not provided:
-`diis` must be '' — which is what `Main.CCSD_GS` uses (Q5).
+moves 3 MB.  DIIS (Solver_GS.py:666-674, 683-686, 709-718) is provided by `ecw_cc_b200.diis.DIIS`: 'tl' extrapolates
+the amplitude sets on the device (history in HBM, only the Gram row comes to the host), 'rdm1' the n x n rdm1 on the
+host.  `pyscf.lib.diis` is not part of the reference tree, so DIIS-accelerated runs are pinned to the restatement of its
+published algorithm (parity unpinned against PySCF itself); the default is diis='' as in `Main.CCSD_GS` (Q5).
 """
 import numpy as np
 
 from ._lib import lib, EcwError
+from .diis import DIIS
 
 
 class Solver_CCSD(object):
@@ -45,8 +48,6 @@ class Solver_CCSD(object):
             ldini = tdini.clone()
         self.tdini = up(tdini, (o, o, v, v))
         self.ldini = up(ldini, (o, o, v, v)) if ldini is not None else self.tdini.clone()
-        if diis not in ('', None):
-            raise NotImplementedError("DIIS is not provided (pyscf.lib.diis is outside the reference tree); diis=''")
         self.diis = diis
         self.maxdiis = maxdiis
         self.maxiter = maxiter
@@ -79,8 +80,8 @@ class Solver_CCSD(object):
         """Same loop as Solver_GS.py:621-742.  Returns (text, Ep(it), (Delta, vmax)(it), conv(it), last rdm1,
         [ts, ls, td, ld]) with numpy arrays (torch CUDA tensors for the amplitudes when return_device)."""
         torch = self.torch
-        if diis not in ('', None):
-            raise NotImplementedError("DIIS is not provided; diis=''")
+        if diis is None:                                   # Q5 (Solver_GS.py:648-649): only None selects self.diis
+            diis = self.diis
         mycc, VXexp = self.mycc, self.myVexp
         dev = mycc.eris.device
         o, v = self.nocc, self.nvir
@@ -106,8 +107,17 @@ class Solver_CCSD(object):
         conv_ite, Delta_ite, Ep_ite = [], [], []
         rdm1 = []
         Conv_text = ''
+        adiis = tl_diis = None
+        if 'rdm1' in diis:                                 # Solver_GS.py:666-674
+            adiis = DIIS()
+            adiis.space, adiis.min_space = self.maxdiis, 2
+        if 'tl' in diis:
+            tl_diis = DIIS(mycc._dev_ops())
+            tl_diis.space, tl_diis.min_space = self.maxdiis, 2
         while Dconv > self.conv_thres:
             rdm1 = mycc.gamma(ts, td, ls, ld).cpu().numpy()                       # n x n to the host
+            if adiis is not None:
+                rdm1 = adiis.update(rdm1)
             Delta, vmax = VXexp.Vexp_update(rdm1, rdm1, (0, 0), L=L)
             fsp_h = np.subtract(self.fock, VXexp.Vexp[0, 0])
             fsp = torch.from_numpy(np.ascontiguousarray(fsp_h, dtype=np.float64)).to(dev)
@@ -115,6 +125,8 @@ class Solver_CCSD(object):
             Ep_ite.append(float(mycc.energy(ts, td, fsp)))
             ts, td = mycc.tupdate(ts, td, fsp=fsp, alpha=alpha)
             ls, ld = mycc.lupdate(ts, td, ls, ld, fsp=fsp, alpha=alpha)
+            if tl_diis is not None:
+                ls, ts, ld, td = tl_diis.update([ls, ts, ld, td])
             if self.conv == 'Ep':
                 ep = float(mycc.energy(ts, td, fsp))
                 if ite > 0:

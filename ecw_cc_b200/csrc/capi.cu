@@ -820,9 +820,17 @@ int ecw_op_dot(ecw_ctx* c, double alpha, const ecw_tensor* A, const ecw_tensor* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (beta != 0.0) ck(cudaMemcpyAsync(c->ptr[S_SCAL] + 1, out_dev, sizeof(double), cudaMemcpyDeviceToDevice, st), "dot in");
     Tensor a = from_desc(A, S_A0), b = from_desc(B, S_A1);
-    Tensor ad = P.tmpv(std::vector<int64_t>(a.dim, a.dim + a.nd)), bd = P.tmpv(std::vector<int64_t>(b.dim, b.dim + b.nd));
-    P.axpby(1.0, a, 0.0, ad);
-    P.axpby(1.0, b, 0.0, bd);
+    auto packed = [](const Tensor& t) {                      // row-major without gaps: read in place
+      int64_t want = 1;
+      for (int i = t.nd - 1; i >= 0; --i) {
+        if (t.dim[i] != 1 && t.str[i] != want) return false;
+        want *= t.dim[i];
+      }
+      return true;
+    };
+    Tensor ad = a, bd = b;
+    if (!packed(a)) { ad = P.tmpv(std::vector<int64_t>(a.dim, a.dim + a.nd)); P.axpby(1.0, a, 0.0, ad); }
+    if (!packed(b)) { bd = P.tmpv(std::vector<int64_t>(b.dim, b.dim + b.nd)); P.axpby(1.0, b, 0.0, bd); }
     P.dot(alpha, ad, bd, beta, 1);
     c->op_plan = std::move(P);
     int rc = run_op_plan(c, c->op_plan, 0.0, stream);

@@ -17,6 +17,10 @@ from .make_golden_solver import target_rdm1
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 H2O = [(8, (0., 0., 0.)), (1, (0., -0.757, 0.587)), (1, (0., 0.757, 0.587))]          # Main.py:104-109
 CASES = [("L0", 0.0, None, 60), ("L05", 0.05, None, 60), ("L05_a", 0.05, 2e-4, 12)]
+# DIIS-accelerated runs of the same solver (tag, L, alpha, maxiter, diis, maxdiis); pyscf.lib.diis comes from
+# oracle/pyscf_stub (restated published algorithm — "parity unpinned" against PySCF itself)
+DIIS_CASES = [("L0_dtl", 0.0, None, 60, "tl", 15), ("L05_dtl", 0.05, None, 60, "tl", 4),
+              ("L05_drdm1", 0.05, None, 60, "rdm1", 15), ("L05_a_dboth", 0.05, 2e-4, 12, ("tl", "rdm1"), 6)]
 
 
 def main():
@@ -27,11 +31,11 @@ def main():
     er = molint.geris(mol, scf)
     o, v = er.nocc, er.fock.shape[0] - er.nocc
     out = {"nocc": o, "nvir": v, "EHF": scf[0], "mo_energy": scf[1], "mo_coeff": scf[2], "conv_thres": 1e-9}
-    for tag, L, alpha, maxiter in CASES:
+    for tag, L, alpha, maxiter, diis, maxdiis in [c + ("", 15) for c in CASES] + DIIS_CASES:
         mycc = CCSD.GCC(er)
         vx = exp_pot.Exp(L, [[["mat", target_rdm1(o, v)]]], None, None)
-        text, ep, delta, conv, rdm1, amps = Solver_GS.Solver_CCSD(mycc, vx, conv="tl", conv_thres=1e-9, maxiter=maxiter).SCF(
-            L, alpha=alpha)
+        text, ep, delta, conv, rdm1, amps = Solver_GS.Solver_CCSD(mycc, vx, conv="tl", conv_thres=1e-9, maxiter=maxiter,
+                                                                  maxdiis=maxdiis).SCF(L, alpha=alpha, diis=diis)
         print("H2O/6-31G %s: %s | E_corr %.10f | Delta %.6f" % (tag, text, ep[-1], delta[-1][0]))
         out[tag + "_text"] = np.array(text)
         out[tag + "_Ep"], out[tag + "_Delta"], out[tag + "_conv"], out[tag + "_rdm1"] = ep, delta, conv, rdm1
