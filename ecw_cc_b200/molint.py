@@ -60,6 +60,45 @@ class Molecule(object):
         rr = np.sqrt((d ** 2).sum(-1))
         iu = np.triu_indices(len(self.Z), 1)
         self.e_nuc = float((self.Z[:, None] * self.Z[None, :])[iu].dot(1.0 / rr[iu]))
+        self._origin = np.zeros(3)
+        self._ints = None
+
+
+    # -- the slice of PySCF's `gto.Mole` surface that exp_pot.Exp / utilities touch (exp_pot.py:90-108) ---------------
+    def atom_charges(self):
+        return self.Z.copy()
+
+    def atom_coords(self):
+        return self.R.copy()                                      # Bohr, like PySCF
+
+    def with_common_orig(self, origin):
+        mol = self
+
+        class _Origin(object):
+            def __enter__(self_inner):
+                self_inner.old = mol._origin
+                mol._origin = np.asarray(origin, dtype=np.float64)
+                return mol
+
+            def __exit__(self_inner, *exc):
+                mol._origin = self_inner.old
+                return False
+        return _Origin()
+
+    def intor_symmetric(self, name, comp=None):
+        if self._ints is None:
+            self._ints = integrals(self)
+        if name == "int1e_kin":
+            return self._ints[1]
+        if name == "int1e_nuc":
+            return self._ints[2]
+        if name == "int1e_ovlp":
+            return self._ints[0]
+        if name == "int1e_r":
+            return dipole_integrals(self, self._origin)
+        raise NotImplementedError("intor %r" % (name,))
+
+    intor = intor_symmetric
 
 
 def _boys(nmax, x):
@@ -191,6 +230,40 @@ def integrals(mol):
     return S, T, V, eri.reshape(nao, nao, nao, nao)
 
 
+def dipole_integrals(mol, origin=(0., 0., 0.)):
+    """<mu| r - origin |nu>, [3, nao, nao] (the 'int1e_r' integrals the reference takes from PySCF with
+    `mol.with_common_orig`, exp_pot.py:90-98): 1-D first moments (E_1 + (P - C) E_0) sqrt(pi/p) times the overlaps of
+    the other two directions."""
+    npr = len(mol.ex)
+    I, J = np.meshgrid(np.arange(npr), np.arange(npr), indexing="ij")
+    I, J = I.ravel(), J.ravel()
+    a, b = mol.ex[I], mol.ex[J]
+    p = a + b
+    mu = a * b / p
+    A, B = mol.cen[I], mol.cen[J]
+    P = (a[:, None] * A + b[:, None] * B) / p[:, None]
+    la, lb = mol.lmn[I], mol.lmn[J]
+    cc = mol.coef[I] * mol.coef[J]
+    origin = np.asarray(origin, dtype=np.float64)
+    S1, M1 = [], []
+    for d in range(3):
+        E = _hermite_E(1, 1, p, P[:, d] - A[:, d], P[:, d] - B[:, d], mu, A[:, d] - B[:, d])
+        e0, e1 = np.zeros(len(p)), np.zeros(len(p))
+        for i in (0, 1):
+            for j in (0, 1):
+                m = (la[:, d] == i) & (lb[:, d] == j)
+                e0[m], e1[m] = E[i][j][0][m], E[i][j][1][m]
+        S1.append(e0 * np.sqrt(np.pi / p))
+        M1.append((e1 + (P[:, d] - origin[d]) * e0) * np.sqrt(np.pi / p))
+    nao = mol.nao
+    pair_ao = mol.ao[I] * nao + mol.ao[J]
+    out = np.zeros((3, nao * nao))
+    for d in range(3):
+        f = [M1[k] if k == d else S1[k] for k in range(3)]
+        np.add.at(out[d], pair_ao, cc * f[0] * f[1] * f[2])
+    return out.reshape(3, nao, nao)
+
+
 def rhf(mol, ints=None, conv=1e-11, maxiter=100):
     """Closed-shell SCF with DIIS.  Returns (E_HF, mo_energy, mo_coeff, ints)."""
     S, T, V, eri = ints if ints is not None else integrals(mol)
@@ -259,6 +332,10 @@ class geris(object):
         self.mo_occ = np.concatenate([np.ones(o), np.zeros(n - o)])
         self.orbspin = spin
         self.mo_coeff = C
+        nao = C.shape[0]
+        self.mo_coeff_g = np.zeros((2 * nao, n))                 # G format: [[C, 0], [0, C]] with interleaved columns,
+        self.mo_coeff_g[:nao, 0::2] = C                           # what scf.addons.convert_to_ghf(mf).mo_coeff holds
+        self.mo_coeff_g[nao:, 1::2] = C
         self.EHF = self.e_hf = ehf
         sl = {"o": slice(0, o), "v": slice(o, n)}
         for name in ("oooo", "ooov", "oovv", "ovov", "ovvo", "ovvv", "vvvv", "vooo", "vovo", "oovo", "vovv", "vvoo", "vvvo",
