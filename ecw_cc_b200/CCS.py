@@ -535,7 +535,12 @@ class Gccs(object):
         d_t, d_l = ops.to_dev(t1), ops.to_dev(l1)
         foo, fov, fvo, fvv = self._f(self.fock if fsp is None else fsp)
         G = self._G(d_t)
-        d = En - 0.5 * ops.dot(d_t, G)
+        shift = 0.5 * ops.dot(d_t, G)
+        if isinstance(En, np.ndarray):                     # Q12: `d = En; d -= ...` (CCS.py:1488-1490) changes the
+            En -= shift                                    # caller's energy array — Solver_ES records it AFTER this call
+            d = En
+        else:
+            d = En - shift
         l0 = ops.dot(d_l, fov)
         l0 += ops.dot(ops.contract('jb,ab->ja', d_t, fvv), d_l)                              # 'jb,ab,ja'
         l0 -= ops.dot(ops.contract('jb,kb->kj', d_l, d_t), foo)                              # 'jb,kb,kj'

@@ -388,7 +388,8 @@ class OracleGccs(object):
             vov, voo = v0m[:no, no:], v0m[:no, :no]
         else:
             vov, voo = np.zeros((no, nv)), np.zeros((no, no))
-        d = En - 0.5 * _e('jb,kc,jkbc', t1, t1, er.oovv)
+        d = En                                                 # Q12: in place when En is an array (CCS.py:1488-1490)
+        d -= 0.5 * _e('jb,kc,jkbc', t1, t1, er.oovv)
         l0 = _e('jb,jb', l1, fov) + _e('jb,ab,ja', t1, fvv, l1) - _e('jb,kb,kj', l1, t1, foo)
         l0 -= _e('jc,kb,kc,jb', t1, t1, fov, l1)
         l0 += _e('jb,kc,kbcj', l1, t1, er.ovvo)

@@ -1,0 +1,46 @@
+"""The ECW-CCS solver loops over the CUDA `Gccs` on H2O/6-31G — `ecw_cc_b200.Solver_CCS` (ground state) and
+`ecw_cc_b200.Solver_ES` (ground + excited states with transition-dipole / state-property potentials; config 3 of
+BASELINE.json in the 6-31G basis) with `ecw_cc_b200.exp_pot.Exp` — against runs of the UNMODIFIED reference solvers,
+`CCS.Gccs` and `exp_pot.Exp` on the same integrals (tests/golden/ccs_solvers_h2o.npz): same texts and iteration counts,
+energies / Delta / rdm1 / t, l, r_n, l_n, r0, l0 to 1e-10."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle.make_golden_ccs_solvers import run_es, run_gs, water
+from test_ccs_solvers_cpu import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ccs_ground_state_solver(built_lib, engine):
+    import ecw_cc_b200 as ecw
+    mol, er = water()
+    worst = compare(run_gs(ecw.Solver_CCS, ecw.Gccs, ecw.exp_pot.Exp, er), load_golden("ccs_solvers_h2o.npz"), "gs_")
+    print("CCS GS solver, engine %s: max deviation %.2e" % (engine, worst))
+
+
+def test_ccs_excited_state_solver(built_lib, engine):
+    import ecw_cc_b200 as ecw
+    mol, er = water()
+    out = run_es(ecw.Solver_ES, ecw.Gccs, ecw.exp_pot.Exp, ecw.utilities.koopman_init_guess, mol, er)
+    worst = compare(out, load_golden("ccs_solvers_h2o.npz"), "es_")
+    print("CCS ES solver, engine %s: max deviation %.2e" % (engine, worst))
+
+
+def test_l0_fromE_changes_its_energy_argument(built_lib):
+    """Q12 (CCS.py:1488-1490): `d = En; d -= ...` — an ndarray energy comes back lowered by 1/2 t1 t1 <jk||bc>;
+    Solver_ES stores the left excitation energy after that call."""
+    import ecw_cc_b200 as ecw
+    from oracle.ccs_np import OracleGccs
+    mol, er = water()
+    rng = np.random.default_rng(3)
+    ts, ls = 0.05 * rng.standard_normal((10, 16)), 0.05 * rng.standard_normal((10, 16))
+    vm = 0.01 * rng.standard_normal((26, 26))
+    res = []
+    for cc in (ecw.Gccs(er), OracleGccs(er)):
+        en = np.array([0.3])
+        l0 = cc.l0_fromE(en, ts, ls, vm)
+        res.append((float(en[0]), float(np.ravel(l0)[0]), float(cc.l0_fromE(0.3, ts, ls, vm))))
+    assert res[0][0] != 0.3 and np.abs(np.subtract(res[0], res[1])).max() < 1e-12
+    assert abs(res[0][1] - res[0][2]) < 1e-14

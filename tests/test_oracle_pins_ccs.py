@@ -54,3 +54,21 @@ def test_ccs_oracle_matches_live_reference():
     b = ccs_calls(ccs_np.OracleGccs(er), _MOD, d)
     for k in a:
         assert np.abs(a[k] - b[k]).max() < TOL, k
+
+
+def test_l0_fromE_energy_argument_quirk():
+    """Q12 (CCS.py:1488-1490): l0_fromE lowers an ndarray energy argument in place by 1/2 t1 t1 <jk||bc>."""
+    from oracle import synth
+    from oracle.ccs_np import OracleGccs
+    o, v = 4, 6
+    er = synth.SynthEris(o, v)
+    rng = np.random.default_rng(2)
+    ts, ls = 0.1 * rng.standard_normal((o, v)), 0.1 * rng.standard_normal((o, v))
+    objs = [OracleGccs(er)]
+    if ref_loader.available():
+        objs.append(ref_loader.load("CCS").Gccs(er))
+    shift = 0.5 * np.einsum('jb,kc,jkbc', ts, ts, er.oovv)
+    for cc in objs:
+        en = np.array([0.3])
+        l0 = cc.l0_fromE(en, ts, ls, None)
+        assert abs(en[0] - (0.3 - shift)) < 1e-15 and abs(float(np.ravel(l0)[0]) - float(cc.l0_fromE(0.3, ts, ls, None))) < 1e-14
