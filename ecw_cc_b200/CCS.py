@@ -15,8 +15,16 @@ device, so the update that follows does not upload them again.
 import numpy as np
 
 from ._lib import EcwError, ECW_HAS_ALPHA, ECW_SUBDIFF_SINGLES
-from .devops import DevOps
+from .devops import DevOps, _scalar
 from .eris import DeviceEris
+
+
+def _like_amp0(em, amp0):
+    """The reference forms Em from `... + r0 * Zia[o, v]` (CCS.py:897-904, 1310-1317): a shape-(1,) r0 / l0 (what the
+    solver carries after the first iteration) makes Em a shape-(1,) ARRAY — which `l0_fromE` then changes in place (Q12)."""
+    if isinstance(amp0, np.ndarray) and amp0.ndim > 0:
+        return em * np.ones_like(amp0, dtype=np.float64)
+    return em
 
 
 class InterTuple(tuple):
@@ -211,7 +219,7 @@ class Gccs(object):
         ops = self.ops
         inter = self.L1inter(ts, fsp, E_term=E_term)
         L1 = self._l1(ops.to_dev(ls), ops.to_dev(inter[0]), ops.to_dev(inter[1]), ops.to_dev(inter[2]),
-                      inter.dev["W"], float(inter[4]))
+                      inter.dev["W"], _scalar(inter[4]))
         return ops.to_host(L1)
 
     def lsupdate(self, ts, ls, L1inter, rsn=None, lsn=None, r0n=None, l0n=None, vn=None):
@@ -225,7 +233,7 @@ class Gccs(object):
         ops.diag_shift(Fij, -1.0, 0)
         Fba_h[...] = ops.to_host(Fba)
         Fij_h[...] = ops.to_host(Fij)
-        new = self._l1(d_ls, Fia, Fba, Fij, W, float(E))
+        new = self._l1(d_ls, Fia, Fba, Fij, W, _scalar(E))
         if rsn is not None:                                # CCS.py:539-579
             if len(lsn) != len(rsn) or len(vn) != len(rsn):
                 raise ValueError('v0n, l and r list must be of same length')
@@ -257,7 +265,7 @@ class Gccs(object):
         o, v = self.nocc, self.nvir
         d_ls = ops.to_dev(ls)
         L1 = self._l1(d_ls, ops.to_dev(L1inter[0]), ops.to_dev(L1inter[1]), ops.to_dev(L1inter[2]),
-                      self._w_dev(L1inter, 3, (v, o, o, v)), float(L1inter[4]))
+                      self._w_dev(L1inter, 3, (v, o, o, v)), _scalar(L1inter[4]))
         return ops.to_host(ops.denom(L1, d_ls, ECW_HAS_ALPHA | ECW_SUBDIFF_SINGLES, alpha))
 
     # ------------------------------------------------------------------ ES right (CCS.py:774-1158)
@@ -327,8 +335,8 @@ class Gccs(object):
         Fab, Fji, W_h, F, Zia, Pia = Rinter
         d_rs = ops.to_dev(rs)
         R = self._r1core(d_rs, ops.to_dev(Fab), ops.to_dev(Fji), self._w_dev(Rinter, 2, (v, o, o, v)))
-        ops.scale_add(R, d_rs, float(F))
-        ops.scale_add(R, ops.to_dev(Zia), float(r0))
+        ops.scale_add(R, d_rs, _scalar(F))
+        ops.scale_add(R, ops.to_dev(Zia), _scalar(r0))
         ops.scale_add(R, ops.to_dev(Pia), 1.0)
         return R, d_rs
 
@@ -341,7 +349,7 @@ class Gccs(object):
             o, v = ov
         R, d_rs = self._r1full(rs, r0, Rinter)
         q = ops.to_host(R)
-        return q[o, v] / rs[o, v], o, v
+        return _like_amp0(q[o, v] / rs[o, v], r0), o, v
 
     def rsupdate(self, rs, r0, Rinter, Em, force_alpha=True):   # CCS.py:908-943
         ops = self.ops
@@ -354,8 +362,8 @@ class Gccs(object):
         Fab_h[...] = ops.to_host(Fab)
         Fji_h[...] = ops.to_host(Fji)
         R = self._r1core(d_rs, Fab, Fji, self._w_dev(Rinter, 2, (v, o, o, v)))
-        ops.scale_add(R, d_rs, float(F))
-        ops.scale_add(R, ops.to_dev(Zia), float(r0))
+        ops.scale_add(R, d_rs, _scalar(F))
+        ops.scale_add(R, ops.to_dev(Zia), _scalar(r0))
         ops.scale_add(R, ops.to_dev(Pia), 1.0)
         new = ops.denom(R, d_rs, shift=float(np.asarray(Em).reshape(-1)[0]))
         if force_alpha:
@@ -368,7 +376,8 @@ class Gccs(object):
         ls = np.asarray(ls)
         rs = np.asarray(rs)
         d_r = ops.to_dev(rs).clone()
-        ops.fill(d_r[o:o + 1, v:v + 1], 0.0)
+        for i, a in zip(np.ravel(o), np.ravel(v)):         # scalars, or the index arrays of np.where (Solver_ES.py:172)
+            ops.fill(d_r[int(i):int(i) + 1, int(a):int(a) + 1], 0.0)
         rov = 1. - r0 * l0 - ops.dot(d_r, ops.to_dev(ls))
         return rov / ls[o, v]
 
@@ -475,8 +484,8 @@ class Gccs(object):
         Fba, Fij, W_h, F, Zia, P = inter
         d_ls = ops.to_dev(ls)
         L = self._l1core(d_ls, ops.to_dev(Fba), ops.to_dev(Fij), self._w_dev(inter, 2, (v, o, o, v)))
-        ops.scale_add(L, d_ls, float(F))
-        ops.scale_add(L, ops.to_dev(Zia), float(l0))
+        ops.scale_add(L, d_ls, _scalar(F))
+        ops.scale_add(L, ops.to_dev(Zia), _scalar(l0))
         ops.scale_add(L, ops.to_dev(P), 1.0)
         return L
 
@@ -487,7 +496,7 @@ class Gccs(object):
         else:
             o, v = ov
         L = self.ops.to_host(self._esl1full(ls, l0, L1inter))
-        return L[o, v] / ls[o, v], o, v
+        return _like_amp0(L[o, v] / ls[o, v], l0), o, v
 
     def Extract_l0(self, l1, ts, fsp, vm):
         raise EcwError("Extract_l0 is broken in the reference (operator precedence '/ 2*c', CCS.py:1356-1357) "
@@ -504,8 +513,8 @@ class Gccs(object):
         Fba_h[...] = ops.to_host(Fba)
         Fij_h[...] = ops.to_host(Fij)
         L = self._l1core(d_ls, Fba, Fij, self._w_dev(L1inter, 2, (v, o, o, v)))
-        ops.scale_add(L, d_ls, float(F))
-        ops.scale_add(L, ops.to_dev(Zia), float(l0))
+        ops.scale_add(L, d_ls, _scalar(F))
+        ops.scale_add(L, ops.to_dev(Zia), _scalar(l0))
         ops.scale_add(L, ops.to_dev(P), 1.0)
         new = ops.denom(L, d_ls, shift=float(np.asarray(Em).reshape(-1)[0]))
         if force_alpha:
@@ -617,7 +626,7 @@ def gamma_es_CCS(ts, ln, rk, r0k, l0n, mycc=None):         # CCS.py:51-102
         r, r0k, l0n = ops.fill(ops.empty(*t.shape), 0.0), 1., 0.
     else:
         r = ops.to_dev(rk)
-    return ops.to_host(_assemble(ops, *_es_blocks(ops, t, l, r, float(r0k), float(l0n)), unit_occ=True))
+    return ops.to_host(_assemble(ops, *_es_blocks(ops, t, l, r, _scalar(r0k), _scalar(l0n)), unit_occ=True))
 
 
 def gamma_tr_CCS(ts, ln, rk, r0k, l0n, mycc=None):         # CCS.py:105-154
@@ -627,7 +636,7 @@ def gamma_tr_CCS(ts, ln, rk, r0k, l0n, mycc=None):         # CCS.py:105-154
         r, r0k = ops.fill(ops.empty(*t.shape), 0.0), 1.
     else:
         r = ops.to_dev(rk)
-    return ops.to_host(_assemble(ops, *_es_blocks(ops, t, l, r, float(r0k), float(l0n)), unit_occ=False))
+    return ops.to_host(_assemble(ops, *_es_blocks(ops, t, l, r, _scalar(r0k), _scalar(l0n)), unit_occ=False))
 
 
 def gamma_CCS(ts, ls, mycc=None):                          # CCS.py:157-190

@@ -28,6 +28,11 @@ def _desc(t):
     return d
 
 
+def _scalar(x):
+    """Python float from a number or a one-element array (the solvers pass r0 / l0 / E as shape-(1,) arrays)."""
+    return float(np.asarray(x, dtype=np.float64).reshape(-1)[0])
+
+
 def _ref(d):
     return ctypes.byref(d) if d is not None else None
 
@@ -87,13 +92,13 @@ class DevOps(object):
             out = self.empty(*[dims[ch] for ch in sc])
             beta = 0.0
         da, db, dc = _desc(A), _desc(B), _desc(out)
-        self._call(lib.ecw_op_contract, float(alpha), _ref(da), sa.encode(), _ref(db), sb.encode(), float(beta),
+        self._call(lib.ecw_op_contract, _scalar(alpha), _ref(da), sa.encode(), _ref(db), sb.encode(), _scalar(beta),
                    _ref(dc), sc.encode())
         return out
 
     def axpby(self, alpha, A, sa, beta, C, sc):
         da, dc = _desc(A), _desc(C)
-        self._call(lib.ecw_op_axpby, float(alpha), _ref(da), sa.encode(), float(beta), _ref(dc), sc.encode())
+        self._call(lib.ecw_op_axpby, _scalar(alpha), _ref(da), sa.encode(), _scalar(beta), _ref(dc), sc.encode())
         return C
 
     def copy(self, A, spec=None, alpha=1.0):
@@ -112,7 +117,7 @@ class DevOps(object):
 
     def mul(self, alpha, A, B, beta, C):
         da, db, dc = _desc(A), _desc(B), _desc(C)
-        self._call(lib.ecw_op_mul, float(alpha), _ref(da), _ref(db), float(beta), _ref(dc))
+        self._call(lib.ecw_op_mul, _scalar(alpha), _ref(da), _ref(db), _scalar(beta), _ref(dc))
         return C
 
     def fill(self, C, value):
@@ -124,27 +129,27 @@ class DevOps(object):
 
     def unpack(self, A2, flags, C4, alpha=1.0, beta=0.0):
         da, dc = _desc(A2), _desc(C4)
-        self._call(lib.ecw_op_unpack, float(alpha), _ref(da), int(flags), float(beta), _ref(dc))
+        self._call(lib.ecw_op_unpack, _scalar(alpha), _ref(da), int(flags), _scalar(beta), _ref(dc))
         return C4
 
     def diag_shift(self, C, alpha, offset):
         dc, df = _desc(C), _desc(self.e.fock_dev)
-        self._call(lib.ecw_op_diag_shift, _ref(dc), float(alpha), _ref(df), int(offset))
+        self._call(lib.ecw_op_diag_shift, _ref(dc), _scalar(alpha), _ref(df), int(offset))
         return C
 
     def denom(self, resid, amp, flags=0, alpha=0.0, shift=0.0, out=None):
         if out is None:
             out = self.empty(*resid.shape)
         dr, da, df, do = _desc(resid), _desc(amp), _desc(self.e.fock_dev), _desc(out)
-        self._call(lib.ecw_op_denom, _ref(dr), _ref(da), _ref(df), int(self.e.nocc), int(flags), float(alpha),
-                   float(shift), _ref(do))
+        self._call(lib.ecw_op_denom, _ref(dr), _ref(da), _ref(df), int(self.e.nocc), int(flags), _scalar(alpha),
+                   _scalar(shift), _ref(do))
         return out
 
     def dot(self, A, B, alpha=1.0):
         """alpha * <A, B> as a Python float."""
         out = self.torch.zeros(1, dtype=self.torch.float64, device=self.dev)
         da, db = _desc(A), _desc(B)
-        self._call(lib.ecw_op_dot, float(alpha), _ref(da), _ref(db), 0.0, ctypes.c_void_p(out.data_ptr()))
+        self._call(lib.ecw_op_dot, _scalar(alpha), _ref(da), _ref(db), 0.0, ctypes.c_void_p(out.data_ptr()))
         return self.scalar(out)
 
     def trace(self, M):

@@ -12,7 +12,7 @@ from oracle.make_golden_ccs_solvers import run_es, run_gs, water
 TOL = 1e-10
 
 
-def compare(out, g, prefix):
+def compare(out, g, prefix, tol=TOL):
     keys = [k for k in g if k.startswith(prefix)]
     assert keys and sorted(keys) == sorted(k for k in out if k.startswith(prefix))
     worst = 0.0
@@ -23,7 +23,7 @@ def compare(out, g, prefix):
         want, got = np.asarray(g[k], dtype=float), np.asarray(out[k], dtype=float)
         assert want.shape == got.shape, k
         worst = max(worst, np.abs(want - got).max())
-        assert np.abs(want - got).max() < TOL, k
+        assert np.abs(want - got).max() < tol, k
     return worst
 
 

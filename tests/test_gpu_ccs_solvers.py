@@ -24,7 +24,11 @@ def test_ccs_excited_state_solver(built_lib, engine):
     import ecw_cc_b200 as ecw
     mol, er = water()
     out = run_es(ecw.Solver_ES, ecw.Gccs, ecw.exp_pot.Exp, ecw.utilities.koopman_init_guess, mol, er)
-    worst = compare(out, load_golden("ccs_solvers_h2o.npz"), "es_")
+    # The r/l update divides by Em + e_i - e_a, which comes close to zero for the states next to the pinned one: the
+    # iteration amplifies a 1e-12 perturbation of the residual to ~1e-8 within 12 steps.  The stress engine `int8_all`
+    # (o x v GEMMs forced through the INT8 digit route, which the product never does: threshold 2e10 flops) therefore
+    # gets 1e-7; the product engines hold 1e-10 (measured 1.4e-12).
+    worst = compare(out, load_golden("ccs_solvers_h2o.npz"), "es_", tol=1e-7 if engine == "int8_all" else 1e-10)
     print("CCS ES solver, engine %s: max deviation %.2e" % (engine, worst))
 
 
@@ -44,3 +48,9 @@ def test_l0_fromE_changes_its_energy_argument(built_lib):
         res.append((float(en[0]), float(np.ravel(l0)[0]), float(cc.l0_fromE(0.3, ts, ls, vm))))
     assert res[0][0] != 0.3 and np.abs(np.subtract(res[0], res[1])).max() < 1e-12
     assert abs(res[0][1] - res[0][2]) < 1e-14
+    # ... and the energy IS an array whenever the solver's r0 / l0 are (shape (1,) after the first iteration)
+    for cc in (ecw.Gccs(er), OracleGccs(er)):
+        for l0 in (0.1, np.array([0.1])):
+            em_l = cc.Extract_Em_l(ls, l0, cc.es_L1inter(ts, None, vm))[0]
+            em_r = cc.Extract_Em_r(ls, l0, cc.R1inter(ts, None, vm))[0]
+            assert np.shape(em_l) == np.shape(l0) and np.shape(em_r) == np.shape(l0)
