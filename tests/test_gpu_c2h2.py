@@ -1,0 +1,39 @@
+"""Config 2 of BASELINE.json in the 6-31G basis on the GPU: C2H2 L1-ECW-CCSD ground state over a sweep of the Vexp
+weight L, driven like `Main.ECW.CCSD_GS` (Main.py:730-763: one solver, previous amplitudes as the next start — here
+they stay on the device between L values), against the UNMODIFIED reference solver / CCSD.GCC / exp_pot.Exp with HF
+reference values on the same integrals (tests/golden/c2h2_631g_sweep.npz, oracle/make_golden_c2h2.py).
+(o, v) = (14, 30); 4 L values x 26 iterations, with and without the L1 term."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle.make_golden_c2h2 import LARRAY, SWEEPS, acetylene, pack, sweep
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def c2h2():
+    g = load_golden("c2h2_631g_sweep.npz")
+    mol, er, _ = acetylene((float(g["EHF"]), g["mo_energy"], g["mo_coeff"]))
+    return g, er
+
+
+@pytest.mark.parametrize("tag,alpha", SWEEPS)
+def test_weight_sweep_matches_reference(built_lib, engine, c2h2, tag, alpha):
+    import ecw_cc_b200 as ecw
+    g, er = c2h2
+    assert (er.nocc, er.fock.shape[0] - er.nocc) == (14, 30)
+    out = {}
+    pack(sweep(ecw.Solver_CCSD, ecw.GCC, ecw.exp_pot.Exp, er, alpha, device=True), tag, out)
+    worst = 0.0
+    for k, want in ((k, g[k]) for k in g if k.startswith(tag + "_")):
+        if k.endswith("_text"):
+            assert str(out[k]) == str(want), k
+            continue
+        dev = np.abs(np.asarray(out[k], dtype=float) - np.asarray(want, dtype=float)).max()
+        worst = max(worst, dev)
+        assert dev < TOL, (k, dev)
+    assert len(LARRAY) == 4 and g[tag + "_L3_Delta"][-1][0] < g[tag + "_L0_Delta"][-1][0]      # the fit tightens with L
+    print("C2H2 sweep %s, engine %s: max deviation %.2e" % (tag, engine, worst))

@@ -60,3 +60,13 @@ def test_config1_oracle_reproduces_reference_runs(water):
                    maxiter=maxiter)
     assert out[0] == str(g[tag + "_text"])
     assert np.abs(out[1] - g[tag + "_Ep"]).max() < 1e-11 and np.abs(out[4] - g[tag + "_rdm1"]).max() < 1e-10
+
+
+def test_acetylene_rhf_is_reproducible():
+    """C2H2/6-31G (config 2 in the 6-31G basis): the RHF solution stored with the sweep fixture is what molint gives."""
+    from oracle.make_golden_c2h2 import acetylene
+    g = load_golden("c2h2_631g_sweep.npz")
+    mol, er, scf = acetylene()
+    assert mol.nao == 22 and (er.nocc, er.fock.shape[0]) == (14, 44)
+    assert abs(scf[0] - float(g["EHF"])) < 1e-9 and abs(scf[0] - (-76.79224)) < 1e-4
+    assert np.abs(scf[1] - g["mo_energy"]).max() < 1e-7
