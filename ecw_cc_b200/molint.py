@@ -1,10 +1,12 @@
-"""Integral source without PySCF: Gaussian one- and two-electron integrals over s and p shells
-(McMurchie-Davidson), restricted Hartree-Fock, and the spin-orbital antisymmetrised MO integrals of the reference's
+"""Integral source without PySCF: Gaussian one- and two-electron integrals over s, p and (spherical) d
+shells (McMurchie-Davidson), restricted Hartree-Fock, and the spin-orbital antisymmetrised MO integrals of the reference's
 `Eris.geris` container (Eris.py:24-154: `<pq||rs> = <pq|rs> - <pq|sr>`, blocks `oooo ... vvvv`, `fock = diag(mo_energy)`),
 built the way `Main.ECW.__init__` does (Main.py:151-217: RHF -> GHF spin orbitals in `[a, b, a, b, ...]` order).
 
 Host-side numpy on purpose: this is the producer of the path's inputs (a 13-function basis for config 1, H2O/6-31G),
-not the path.  Basis sets embedded: 6-31G for H, C, N, O.  Anchor: E_HF(H2O/6-31G) = -75.9839 (ECW_CC/__init__.py:39).
+not the path.  Basis sets embedded for H, C, N, O: the 6-31G family — 6-31G, 6-31G*, 6-31G**, 6-31+G*, 6-31++G** ...
+(Pople's standard polarisation / diffuse exponents; five spherical d functions per shell, PySCF's default) — and
+cc-pVDZ for H, C, O.  Anchor: E_HF(H2O/6-31G) = -75.9839 (ECW_CC/__init__.py:39).
 """
 import numpy as np
 from scipy.special import hyp1f1
@@ -30,13 +32,74 @@ BASIS_631G = {
 }
 
 
+# polarisation / diffuse functions of the 6-31G family: d exponent ('*'), diffuse sp exponent ('+') of the heavy atoms,
+# p exponent ('**') and diffuse s exponent ('++') of hydrogen
+POPLE_D = {6: 0.8, 7: 0.8, 8: 0.8}
+POPLE_DIFFUSE_SP = {6: 0.0438, 7: 0.0639, 8: 0.0845}
+POPLE_H_P, POPLE_H_DIFFUSE_S = 1.1, 0.036
+
+# cc-pVDZ (Dunning 1989): general contractions written out per contracted function
+BASIS_CCPVDZ = {
+    1: [("S", [13.01, 1.962, 0.4446], [0.019685, 0.137977, 0.478148], None),
+        ("S", [0.122], [1.0], None),
+        ("P", [0.727], None, [1.0])],
+    6: [("S", [6665.0, 1000.0, 228.0, 64.71, 21.06, 7.495, 2.797, 0.5215],
+         [0.000692, 0.005329, 0.027077, 0.101718, 0.27474, 0.448564, 0.285074, 0.015204], None),
+        ("S", [6665.0, 1000.0, 228.0, 64.71, 21.06, 7.495, 2.797, 0.5215],
+         [-0.000146, -0.001154, -0.005725, -0.023312, -0.063955, -0.149981, -0.127262, 0.544529], None),
+        ("S", [0.1596], [1.0], None),
+        ("P", [9.439, 2.002, 0.5456], None, [0.038109, 0.20948, 0.508557]),
+        ("P", [0.1517], None, [1.0]),
+        ("D", [0.55], None, [1.0])],
+    8: [("S", [11720.0, 1759.0, 400.8, 113.7, 37.03, 13.27, 5.025, 1.013],
+         [0.00071, 0.00547, 0.027837, 0.1048, 0.283062, 0.448719, 0.270952, 0.015458], None),
+        ("S", [11720.0, 1759.0, 400.8, 113.7, 37.03, 13.27, 5.025, 1.013],
+         [-0.00016, -0.001263, -0.006267, -0.025716, -0.070924, -0.165411, -0.116955, 0.557368], None),
+        ("S", [0.3023], [1.0], None),
+        ("P", [17.7, 3.854, 1.046], None, [0.043018, 0.228913, 0.508728]),
+        ("P", [0.2753], None, [1.0]),
+        ("D", [1.185], None, [1.0])],
+}
+
+# real solid harmonics of a d shell over Cartesian monomials, in PySCF's order (xy, yz, z2, xz, x2-y2); factors are
+# relative to the norm of an xy-type Gaussian, N = (2a/pi)^(3/4) * 4a
+_S3 = 1.0 / (2.0 * np.sqrt(3.0))
+D_SPHERICAL = [[((1, 1, 0), 1.0)], [((0, 1, 1), 1.0)], [((0, 0, 2), 2 * _S3), ((2, 0, 0), -_S3), ((0, 2, 0), -_S3)],
+               [((1, 0, 1), 1.0)], [((2, 0, 0), 0.5), ((0, 2, 0), -0.5)]]
+
+
+def basis_shells(name, z):
+    """Shell list [(kind, exponents, s coefficients, p-or-d coefficients)] of element z in the named basis."""
+    key = name.lower().replace("-", "").replace("(d)", "*").replace("(d,p)", "**")
+    if key == "ccpvdz":
+        if z not in BASIS_CCPVDZ:
+            raise NotImplementedError("cc-pVDZ is embedded for H, C, O")
+        return BASIS_CCPVDZ[z]
+    import re
+    m = re.fullmatch(r"631(\+{0,2})g(\*{0,2})", key)
+    if m is None:
+        raise NotImplementedError("embedded basis sets: 6-31G family (6-31G, 6-31G*, 6-31+G*, 6-31++G**, ...) and cc-pVDZ")
+    plus, star = len(m.group(1)), len(m.group(2))
+    shells = list(BASIS_631G[z])
+    if z == 1:
+        if plus == 2:
+            shells.append(("S", [POPLE_H_DIFFUSE_S], [1.0], None))
+        if star == 2:
+            shells.append(("P", [POPLE_H_P], None, [1.0]))
+    else:
+        if plus >= 1:
+            shells.append(("SP", [POPLE_DIFFUSE_SP[z]], [1.0], [1.0]))
+        if star >= 1:
+            shells.append(("D", [POPLE_D[z]], None, [1.0]))
+    return shells
+
+
 class Molecule(object):
-    """atoms: [(Z or element symbol, (x, y, z)), ...] in Angstrom (Main.py:104-109 style); basis: '6-31g'."""
+    """atoms: [(Z or element symbol, (x, y, z)), ...] in Angstrom (Main.py:104-109 style); basis: '6-31g', '6-31+g*',
+    '6-31++g**', 'cc-pvdz', ... (see `basis_shells`)."""
     SYMBOLS = {"H": 1, "C": 6, "N": 7, "O": 8}
 
     def __init__(self, atoms, basis="6-31g", charge=0):
-        if basis.lower().replace("-", "") != "631g":
-            raise NotImplementedError("embedded basis sets: 6-31G (s and p shells)")
         self.Z = np.array([self.SYMBOLS[a[0].capitalize()] if isinstance(a[0], str) else a[0] for a in atoms], dtype=np.float64)
         self.R = np.array([a[1] for a in atoms], dtype=np.float64) * ANGSTROM
         self.nelec = int(self.Z.sum()) - charge
@@ -46,16 +109,28 @@ class Molecule(object):
         cen, ex, lmn, coef, ao = [], [], [], [], []
         nao = 0
         for z, r in zip(self.Z, self.R):
-            for kind, exps, cs, cp in BASIS_631G[int(z)]:
-                for ang, cc in ((0, cs),) + (((1, cp),) if kind == "SP" else ()):
-                    for l3 in ([(0, 0, 0)] if ang == 0 else [(1, 0, 0), (0, 1, 0), (0, 0, 1)]):
+            for kind, exps, cs, cp in basis_shells(basis, int(z)):
+                parts = {"S": ((0, cs),), "P": ((1, cp),), "SP": ((0, cs), (1, cp)), "D": ((2, cp),)}[kind]
+                for ang, cc in parts:
+                    if ang == 2:                               # five spherical d functions
+                        comps = D_SPHERICAL
+                    else:
+                        comps = [[((0, 0, 0), 1.0)]] if ang == 0 else [[(l3, 1.0)] for l3 in ((1, 0, 0), (0, 1, 0), (0, 0, 1))]
+                    for comp in comps:
                         for a, c in zip(exps, cc):
-                            norm = (2 * a / np.pi) ** 0.75 * (2 * np.sqrt(a)) ** ang      # primitive s / p norm
-                            cen.append(r); ex.append(a); lmn.append(l3); coef.append(c * norm); ao.append(nao)
+                            norm = (2 * a / np.pi) ** 0.75 * (2 * np.sqrt(a)) ** ang      # s / p / xy-type d norm
+                            for l3, f in comp:
+                                cen.append(r); ex.append(a); lmn.append(l3); coef.append(c * norm * f); ao.append(nao)
                         nao += 1
         self.cen, self.ex = np.array(cen), np.array(ex)
         self.lmn, self.coef, self.ao = np.array(lmn), np.array(coef), np.array(ao)
         self.nao = nao
+        self.lmax = int(self.lmn.sum(1).max())
+        # Tables of general contractions (cc-pVDZ) list contracted functions that are not unit normalised: rescale
+        # those.  Segmented Pople functions are normalised to ~1e-7 as published and are left exactly as tabulated.
+        sii = self._self_overlaps()
+        scale = np.where(np.abs(sii - 1.0) > 1e-4, 1.0 / np.sqrt(sii), 1.0)
+        self.coef = self.coef * scale[self.ao]
         d = self.R[:, None, :] - self.R[None, :, :]
         rr = np.sqrt((d ** 2).sum(-1))
         iu = np.triu_indices(len(self.Z), 1)
@@ -63,6 +138,25 @@ class Molecule(object):
         self._origin = np.zeros(3)
         self._ints = None
 
+
+    def _self_overlaps(self):
+        """<mu|mu> of every AO from its own primitives (all on one centre: products of 1-D Gaussian moments)."""
+        def dfact(n):                                             # (n-1)!! for even n >= 0
+            return float(np.prod(np.arange(n - 1, 0, -2))) if n > 0 else 1.0
+        out = np.zeros(self.nao)
+        for mu in range(self.nao):
+            k = np.where(self.ao == mu)[0]
+            for i in k:
+                for j in k:
+                    n3 = self.lmn[i] + self.lmn[j]
+                    if (n3 % 2).any():
+                        continue
+                    pq = self.ex[i] + self.ex[j]
+                    val = (np.pi / pq) ** 1.5
+                    for n in n3:
+                        val *= dfact(n) / (2 * pq) ** (n // 2)
+                    out[mu] += self.coef[i] * self.coef[j] * val
+        return out
 
     # -- the slice of PySCF's `gto.Mole` surface that exp_pot.Exp / utilities touch (exp_pot.py:90-108) ---------------
     def atom_charges(self):
@@ -147,11 +241,22 @@ def _hermite_R(L, alpha, D):
     return {(t, u, v): get(t, u, v, 0) for t in range(L + 1) for u in range(L + 1 - t) for v in range(L + 1 - t - u)}
 
 
+def _pairs(mol):
+    """Unique primitive pairs I >= J and the matrix that adds a pair quantity into the AO pairs (mu nu) and (nu mu)."""
+    I, J = np.tril_indices(len(mol.ex))
+    nao = mol.nao
+    M = np.zeros((len(I), nao * nao))
+    k = np.arange(len(I))
+    np.add.at(M, (k, mol.ao[I] * nao + mol.ao[J]), 1.0)
+    off = I != J
+    np.add.at(M, (k[off], mol.ao[J[off]] * nao + mol.ao[I[off]]), 1.0)
+    return I, J, M
+
+
 def integrals(mol):
-    """Overlap, kinetic, nuclear-attraction [nao, nao] and electron-repulsion (mu nu|la si) [nao]*4, AO basis."""
-    npr = len(mol.ex)
-    I, J = np.meshgrid(np.arange(npr), np.arange(npr), indexing="ij")
-    I, J = I.ravel(), J.ravel()
+    """Overlap, kinetic, nuclear-attraction [nao, nao] and electron-repulsion (mu nu|la si) [nao]*4, AO basis.
+    McMurchie-Davidson over the unique primitive pairs (I >= J) and the lower triangle of pair-pairs."""
+    I, J, M = _pairs(mol)
     a, b = mol.ex[I], mol.ex[J]
     p = a + b
     mu = a * b / p
@@ -159,14 +264,18 @@ def integrals(mol):
     P = (a[:, None] * A + b[:, None] * B) / p[:, None]
     la, lb = mol.lmn[I], mol.lmn[J]
     cc = mol.coef[I] * mol.coef[J]
+    lm = mol.lmax
+    nt = 2 * lm + 1                                               # Hermite orders 0..2*lmax per direction
     # 1-D coefficients with j up to l_b + 2 (kinetic energy)
-    Ed = [_hermite_E(1, 3, p, P[:, d] - A[:, d], P[:, d] - B[:, d], mu, A[:, d] - B[:, d]) for d in range(3)]
+    Ed = [_hermite_E(lm, lm + 2, p, P[:, d] - A[:, d], P[:, d] - B[:, d], mu, A[:, d] - B[:, d]) for d in range(3)]
 
     def pick(d, dj, t):
         """E^{la_d, lb_d + dj}_t per pair (lb_d + dj may be -1 or -2: zero)."""
         out = np.zeros(len(p))
-        for i in (0, 1):
-            for j in range(0, 4):
+        for i in range(lm + 1):
+            for j in range(0, lm + 3):
+                if t > i + j:
+                    continue
                 m = (la[:, d] == i) & (lb[:, d] + dj == j)
                 if m.any():
                     out[m] = Ed[d][i][j][t][m]
@@ -179,54 +288,48 @@ def integrals(mol):
                   * np.sqrt(np.pi / p))
     Sp = S1[0] * S1[1] * S1[2]
     Tp = T1[0] * S1[1] * S1[2] + S1[0] * T1[1] * S1[2] + S1[0] * S1[1] * T1[2]
-    # Hermite tensor of every pair: Eab[pair, t, u, v], t,u,v <= 2
-    Eab = np.zeros((len(p), 3, 3, 3))
-    for t in range(3):
-        for u in range(3):
-            for v in range(3):
-                if t + u + v <= 2:
-                    Eab[:, t, u, v] = pick(0, 0, t) * pick(1, 0, u) * pick(2, 0, v)
+    # Hermite tensor of every pair: Eab[pair, t, u, v], t + u + v <= 2*lmax
+    Eab = np.zeros((len(p), nt, nt, nt))
+    e1 = [[pick(d, 0, t) for t in range(nt)] for d in range(3)]
+    for t in range(nt):
+        for u in range(nt):
+            for v in range(nt):
+                if t + u + v <= 2 * lm:
+                    Eab[:, t, u, v] = e1[0][t] * e1[1][u] * e1[2][v]
     Vp = np.zeros(len(p))
     for Zc, C in zip(mol.Z, mol.R):
-        R = _hermite_R(2, p, P - C)
+        R = _hermite_R(2 * lm, p, P - C)
         acc = np.zeros(len(p))
         for (t, u, v), r in R.items():
             acc += Eab[:, t, u, v] * r
         Vp -= Zc * 2 * np.pi / p * acc
-    # contraction to AOs
     nao = mol.nao
-    pair_ao = mol.ao[I] * nao + mol.ao[J]
-
-    def contract1(x):
-        out = np.zeros(nao * nao)
-        np.add.at(out, pair_ao, cc * x)
-        return out.reshape(nao, nao)
-    S, T, V = contract1(Sp), contract1(Tp), contract1(Vp)
+    S, T, V = ((M.T @ (cc * x)).reshape(nao, nao) for x in (Sp, Tp, Vp))
     # electron repulsion: (ab|cd) = 2 pi^2.5 / (p q sqrt(p+q)) sum E_ab(tuv) (-1)^(t'+u'+v') E_cd(t'u'v') R(t+t',u+u',v+v')
-    sign = np.array([[[(-1.0) ** (t + u + v) for v in range(3)] for u in range(3)] for t in range(3)])
+    sign = np.array([[[(-1.0) ** (t + u + v) for v in range(nt)] for u in range(nt)] for t in range(nt)])
     Ecd = Eab * sign[None]
-    eri = np.zeros((nao * nao, nao * nao))
-    idx = [(t, u, v) for t in range(3) for u in range(3) for v in range(3) if t + u + v <= 2]
+    idx = [(t, u, v) for t in range(nt) for u in range(nt) for v in range(nt) if t + u + v <= 2 * lm]
+    W = np.zeros((len(p), len(p)))                                # pair-pair integrals, lower block triangle
     chunk = 64
     for s0 in range(0, len(p), chunk):
-        sl = slice(s0, min(len(p), s0 + chunk))
-        pq = p[sl, None] + p[None, :]
-        alpha = p[sl, None] * p[None, :] / pq
-        R = _hermite_R(4, alpha, P[sl, None, :] - P[None, :, :])
+        s1 = min(len(p), s0 + chunk)
+        sl, kt = slice(s0, s1), slice(0, s1)
+        pq = p[sl, None] + p[None, kt]
+        alpha = p[sl, None] * p[None, kt] / pq
+        R = _hermite_R(4 * lm, alpha, P[sl, None, :] - P[None, kt, :])
         acc = np.zeros_like(alpha)
         for (t, u, v) in idx:
             ea = Eab[sl, t, u, v]
             if not ea.any():
                 continue
             for (t2, u2, v2) in idx:
-                ec = Ecd[:, t2, u2, v2]
+                ec = Ecd[kt, t2, u2, v2]
                 if not ec.any():
                     continue
                 acc += ea[:, None] * ec[None, :] * R[(t + t2, u + u2, v + v2)]
-        val = 2 * np.pi ** 2.5 / (p[sl, None] * p[None, :] * np.sqrt(pq)) * acc * cc[sl, None] * cc[None, :]
-        # scatter rows to AO pairs
-        for k, row in zip(pair_ao[sl], val):
-            np.add.at(eri[k], pair_ao, row)
+        W[sl, kt] = 2 * np.pi ** 2.5 / (p[sl, None] * p[None, kt] * np.sqrt(pq)) * acc * cc[sl, None] * cc[None, kt]
+    W = np.tril(W) + np.tril(W, -1).T
+    eri = M.T @ W @ M
     return S, T, V, eri.reshape(nao, nao, nao, nao)
 
 
@@ -234,9 +337,7 @@ def dipole_integrals(mol, origin=(0., 0., 0.)):
     """<mu| r - origin |nu>, [3, nao, nao] (the 'int1e_r' integrals the reference takes from PySCF with
     `mol.with_common_orig`, exp_pot.py:90-98): 1-D first moments (E_1 + (P - C) E_0) sqrt(pi/p) times the overlaps of
     the other two directions."""
-    npr = len(mol.ex)
-    I, J = np.meshgrid(np.arange(npr), np.arange(npr), indexing="ij")
-    I, J = I.ravel(), J.ravel()
+    I, J, M = _pairs(mol)
     a, b = mol.ex[I], mol.ex[J]
     p = a + b
     mu = a * b / p
@@ -247,21 +348,21 @@ def dipole_integrals(mol, origin=(0., 0., 0.)):
     origin = np.asarray(origin, dtype=np.float64)
     S1, M1 = [], []
     for d in range(3):
-        E = _hermite_E(1, 1, p, P[:, d] - A[:, d], P[:, d] - B[:, d], mu, A[:, d] - B[:, d])
+        lm = mol.lmax
+        E = _hermite_E(lm, lm, p, P[:, d] - A[:, d], P[:, d] - B[:, d], mu, A[:, d] - B[:, d])
         e0, e1 = np.zeros(len(p)), np.zeros(len(p))
-        for i in (0, 1):
-            for j in (0, 1):
+        for i in range(lm + 1):
+            for j in range(lm + 1):
                 m = (la[:, d] == i) & (lb[:, d] == j)
                 e0[m], e1[m] = E[i][j][0][m], E[i][j][1][m]
         S1.append(e0 * np.sqrt(np.pi / p))
         M1.append((e1 + (P[:, d] - origin[d]) * e0) * np.sqrt(np.pi / p))
     nao = mol.nao
-    pair_ao = mol.ao[I] * nao + mol.ao[J]
-    out = np.zeros((3, nao * nao))
+    out = []
     for d in range(3):
         f = [M1[k] if k == d else S1[k] for k in range(3)]
-        np.add.at(out[d], pair_ao, cc * f[0] * f[1] * f[2])
-    return out.reshape(3, nao, nao)
+        out.append((M.T @ (cc * f[0] * f[1] * f[2])).reshape(nao, nao))
+    return np.stack(out)
 
 
 def rhf(mol, ints=None, conv=1e-11, maxiter=100):

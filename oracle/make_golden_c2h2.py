@@ -5,7 +5,7 @@ UNMODIFIED reference solver / CCSD.GCC / exp_pot.Exp on the integrals of ecw_cc_
 
     python -m oracle.make_golden_c2h2
 
-(cc-pVDZ needs d functions, which molint does not have: the sweep logic and the kernels are basis independent.)
+(6-31G instead of cc-pVDZ to keep the reference sweep at minutes: the sweep logic and the kernels are basis independent.)
 """
 import os
 

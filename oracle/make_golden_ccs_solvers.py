@@ -50,10 +50,10 @@ def run_gs(Solver_CCS, Gccs, Exp, er):
     return out
 
 
-def run_es(Solver_ES, Gccs, Exp, koopman, mol, er):
+def run_es(Solver_ES, Gccs, Exp, koopman, mol, er, cases=None):
     o, v = er.nocc, er.fock.shape[0] - er.nocc
     out = {}
-    for tag, exp_data, (val_core, kidx), conv_var, diis, Ls, maxiter in es_cases(o, v):
+    for tag, exp_data, (val_core, kidx), conv_var, diis, Ls, maxiter in (cases or es_cases(o, v)):
         rn, _ = koopman(er.mo_energy, er.mo_occ, val_core, koop_idx=kidx)
         vx = Exp(Ls[0], exp_data, mol, er.mo_coeff_g)
         solver = Solver_ES(Gccs(er), vx, rn_ini=rn, conv_var=conv_var, conv_thres=1e-9, maxiter=maxiter, diis=diis,

@@ -70,3 +70,27 @@ def test_acetylene_rhf_is_reproducible():
     assert mol.nao == 22 and (er.nocc, er.fock.shape[0]) == (14, 44)
     assert abs(scf[0] - float(g["EHF"])) < 1e-9 and abs(scf[0] - (-76.79224)) < 1e-4
     assert np.abs(scf[1] - g["mo_energy"]).max() < 1e-7
+
+
+def test_d_shells_and_basis_families():
+    """Five spherical d functions per shell (PySCF's default): function counts of the named basis sets, rotational
+    invariance of the RHF energy (mixes the d components), energies against known values, normalised AOs."""
+    from ecw_cc_b200 import molint
+    counts = {"6-31g": 13, "6-31g*": 18, "6-31+g*": 22, "6-31++g**": 30, "cc-pvdz": 24}
+    for basis, nao in counts.items():
+        assert molint.Molecule(H2O, basis).nao == nao, basis
+    with pytest.raises(NotImplementedError):
+        molint.Molecule(H2O, "def2-svp")
+    rng = np.random.default_rng(0)
+    Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    turned = [(z, tuple(Q @ np.array(r))) for z, r in H2O]
+    # RHF/cc-pVDZ water at this geometry: -76.0268 (literature); 6-31+G*: value of this implementation
+    for basis, want, tol in (("cc-pvdz", -76.0268, 1e-4), ("6-31+g*", -76.0162450889, 1e-8)):
+        mol = molint.Molecule(H2O, basis)
+        ints = molint.integrals(mol)
+        e0 = molint.rhf(mol, ints)[0]
+        assert abs(e0 - want) < tol, (basis, e0)
+        assert np.abs(np.diag(ints[0]) - 1).max() < 1e-6
+        assert abs(molint.rhf(molint.Molecule(turned, basis))[0] - e0) < 1e-10, basis
+    er = molint.geris(molint.Molecule(H2O, "6-31+g*"))
+    assert (er.nocc, er.fock.shape[0] - er.nocc) == (10, 34)          # the (10, 34) of SURVEY §8(f)-1
