@@ -330,7 +330,7 @@ def run_ours(args):
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic = ncu_traffic()
+        traffic = ncu_traffic() if (o, v) == (40, 400) else None    # the committed capture is of the default workload
         # the ladder is timed inside the step (per-op events between back-to-back launches): the SUSTAINED figure is the
         # denominator the measurement rules name for that; the burst-based fraction is reported next to it
         bf16_burst = float(mp.get("bf16_tflops", 0.0))

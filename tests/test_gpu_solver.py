@@ -55,5 +55,11 @@ def test_solver_numpy_api_and_device_api_agree(built_lib):
     s = ecw.Solver_CCSD(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), conv_thres=1e-8, maxiter=30)
     out = s.SCF(L, ref[5][0], ref[5][1], ref[5][2], ref[5][3])
     assert abs(out[1][-1] - ref[1][-1]) < 1e-9
-    with pytest.raises(NotImplementedError):
-        ecw.Solver_CCSD(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), diis='tl')
+    # Q5 (Solver_GS.py:648-649): the constructor's diis is only used when SCF gets diis=None; the numpy-API loop with
+    # the restated pyscf DIIS and the device-resident DIIS walk through the same iterates
+    s = ecw.Solver_CCSD(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), conv_thres=1e-8, maxiter=30, diis='tl', maxdiis=5)
+    plain = s.SCF(L, alpha=alpha)
+    assert plain[0] == ref[0] and np.abs(plain[1] - ref[1]).max() < 1e-12
+    acc = s.SCF(L, alpha=alpha, diis=None)
+    r3 = scf_loop(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), L, alpha=alpha, conv_thres=1e-8, maxiter=30, diis='tl', maxdiis=5)
+    assert acc[0] == r3[0] and np.abs(acc[1] - r3[1]).max() < 1e-11 and abs(acc[1][-1] - ref[1][-1]) < 1e-8
