@@ -383,9 +383,11 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_per_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "solver_loop": {"value": solver_iters / (ms_solver / 1e3), "unit": "iterations/s",
-                        "h2d_bytes_per_iteration": n * n * 8, "d2h_bytes_per_iteration": n * n * 8 + 16,
-                        "what": "ecw_cc_b200.Solver_CCSD.SCF (mirror of Solver_GS.Solver_CCSD.SCF): the same iteration "
-                                "with the amplitudes resident on the GPU; only rdm1 / dressed Fock cross PCIe"},
+                        "h2d_bytes_per_iteration": 0, "d2h_bytes_per_iteration": 32,
+                        "what": "ecw_cc_b200.Solver_CCSD.SCF (mirror of Solver_GS.Solver_CCSD.SCF) with "
+                                "ecw_cc_b200.exp_pot.Exp ('mat' target): the same iteration with the amplitudes, the "
+                                "rdm1, the experimental potential and the dressed Fock resident on the GPU; only "
+                                "Delta, vmax, the energy and the convergence distance (4 doubles) cross PCIe"},
         "gpu_launches": int(launches * args.steps),
         "roofline": roofline,
     }

@@ -1,9 +1,11 @@
 """Device-resident mirror of the reference ground-state solver `Solver_GS.Solver_CCSD`
 (Solver_GS.py:522-742): same constructor and `SCF` signatures, same iteration order, same convergence bookkeeping
 (Q7: `Dconv` stays 1.0 on iteration 0; divergence threshold 1.0) and the same return tuple — but the o^2v^2 amplitudes
-never leave the GPU.  Per iteration only the rdm1 (n x n) comes to the host, where the caller's unchanged `VX_exp`
-object (`exp_pot.Exp`, exp_pot.py:131-345) turns it into Vexp, and the dressed Fock goes back; the convergence vector
-and its norm are formed on the device (`ecw_conv_check`).
+never leave the GPU.  With `ecw_cc_b200.exp_pot.Exp` and a single density-matrix target (what `Main.CCSD_GS` fits) the
+potential and the dressed Fock matrix are formed on the device too (`ecw_vexp_mat`) and only scalars cross PCIe; with
+any other `VX_exp` object (e.g. the unchanged reference `exp_pot.Exp`, exp_pot.py:131-345) the rdm1 (n x n) goes to the
+host once per iteration and the dressed Fock comes back.  The convergence vector and its norm are formed on the device
+(`ecw_conv_check`).
 
 The reference loop driven through the numpy API of `GCC` moves 16 GB over PCIe per iteration at (40,400); this loop
 moves 3 MB.  DIIS (Solver_GS.py:666-674, 683-686, 709-718) is provided by `ecw_cc_b200.diis.DIIS`: 'tl' extrapolates
@@ -114,13 +116,22 @@ class Solver_CCSD(object):
         if 'tl' in diis:
             tl_diis = DIIS(mycc._dev_ops())
             tl_diis.space, tl_diis.min_space = self.maxdiis, 2
+        # a single density-matrix target of our own Exp class is evaluated on the device (ecw_vexp_mat): then nothing
+        # but scalars crosses PCIe inside the loop.  Any other potential object, and DIIS on the rdm1, take the host route.
+        on_device = adiis is None and getattr(VXexp, "device_mat_ready", lambda: False)()
+        fock_dev = mycc.eris.fock_dev if on_device else None
+        rdm1_dev = None
         while Dconv > self.conv_thres:
-            rdm1 = mycc.gamma(ts, td, ls, ld).cpu().numpy()                       # n x n to the host
-            if adiis is not None:
-                rdm1 = adiis.update(rdm1)
-            Delta, vmax = VXexp.Vexp_update(rdm1, rdm1, (0, 0), L=L)
-            fsp_h = np.subtract(self.fock, VXexp.Vexp[0, 0])
-            fsp = torch.from_numpy(np.ascontiguousarray(fsp_h, dtype=np.float64)).to(dev)
+            if on_device:
+                rdm1_dev = mycc.gamma(ts, td, ls, ld)
+                Delta, vmax, fsp = VXexp.mat_update_device(rdm1_dev, fock_dev, L=L)
+            else:
+                rdm1 = mycc.gamma(ts, td, ls, ld).cpu().numpy()                   # n x n to the host
+                if adiis is not None:
+                    rdm1 = adiis.update(rdm1)
+                Delta, vmax = VXexp.Vexp_update(rdm1, rdm1, (0, 0), L=L)
+                fsp_h = np.subtract(self.fock, VXexp.Vexp[0, 0])
+                fsp = torch.from_numpy(np.ascontiguousarray(fsp_h, dtype=np.float64)).to(dev)
             Delta_ite.append((Delta, vmax))
             Ep_ite.append(float(mycc.energy(ts, td, fsp)))
             ts, td = mycc.tupdate(ts, td, fsp=fsp, alpha=alpha)
@@ -148,6 +159,9 @@ class Solver_CCSD(object):
             ite += 1
         else:
             Conv_text = 'Convergence reached for lambda= {} and alpha={}, after {} iteration'.format(L, alpha, ite)
+        if on_device:
+            rdm1 = rdm1_dev.cpu().numpy() if rdm1_dev is not None else []
+            VXexp.sync_host()
         amps = [ts, ls, td, ld]
         if not return_device:
             amps = [a.cpu().numpy() for a in amps]

@@ -118,6 +118,7 @@ class _Lib(object):
             "ecw_op_dot": (c_i, [c_p, c_d, c_p, c_p, c_d, c_p, c_p]),
             "ecw_op_workspace_needed": (c_l, [c_p]),
             "ecw_conv_check": (c_i, [c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_i, c_p]),
+            "ecw_vexp_mat": (c_i, [c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_l, c_p]),
             "ecw_profile_enable": (c_i, [c_p, c_i]),
             "ecw_profile_dump": (c_l, [c_p, c_p, c_l]),
         }

@@ -848,6 +848,15 @@ int ecw_conv_check(const double* a, const double* b, const double* prev, double*
   });
 }
 
+int ecw_vexp_mat(const double* rdm1, const double* target, const double* fock, double L, double* vexp, double* fsp,
+                 double* stats2, int64_t n, void* stream) {
+  return guarded(nullptr, [&] {
+    require_device();
+    if (!rdm1 || !target || !fock || !vexp || !fsp || !stats2) throw Fail("ecw_vexp_mat: null pointer");
+    ck(launch_vexp_mat(rdm1, target, fock, L, vexp, fsp, stats2, n, static_cast<cudaStream_t>(stream)), "vexp_mat");
+  });
+}
+
 int ecw_profile_enable(ecw_ctx* c, int on) {
   if (!c) return -1;
   c->profile = on != 0;

@@ -400,6 +400,38 @@ conv_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, 
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// experimental potential of the density-matrix target (exp_pot.py:185-195): diff = target - rdm1,
+// vexp = L diff, fsp = fock - vexp, stats = {sum |diff|, max |diff|}.  n x n is tiny: one block, fixed reduction order.
+__global__ void __launch_bounds__(EW_THREADS)
+vexp_mat_kernel(const double* __restrict__ rdm1, const double* __restrict__ target, const double* __restrict__ fock,
+                double L, double* __restrict__ vexp, double* __restrict__ fsp, double* __restrict__ stats, int64_t n) {
+  __shared__ double sh_sum[EW_THREADS];
+  __shared__ double sh_max[EW_THREADS];
+  double s = 0.0, m = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = target[i] - rdm1[i];
+    const double w = L * d;
+    vexp[i] = w;
+    fsp[i] = fock[i] - w;
+    s += fabs(d);
+    m = fmax(m, fabs(d));
+  }
+  sh_sum[threadIdx.x] = s;
+  sh_max[threadIdx.x] = m;
+  __syncthreads();
+  for (int w = EW_THREADS / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      sh_sum[threadIdx.x] += sh_sum[threadIdx.x + w];
+      sh_max[threadIdx.x] = fmax(sh_max[threadIdx.x], sh_max[threadIdx.x + w]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    stats[0] = sh_sum[0];
+    stats[1] = sh_max[0];
+  }
+}
+
 __global__ void __launch_bounds__(EW_THREADS)
 dot_final_kernel(const double* partial, int nb, double* scal, double alpha, double beta) {
   __shared__ double sh[EW_THREADS];
@@ -609,6 +641,13 @@ cudaError_t launch_conv(const double* a, const double* b, const double* prev, do
   int nb = (int)std::min<int64_t>(nblocks, std::max<int64_t>(1, (n + EW_THREADS - 1) / EW_THREADS));
   conv_partial_kernel<<<nb, EW_THREADS, 0, st>>>(a, b, prev, conv, n, partial);
   dot_final_kernel<<<1, EW_THREADS, 0, st>>>(partial, nb, scal, 1.0, beta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vexp_mat(const double* rdm1, const double* target, const double* fock, double L, double* vexp,
+                            double* fsp, double* stats, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  vexp_mat_kernel<<<1, EW_THREADS, 0, st>>>(rdm1, target, fock, L, vexp, fsp, stats, n);
   return cudaGetLastError();
 }
 

@@ -115,6 +115,8 @@ cudaError_t launch_finish(const double* r, const double* amp, const double* fock
                           int sub_singles, cudaStream_t st);
 cudaError_t launch_subdiff(const double* e, const double* v, double alpha, double* out, int64_t n, cudaStream_t st);
 // conv = |a| + |b| (b null: a); scal = beta*scal + sum (conv - prev)^2 (prev null: + 0); partial: nblocks doubles
+cudaError_t launch_vexp_mat(const double* rdm1, const double* target, const double* fock, double L, double* vexp,
+                            double* fsp, double* stats, int64_t n, cudaStream_t st);
 cudaError_t launch_conv(const double* a, const double* b, const double* prev, double* conv, int64_t n, double* partial,
                         int nblocks, double* scal, double beta, cudaStream_t st);
 cudaError_t launch_dot(const double* a, const double* b, int64_t n, double* partial, int nblocks, double* scal,

@@ -7,8 +7,10 @@ Targets (exp_pot.py:131-345): 'mat' (ground or excited state rdm1), 'trmat' (lef
 AO pairs (PySCF `ft_ao`) and is not provided.  Property targets take their AO integrals from `mol`, which may be a PySCF
 `Mole` or `ecw_cc_b200.molint.Molecule` (same `intor_symmetric` / `with_common_orig` / `atom_charges` / `atom_coords`).
 
-n x n work on the host: the device-resident solver (`ecw_cc_b200.Solver_CCSD`) sends it the rdm1 (n x n) once per
-iteration and takes the dressed Fock back — 3 MB of PCIe traffic per iteration at (40,400).
+n x n work on the host, except for the case `Main.CCSD_GS` runs — one density-matrix target for the ground state —
+which `mat_update_device` evaluates on the GPU (`ecw_vexp_mat`): the device-resident solver (`ecw_cc_b200.Solver_CCSD`)
+then moves only scalars per iteration; for every other target it sends the rdm1 (n x n) to the host once per iteration
+and takes the dressed Fock back (3 MB of PCIe traffic per iteration at (40,400)).
 """
 import numpy as np
 
@@ -173,3 +175,47 @@ class Exp(object):
                     vmax += np.max(np.abs(diff))
                 self.prop_calc.append([name, calc])
         return Delta, vmax
+
+    # -- the 'mat' ground-state target without leaving the GPU ------------------------------------------
+    def device_mat_ready(self):
+        """True when Vexp[0, 0] is exactly one density-matrix target (what `Main.CCSD_GS` fits): then the potential and
+        the dressed Fock matrix can be formed on the device by `mat_update_device`."""
+        return bool(self.prop_names) and self.prop_names[0] == ['mat'] and self.Ek_exp_GS is None
+
+    def mat_update_device(self, rdm1_dev, fock_dev, L=None):
+        """Device version of `Vexp_update(rdm1, rdm1, (0, 0), L)` + `fsp = fock - Vexp[0, 0]` (exp_pot.py:185-195,
+        Solver_GS.py:690-692) through `ecw_vexp_mat`: returns (Delta, vmax, fsp) with fsp a device tensor; only the two
+        reduction results (16 bytes) come to the host.  `self.Vexp[0, 0]` holds the DEVICE potential afterwards; call
+        `sync_host()` to turn it into the numpy array the host path leaves there."""
+        import torch
+        from ._lib import lib, EcwError
+        if not self.device_mat_ready():
+            raise EcwError("mat_update_device needs a single 'mat' ground-state target")
+        L = self.L if L is None else self.L_check(L)
+        dev = rdm1_dev.device
+        st = getattr(self, "_dev", None)
+        if st is None or st["device"] != dev:
+            target = np.ascontiguousarray(self.exp_data[0][0][1], dtype=np.float64)
+            hf = self.HF_prop[0][0]
+            st = {"device": dev, "target": torch.from_numpy(target).to(dev),
+                  "norm": float(np.sum(abs(target if hf is None else target - hf))),
+                  "vexp": torch.empty_like(rdm1_dev), "stats": torch.zeros(2, dtype=torch.float64, device=dev)}
+            self._dev = st
+        if tuple(rdm1_dev.shape) != tuple(st["target"].shape) or not rdm1_dev.is_contiguous():
+            raise ValueError("rdm1 must be a contiguous device matrix of the target's shape")
+        fsp = torch.empty_like(rdm1_dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.ecw_vexp_mat(rdm1_dev.data_ptr(), st["target"].data_ptr(), fock_dev.data_ptr(), float(L[0][0]),
+                              st["vexp"].data_ptr(), fsp.data_ptr(), st["stats"].data_ptr(), rdm1_dev.numel(), stream)
+        if rc != 0:
+            raise EcwError("ecw_vexp_mat failed")
+        self.Vexp[0, 0] = st["vexp"]
+        self.prop_calc = []
+        s = st["stats"].cpu()
+        return float(s[0]) / st["norm"], float(s[1]), fsp
+
+    def sync_host(self):
+        """Replace a device-resident Vexp[0, 0] by its numpy copy."""
+        v = self.Vexp[0, 0]
+        if v is not None and not isinstance(v, np.ndarray) and hasattr(v, "cpu"):
+            self.Vexp[0, 0] = v.cpu().numpy()

@@ -131,6 +131,13 @@ int ecw_subdiff(const double* eq, const double* var, double alpha, double* out, 
 int ecw_conv_check(const double* a, const double* b, const double* prev, double* conv, int64_t n, double* scratch1024,
                    double* sumsq, int accumulate, void* stream);
 
+/* Experimental potential of the density-matrix ('mat') ground-state target and the dressed Fock matrix, on the device
+ * (exp_pot.Exp.Vexp_update 'mat' branch, exp_pot.py:185-195, and Solver_GS.py:690-692): for the n = dim*dim elements
+ * diff = target - rdm1, vexp = L*diff, fsp = fock - vexp; stats2[0] = sum |diff|, stats2[1] = max |diff| (the numerator
+ * of Delta and vmax).  All pointers are device pointers; deterministic. */
+int ecw_vexp_mat(const double* rdm1, const double* target, const double* fock, double L, double* vexp, double* fsp,
+                 double* stats2, int64_t n, void* stream);
+
 /* ---- primitive device ops ---------------------------------------------------------
  * The CCS class (CCS.py:197-1518: T1inter/tsupdate/L1inter/lsupdate/R1inter/rsupdate/es_L1inter/
  * es_lsupdate/R0inter/L0inter/*_fromE/gamma_*) and the GCC intermediate getters (cc_Fvv, cc_Woooo,

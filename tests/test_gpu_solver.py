@@ -63,3 +63,35 @@ def test_solver_numpy_api_and_device_api_agree(built_lib):
     acc = s.SCF(L, alpha=alpha, diis=None)
     r3 = scf_loop(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), L, alpha=alpha, conv_thres=1e-8, maxiter=30, diis='tl', maxdiis=5)
     assert acc[0] == r3[0] and np.abs(acc[1] - r3[1]).max() < 1e-11 and abs(acc[1][-1] - ref[1][-1]) < 1e-8
+
+
+def test_density_matrix_potential_on_the_device(built_lib):
+    """`ecw_vexp_mat`: potential, dressed Fock, Delta and vmax of the 'mat' target formed on the device —
+    against the host route of the same class, bit for bit for the matrices; and the solver takes that route."""
+    import torch
+    import ecw_cc_b200 as ecw
+    o, v = 6, 10
+    n = o + v
+    er = synth.SynthEris(o, v)
+    cc = ecw.GCC(er)
+    rng = np.random.default_rng(11)
+    rdm1 = np.diag(np.concatenate([np.ones(o), np.zeros(v)])) + 0.01 * rng.standard_normal((n, n))
+    hf = np.diag(np.concatenate([np.ones(o), np.zeros(v)]))
+    for hf_prop in (False, [[hf]]):
+        host = ecw.exp_pot.Exp(0.3, [[["mat", target_rdm1(o, v)]]], None, None, HF_prop=hf_prop)
+        devp = ecw.exp_pot.Exp(0.3, [[["mat", target_rdm1(o, v)]]], None, None, HF_prop=hf_prop)
+        assert devp.device_mat_ready()
+        d_h, vmax_h = host.Vexp_update(rdm1, rdm1, (0, 0), L=0.7)
+        d_d, vmax_d, fsp = devp.mat_update_device(torch.from_numpy(rdm1).cuda(), cc.eris.fock_dev, L=0.7)
+        assert abs(d_h - d_d) < 1e-14 and vmax_h == vmax_d
+        assert np.array_equal(fsp.cpu().numpy(), np.subtract(cc.fock, host.Vexp[0, 0]))
+        devp.sync_host()
+        assert isinstance(devp.Vexp[0, 0], np.ndarray) and np.array_equal(devp.Vexp[0, 0], host.Vexp[0, 0])
+    assert not ecw.exp_pot.Exp(0.3, [[["mat", hf], ["mat", hf]]], None, None).device_mat_ready()
+    # the solver: device route (our Exp) and host route (any other object) walk through the same iterates
+    L = 0.05
+    a = ecw.Solver_CCSD(ecw.GCC(er), ecw.exp_pot.Exp(L, [[["mat", target_rdm1(o, v)]]], None, None), conv_thres=1e-8,
+                        maxiter=30).SCF(L)
+    b = ecw.Solver_CCSD(ecw.GCC(er), ExpMat(L, target_rdm1(o, v)), conv_thres=1e-8, maxiter=30).SCF(L)
+    assert a[0] == b[0] and np.abs(a[1] - b[1]).max() < 1e-13 and np.abs(a[2] - b[2]).max() < 1e-13
+    assert isinstance(a[4], np.ndarray) and np.abs(a[4] - b[4]).max() < 1e-13
