@@ -128,15 +128,15 @@ class Solver_ES(object):
                 inter = mycc.R1inter(ts, fsp[n], vexp)
                 En_r, i, a = mycc.Extract_Em_r(rn[k], r0n[k], inter, ov=ov[k])
                 rnew[k] = mycc.rsupdate(rn[k], r0n[k], inter, En_r, force_alpha=force_alpha)
-                rnew[k][i, a] = mycc.get_ov(ln[k], l0n[k], rn[k], r0n[k], [i, a])
+                rnew[k][i, a] = np.ravel(mycc.get_ov(ln[k], l0n[k], rn[k], r0n[k], [i, a]))[0]
                 r0new[k] = mycc.r0_fromE(En_r, ts, rn[k], vexp, fsp=fsp[n])
                 vexp = V.Vexp[n, 0]
                 inter = mycc.es_L1inter(ts, fsp[n], vexp)
                 En_l, i, a = mycc.Extract_Em_l(ln[k], l0n[k], inter, ov=ov[k])
                 lnew[k] = mycc.es_lsupdate(ln[k], l0n[k], En_l, inter, force_alpha=force_alpha)
-                lnew[k][i, a] = mycc.get_ov(rn[k], r0n[k], ln[k], l0n[k], [i, a])
+                lnew[k][i, a] = np.ravel(mycc.get_ov(rn[k], r0n[k], ln[k], l0n[k], [i, a]))[0]
                 l0new[k] = mycc.l0_fromE(En_l, ts, ln[k], vexp, fsp=fsp[n])
-                Ep[n, 0], Ep[n, 1] = En_r, En_l
+                Ep[n, 0], Ep[n, 1] = np.ravel(En_r)[0], np.ravel(En_l)[0]
             if diis == 'all':                              # one vector: ts, ls, all r, all l, all r0, all l0
                 vec = np.concatenate((np.ravel(ts), np.ravel(ls), np.ravel([np.ravel(x) for x in rnew]),
                                       np.ravel([np.ravel(x) for x in lnew]), np.ravel([np.ravel(x) for x in r0new]),
@@ -153,7 +153,7 @@ class Solver_ES(object):
                 Spin[k] = utilities.check_spin(rnew[k], lnew[k])
             rn, ln, r0n, l0n = (copy.deepcopy(x) for x in (rnew, lnew, r0new, l0new))
             amp = {'ts': ts, 'ls': ls, 'rn': rn, 'ln': ln, 'r0n': r0n, 'l0n': l0n}
-            Ep[0, 0] = mycc.energy_ccs(ts, fsp[0], rsn=rn, r0n=r0n, vn=[V.Vexp[0, n] for n in range(1, ns)])
+            Ep[0, 0] = np.ravel(mycc.energy_ccs(ts, fsp[0], rsn=rn, r0n=r0n, vn=[V.Vexp[0, n] for n in range(1, ns)]))[0]
             conv = self._conv_vector(amp)
             if ite > 0:
                 Dconv = np.linalg.norm(conv - conv_old)

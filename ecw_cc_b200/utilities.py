@@ -193,5 +193,5 @@ def check_ortho(rn, ln, r0n, l0n):
     C = np.zeros((ns, ns))
     for k in range(ns):
         for l in range(ns):
-            C[k, l] = (get_norm(rn[k], ln[l], r0n[k], l0n[l]) + get_norm(rn[l], ln[k], r0n[l], l0n[k])) / 2.
+            C[k, l] = np.ravel((get_norm(rn[k], ln[l], r0n[k], l0n[l]) + get_norm(rn[l], ln[k], r0n[l], l0n[k])) / 2.)[0]
     return C
