@@ -409,7 +409,7 @@ def main():
     ap.add_argument("--alpha", type=float, default=None, help="L1 coefficient (default: none, as Main.CCSD_GS)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gemm", default=None, choices=["int8", "dmma"], help="GEMM engine (default: int8)")
-    ap.add_argument("--int8-digits", type=int, default=None, help="7-bit digits of the INT8 engine (default 7)")
+    ap.add_argument("--int8-digits", type=int, default=None, help="base-256 digits of the INT8 engine (default: from the integral magnitudes, 6 for the benchmark)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
