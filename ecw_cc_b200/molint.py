@@ -100,6 +100,9 @@ class Molecule(object):
     SYMBOLS = {"H": 1, "C": 6, "N": 7, "O": 8}
 
     def __init__(self, atoms, basis="6-31g", charge=0):
+        for a in atoms:
+            if (a[0].capitalize() if isinstance(a[0], str) else int(a[0])) not in (set(self.SYMBOLS) | set(self.SYMBOLS.values())):
+                raise NotImplementedError("element %r: basis sets are embedded for H, C, N, O" % (a[0],))
         self.Z = np.array([self.SYMBOLS[a[0].capitalize()] if isinstance(a[0], str) else a[0] for a in atoms], dtype=np.float64)
         self.R = np.array([a[1] for a in atoms], dtype=np.float64) * ANGSTROM
         self.nelec = int(self.Z.sum()) - charge
