@@ -193,6 +193,23 @@ def ncu_traffic():
         return None
 
 
+def time_parts(cc, timed, t1, t2, l1, l2, fsp, reps=2, alpha=1e-3):
+    """ms per call of the four functions of one evaluation, and of the two updates with the L1 term (SURVEY §8d:
+    "report also tupdate and lupdate separately, and with/without alpha").  `timed(fn, steps, warmup) -> (ms, out)`."""
+    calls = [("gamma", lambda: cc.gamma(t1, t2, l1, l2)),
+             ("energy", lambda: cc.energy(t1, t2, fsp)),
+             ("tupdate", lambda: cc.tupdate(t1, t2, fsp=fsp, alpha=None)),
+             ("lupdate", lambda: cc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=None)),
+             ("tupdate_alpha", lambda: cc.tupdate(t1, t2, fsp=fsp, alpha=alpha)),
+             ("lupdate_alpha", lambda: cc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha))]
+    out = {"alpha": alpha, "reps": reps}
+    for name, fn in calls:
+        ms, res = timed(fn, reps, 1)
+        del res
+        out[name + "_ms"] = ms / reps
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -252,6 +269,12 @@ def run_ours(args):
     lib.ecw_profile_enable(de._h, 0)
     ms_dev, _ = timed(step_dev, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the functions of one evaluation on their own, and the updates with the L1 term (extra key "parts")
+    try:
+        parts = time_parts(cc, timed, t1, t2, l1, l2, fsp)
+    except Exception as exc:                                   # never lose the bench line over the breakdown
+        parts = {"error": repr(exc)[:200]}
 
     # ---- dominant launch, timed live with CUDA events on the launching stream
     lib.ecw_profile_enable(de._h, 1)
@@ -388,6 +411,7 @@ def run_ours(args):
                                 "ecw_cc_b200.exp_pot.Exp ('mat' target): the same iteration with the amplitudes, the "
                                 "rdm1, the experimental potential and the dressed Fock resident on the GPU; only "
                                 "Delta, vmax, the energy and the convergence distance (4 doubles) cross PCIe"},
+        "parts": parts,
         "gpu_launches": int(launches * args.steps),
         "roofline": roofline,
     }
