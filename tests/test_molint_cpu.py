@@ -94,3 +94,16 @@ def test_d_shells_and_basis_families():
         assert abs(molint.rhf(molint.Molecule(turned, basis))[0] - e0) < 1e-10, basis
     er = molint.geris(molint.Molecule(H2O, "6-31+g*"))
     assert (er.nocc, er.fock.shape[0] - er.nocc) == (10, 34)          # the (10, 34) of SURVEY §8(f)-1
+
+
+def test_basis_name_variants():
+    from ecw_cc_b200 import molint
+    kinds = lambda name, z: [sh[0] for sh in molint.basis_shells(name, z)]
+    assert kinds("6-31G(d)", 8) == kinds("6-31g*", 8) == ["S", "SP", "SP", "D"]
+    assert kinds("6-31+G(d,p)", 1) == ["S", "S", "P"] and kinds("6-31+G(d,p)", 6) == ["S", "SP", "SP", "SP", "D"]
+    assert kinds("6-31++G**", 1) == ["S", "S", "S", "P"]
+    assert kinds("cc-pVDZ", 6) == ["S", "S", "S", "P", "P", "D"]
+    with pytest.raises(NotImplementedError):
+        molint.basis_shells("cc-pvdz", 7)
+    with pytest.raises(NotImplementedError):
+        molint.Molecule([("Fe", (0., 0., 0.))])
