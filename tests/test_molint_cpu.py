@@ -107,3 +107,16 @@ def test_basis_name_variants():
         molint.basis_shells("cc-pvdz", 7)
     with pytest.raises(NotImplementedError):
         molint.Molecule([("Fe", (0., 0., 0.))])
+
+
+def test_acetylene_ccpvdz_shape_of_config2():
+    """C2H2/cc-pVDZ (config 2's named basis; carbon's cc-pVDZ table and hydrogen's p shell): 38 functions,
+    (nocc, nvir) = (14, 62) as SURVEY §8(f)-1 quotes, RHF energy -76.8255 (literature, 5e-4) — one minute of integrals."""
+    from ecw_cc_b200 import molint
+    from oracle.make_golden_c2h2 import C2H2
+    mol = molint.Molecule(C2H2, "cc-pvdz")
+    ints = molint.integrals(mol)
+    ehf, e, C, _ = molint.rhf(mol, ints)
+    assert mol.nao == 38 and np.abs(np.diag(ints[0]) - 1).max() < 1e-6
+    assert abs(ehf - (-76.82553727888)) < 1e-8 and abs(ehf - (-76.8255)) < 5e-4
+    assert 2 * mol.nao - mol.nelec == 62
