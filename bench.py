@@ -85,12 +85,30 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------- CPU (reference algorithm)
-def cpu_eval_time(o, v, reps=2, warm=1):
-    """Seconds per evaluation of the reference algorithm (oracle port, reference's own einsum routing)."""
-    from oracle import synth
+CPU_SHAPES = [(10, 48), (16, 96)]          # BASELINE.md section 3 / SURVEY 8(d): the sizes the reference's CPU path is timed at
+
+
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs use every host core (and say how many)."""
+    n = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(n)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
+def cpu_eval_time(o, v, reps=1, warm=0):
+    """Seconds per evaluation (gamma + energy + tupdate + lupdate) of the reference algorithm: the numpy port
+    oracle/ccsd_np.py with the reference's own einsum routing (pyscf.lib.einsum -> BLAS, plain np.einsum -> C loops),
+    pinned to the unmodified reference in tests/test_oracle_pins.py."""
+    from oracle import synth, synth_fast
     from oracle.ccsd_np import OracleGCC
-    er = synth.SynthEris(o, v)
-    t1, t2, l1, l2 = synth.amplitudes(o, v)
+    er = synth_fast.FastSynthEris(o, v)
+    t1, t2, l1, l2 = synth_fast.amplitudes(o, v)
     fsp = synth.fsp(o, v)
     cc = OracleGCC(er, faithful=True)
 
@@ -119,43 +137,76 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(o, v, sample=(12, 64), reps=2, warm=1):
-    so, sv = sample
-    sec = cpu_eval_time(so, sv, reps=reps, warm=warm)
-    scaled = (1.0 / sec) * f_ref(so, sv) / f_ref(o, v)
-    return {"value": scaled, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-            "sample": "reference algorithm (oracle/ccsd_np.py, reference's einsum routing) at (nocc,nvir)=(%d,%d): "
-                      "%.3f s/eval measured = %.4g evals/s at that size; value is that rate scaled by the "
-                      "reference's dense flop count to (%d,%d) (x%.3g) - the reference cannot run (%d,%d) itself "
-                      "(~600 GB of v^4 intermediates)" % (so, sv, sec, 1.0 / sec, o, v,
-                                                          f_ref(so, sv) / f_ref(o, v), o, v),
-            "sample_evals_per_sec": 1.0 / sec, "sample_shape": [so, sv]}
+def cpu_measure():
+    """{shape: seconds per eval} at CPU_SHAPES: 3 evals (best) at (10,48), one at (16,96) — 30-60 s of CPU work."""
+    use_all_host_cores()
+    return {(10, 48): cpu_eval_time(10, 48, reps=3, warm=1), (16, 96): cpu_eval_time(16, 96, reps=1, warm=0)}
+
+
+def cpu_baseline(o, v, gpu_same_shape):
+    """Measured CPU numbers at the shapes the reference can run, beside THIS RUN's GPU numbers at the same shapes; the
+    (nocc, nvir) of the bench line itself is out of the reference's reach (three v^4 arrays: ~600 GB at (40,400)), so
+    the figure for it is an extrapolation and is labelled as one."""
+    sec = cpu_measure()
+    so, sv = CPU_SHAPES[-1]
+    same = []
+    for (a, b) in CPU_SHAPES:
+        g = gpu_same_shape.get((a, b), {})
+        cpu = 1.0 / sec[(a, b)]
+        same.append({"shape": [a, b], "cpu_evals_s": cpu, "cpu_s_per_eval": sec[(a, b)],
+                     "gpu_evals_s": g.get("dev"), "gpu_e2e_evals_s": g.get("e2e"),
+                     "ratio": (g.get("e2e") / cpu) if g.get("e2e") else None,
+                     "ratio_device_resident": (g.get("dev") / cpu) if g.get("dev") else None})
+    factor = f_ref(so, sv) / f_ref(o, v)
+    return {"value": 1.0 / sec[(so, sv)], "unit": UNIT, "cores": blas_threads(), "kind": "port",
+            "sample": "MEASURED at (nocc,nvir)=(%d,%d), the largest SURVEY 8(d) CPU size: reference algorithm "
+                      "(oracle/ccsd_np.py, reference's einsum routing), %d BLAS threads, %.2f s per eval; the bench "
+                      "shape (%d,%d) cannot be run by the reference (~600 GB of v^4 intermediates)"
+                      % (so, sv, blas_threads(), sec[(so, sv)], o, v),
+            "sample_shape": [so, sv],
+            "same_shape": same[-1], "same_shape_all": same,
+            "extrapolated_evals_per_sec_at_bench_shape": (1.0 / sec[(so, sv)]) * factor,
+            "extrapolation": "NOT a measurement: the (%d,%d) rate times the ratio of the reference's dense flop "
+                             "counts f_ref(%d,%d)/f_ref(%d,%d) = %.3g" % (so, sv, so, sv, o, v, factor)}
 
 
 def run_reference(args):
+    """The reference arm: the reference algorithm on the host cores.  It cannot execute the bench shape, so every
+    number printed here is MEASURED at the CPU shapes of BASELINE.md section 3 and the line says so in `config`; the
+    flop-count extrapolation to the bench shape sits under an `extrapolated_*` key only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    ncores = use_all_host_cores()
     o, v = args.nocc, args.nvir
-    sample = (12, 64)
-    t = []
-    for _ in range(min(args.warmup, 1)):        # one warm-up pass is enough for numpy; keeps the run bounded
-        cpu_eval_time(sample[0], sample[1], reps=1, warm=0)
-    for _ in range(args.steps):
-        t.append(cpu_eval_time(sample[0], sample[1], reps=1, warm=0))
-    sec = sum(t) / len(t)
-    scaled = (1.0 / sec) * f_ref(*sample) / f_ref(o, v)
-    cb = {"value": scaled, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-          "sample": "reference algorithm (oracle port, reference's einsum routing) at (%d,%d): %.3f s/eval, "
-                    "scaled by the reference's dense flop count to (%d,%d)" % (sample[0], sample[1], sec, o, v),
-          "sample_evals_per_sec": 1.0 / sec}
-    line = {"impl": "reference", "metric": METRIC, "value": scaled, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / scaled, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic spin-orbital CCSD T+Lambda residual, nocc=%d nvir=%d FP64" % (o, v),
-                       "nocc": o, "nvir": v, "sample_shape": list(sample)},
+    so, sv = CPU_SHAPES[-1]
+    for _ in range(min(args.warmup, 1)):
+        cpu_eval_time(10, 48)
+    small = [cpu_eval_time(10, 48) for _ in range(max(1, min(args.steps, 20)))]
+    t0 = time.perf_counter()
+    big = []
+    while len(big) < args.steps and (not big or time.perf_counter() - t0 + big[-1] < 100.0):
+        big.append(cpu_eval_time(so, sv))                       # bounded: as many (16,96) evals as fit ~100 s
+    sec = sum(big) / len(big)
+    val = 1.0 / sec
+    factor = f_ref(so, sv) / f_ref(o, v)
+    cb = {"value": val, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+          "sample": "reference algorithm (oracle port, reference's einsum routing) MEASURED at (%d,%d): %d evals, "
+                    "%.2f s each, %d host threads; (10,48): %d evals, %.3f s each"
+                    % (so, sv, len(big), sec, ncores, len(small), sum(small) / len(small)),
+          "sample_shape": [so, sv], "evals_per_sec_10_48": len(small) / sum(small),
+          "extrapolated_evals_per_sec_at_bench_shape": val * factor,
+          "extrapolation": "NOT a measurement: x f_ref(%d,%d)/f_ref(%d,%d) = %.3g" % (so, sv, o, v, factor)}
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "steps_timed": len(big), "warmup": args.warmup, "ms_per_step": 1e3 * sec,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic spin-orbital CCSD T+Lambda residual (gamma+energy+tupdate+lupdate), "
+                                   "nocc=%d nvir=%d FP64 - the largest shape of SURVEY 8(d) the reference's CPU path "
+                                   "runs; the bench shape nocc=%d nvir=%d needs ~600 GB there.  Same-shape GPU numbers: "
+                                   "cpu_baseline.same_shape of the other arm's line" % (so, sv, o, v),
+                       "nocc": so, "nvir": sv, "bench_shape": [o, v]},
             "cpu_baseline": cb,
-            "e2e": {"value": scaled, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -179,18 +230,81 @@ def measure_fp64_peak(torch, n=8192, reps=5):
     return 2.0 * n ** 3 / best / 1e9
 
 
-def ncu_traffic():
-    """dram bytes read+written by the dominant launch, from the committed ncu --set full capture."""
+def measure_int8_peak(torch, n=8192, burst_reps=10, sustain_s=4.0):
+    """Dense INT8 tensor-core rate of this GPU, TOP/s: torch._int_mm (cuBLASLt int8 -> int32) 8192^3, best of 10
+    (burst) and back to back for ~4 s (sustained) — the same protocol as MEASURED_PEAKS.json's bf16 figures."""
+    a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+    b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+    for _ in range(3):
+        torch._int_mm(a, b)
+    torch.cuda.synchronize()
+    ops = 2.0 * n ** 3
+    best = 1e99
+    for _ in range(burst_reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        torch._int_mm(a, b)
+        e.record()
+        e.synchronize()
+        best = min(best, s.elapsed_time(e))
+    reps = max(10, int(sustain_s * 1e3 / best))
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        torch._int_mm(a, b)
+    e.record()
+    e.synchronize()
+    sustained = ops * reps / s.elapsed_time(e) / 1e9
+    del a, b
+    torch.cuda.empty_cache()
+    return {"burst_tops": ops / best / 1e9, "sustained_tops": sustained, "reps_sustained": reps,
+            "how": "torch._int_mm int8 %d^3: best of %d (burst); %d back-to-back launches (sustained)" % (n, burst_reps, reps)}
+
+
+def ncu_traffic(o, v, world):
+    """dram bytes read+written by the dominant launch from the committed `ncu --set full` capture of THIS shape and
+    GPU count (profiles/r2_ladder_ncu.json); None when there is no capture that matches."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_int8_oz_tupdate_ncu.json")))
-        rec = [r for r in d["launches"] if "pp ladder" in r.get("launch", "")][0]
-        rd, wr = rec["dram__bytes_read.sum"].split(), rec["dram__bytes_write.sum"].split()
-        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        return {"bytes_per_launch": float(rd[0]) * unit[rd[1]] + float(wr[0]) * unit[wr[1]],
-                "algorithmic_bytes_per_launch": 3.86e10 + 0.5e9,
-                "source": "profiles/r1_int8_oz_tupdate_ncu.json (ncu --set full, same launch, 1 GPU)"}
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_ladder_ncu.json")))
+        if [o, v, world] != [d["nocc"], d["nvir"], d["n_gpus"]]:
+            return None
+        return {"bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"],
+                "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "source": d["source"]}
     except Exception:
         return None
+
+
+def same_shape_gpu(ecw, torch, shapes, reps=5):
+    """evals/s of this repo's path at the shapes the CPU leg is measured at: device resident and through the numpy API
+    (host arrays in, host arrays out)."""
+    from oracle import synth, synth_fast
+    out = {}
+    for (o, v) in shapes:
+        er = synth_fast.FastSynthEris(o, v)
+        t1, t2, l1, l2 = synth_fast.amplitudes(o, v)
+        fsp = synth.fsp(o, v)
+        cc = ecw.GCC(er)
+        dev = [torch.from_numpy(x).cuda() for x in (t1, t2, l1, l2, fsp)]
+
+        def step(a):
+            cc.gamma(a[0], a[1], a[2], a[3])
+            cc.energy(a[0], a[1], a[4])
+            cc.tupdate(a[0], a[1], fsp=a[4])
+            cc.lupdate(a[0], a[1], a[2], a[3], fsp=a[4])
+
+        res = {}
+        for tag, args_ in (("dev", dev), ("e2e", [t1, t2, l1, l2, fsp])):
+            step(args_)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                step(args_)
+            torch.cuda.synchronize()
+            res[tag] = reps / (time.perf_counter() - t0)
+        out[(o, v)] = res
+        del cc, dev
+        torch.cuda.empty_cache()
+    return out
 
 
 def time_parts(cc, timed, t1, t2, l1, l2, fsp, reps=2, alpha=1e-3):
@@ -202,12 +316,25 @@ def time_parts(cc, timed, t1, t2, l1, l2, fsp, reps=2, alpha=1e-3):
              ("lupdate", lambda: cc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=None)),
              ("tupdate_alpha", lambda: cc.tupdate(t1, t2, fsp=fsp, alpha=alpha)),
              ("lupdate_alpha", lambda: cc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha))]
-    out = {"alpha": alpha, "reps": reps}
+    # the path every L1-regularised iteration after the first runs: amplitudes without antisymmetry (Q11)
+    g2, gl2 = t2.clone(), l2.clone()
+    g2[0, 1, 2, 3] += 1e-3
+    gl2[0, 1, 2, 3] += 1e-3
+    calls += [("tupdate_general_alpha", lambda: cc.tupdate(t1, g2, fsp=fsp, alpha=alpha)),
+              ("lupdate_general_alpha", lambda: cc.lupdate(t1, g2, l1, gl2, fsp=fsp, alpha=alpha))]
+    out = {"alpha": alpha, "reps": reps,
+           "note": "*_general_*: doubles amplitudes without antisymmetry (what the reference's L1 update leaves, "
+                   "utilities.py:59-67): the general plans, dense (ij) ladder rows"}
     for name, fn in calls:
         ms, res = timed(fn, reps, 1)
         del res
         out[name + "_ms"] = ms / reps
     return out
+
+
+def np_copy(x):
+    import numpy as np
+    return np.array(x, copy=True)
 
 
 def run_ours(args):
@@ -293,9 +420,13 @@ def run_ours(args):
     gemm_ms = sum(x["ms"] for x in ops if x["kind"] in ("gemm", "oz_gemm", "oz_split"))
     int8_ms = sum(x["ms"] for x in ops if x["kind"] in ("oz_gemm", "oz_split"))
 
-    # ---- end-to-end leg: host (pinned numpy) buffers through the reference-facing API
-    cc.h2d_bytes = cc.d2h_bytes = 0
-    h = {k: cc._to_host(x) for k, x in (("t1", t1), ("t2", t2), ("l1", l1), ("l2", l2), ("fsp", fsp))}
+    # ---- end-to-end leg: host (pinned numpy) buffers through the reference-facing API.  As in the solver loop
+    # (Solver_GS.py:683-705) the amplitudes a step receives are arrays the class itself handed out earlier, so their
+    # device copies are reused (GCC._to_dev); fsp — rebuilt on the host from the rdm1 every iteration — and the singles
+    # are uploaded every step, every result is downloaded every step.
+    h = {k: cc.to_numpy(x) for k, x in (("t1", t1), ("t2", t2), ("l1", l1), ("l2", l2))}
+    h["t1"], h["l1"] = h["t1"].copy(), h["l1"].copy()          # small: plain host arrays, uploaded per call
+    h["fsp"] = fsp.cpu().numpy()
 
     def step_host():
         g = cc.gamma(h["t1"], h["t2"], h["l1"], h["l2"])
@@ -304,12 +435,24 @@ def run_ours(args):
         c, d = cc.lupdate(h["t1"], h["t2"], h["l1"], h["l2"], fsp=h["fsp"], alpha=alpha)
         return g, e, a, b, c, d
 
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     step_host()
-    cc.h2d_bytes = cc.d2h_bytes = 0
+    cc.h2d_bytes = cc.d2h_bytes = cc.h2d_reused = 0
     ms_e2e, _ = timed(step_host, e2e_steps, 1)
     h2d = cc.h2d_bytes // (e2e_steps + 1)
     d2h = cc.d2h_bytes // (e2e_steps + 1)
+    h2d_reused = cc.h2d_reused // (e2e_steps + 1)
+    # the same with every input uploaded (arrays the class has never seen): the round-1 protocol, kept for comparison
+    cold = {k: np_copy(x) for k, x in h.items()}
+
+    def step_cold():
+        cc.gamma(cold["t1"], cold["t2"], cold["l1"], cold["l2"])
+        cc.energy(cold["t1"], cold["t2"], cold["fsp"])
+        cc.tupdate(cold["t1"], cold["t2"], fsp=cold["fsp"], alpha=alpha)
+        cc.lupdate(cold["t1"], cold["t2"], cold["l1"], cold["l2"], fsp=cold["fsp"], alpha=alpha)
+
+    ms_cold, _ = timed(step_cold, 1, 1)
+    del cold
 
     # ---- the solver loop itself, device resident (ecw_cc_b200.Solver_CCSD mirrors Solver_GS.Solver_CCSD.SCF): per
     # iteration gamma -> Vexp('mat') on the host (n x n) -> energy -> tupdate -> lupdate -> convergence vector
@@ -353,12 +496,14 @@ def run_ours(args):
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic = ncu_traffic() if (o, v) == (40, 400) else None    # the committed capture is of the default workload
+        traffic = ncu_traffic(o, v, world)      # only a capture of this shape and GPU count counts
         # the ladder is timed inside the step (per-op events between back-to-back launches): the SUSTAINED figure is the
-        # denominator the measurement rules name for that; the burst-based fraction is reported next to it
+        # denominator the measurement rules name for that; the burst-based fraction is reported next to it.  The INT8
+        # rate itself is MEASURED in this run (cuBLASLt int8 GEMM), not derived from the bf16 figure.
         bf16_burst = float(mp.get("bf16_tflops", 0.0))
         bf16 = float(mp.get("bf16_tflops_sustained", 0.0)) or bf16_burst
-        int8_peak = 2.0 * bf16 if bf16 > 0 else 4500.0
+        i8 = measure_int8_peak(torch)
+        int8_peak = i8["sustained_tops"]
         roofline = {"bound": "tensor",
                     "kernel": "ecw::ozaki_gemm_kernel<%d> (tcgen05.mma kind::i8, TMEM accumulators), launch = packed "
                               "pp-ladder %dx%dx%d (CCSD.py:305)" % (ns, ladder["M"], ladder["N"], ladder["K"]),
@@ -367,11 +512,11 @@ def run_ours(args):
                                  "are int8 digits; the FP64-equivalent rate is in fp64_equivalent_tflops",
                     "frac": fp64_equiv * nprod / int8_peak,
                     "traffic": (traffic or {}).get("bytes_per_launch"), "traffic_detail": traffic,
-                    "frac_vs_burst_peak": (fp64_equiv * nprod / (2.0 * bf16_burst)) if bf16_burst > 0 else None,
-                    "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (%.1f; kernel timed inside a long "
-                                    "step; burst figure %.1f): the INT8 dense rate of the tcgen05 pipe is twice the "
-                                    "bf16 rate (nominal 4500 vs 2250)" % (bf16, bf16_burst)) if bf16 > 0
-                    else "nominal INT8 dense 4500 TOP/s (B200_PROFILING.md fallback)",
+                    "frac_vs_burst_peak": fp64_equiv * nprod / i8["burst_tops"],
+                    "peak_source": "INT8 dense GEMM rate measured in this run, sustained (%s); burst %.0f TOP/s; for "
+                                   "comparison 2 x MEASURED_PEAKS.json bf16 = %.0f (sustained) / %.0f (burst), nominal 4500"
+                                   % (i8["how"], i8["burst_tops"], 2.0 * bf16, 2.0 * bf16_burst),
+                    "int8_peak_measured": i8,
                     "int8_products_per_fp64_product": nprod,
                     "fp64_equivalent_tflops": fp64_equiv, "cublas_dgemm_tflops_measured": peak,
                     "fp64_equivalent_over_fp64_tensor_peak": fp64_equiv / peak,
@@ -404,7 +549,14 @@ def run_ours(args):
                    "f_alg_flops_per_eval": f_alg(o, v), "executed_gemm_flops_per_eval": exec_flops,
                    "tflops_alg": f_alg(o, v) * evals_per_s / 1e12, "tflops_executed": exec_flops * evals_per_s / 1e12},
         "clocks": clocks,
-        "e2e": {"value": e2e_per_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e": {"value": e2e_per_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "h2d_bytes_reused_per_step": int(h2d_reused),
+                "protocol": "GCC.gamma/energy/tupdate/lupdate with numpy arrays in and out; the doubles amplitudes are "
+                            "arrays the class handed out (as in Solver_CCSD.SCF, where each step's amplitudes are the "
+                            "previous step's results), so their device copies are reused; fsp, t1, l1 are uploaded and "
+                            "all results downloaded every step",
+                "all_inputs_uploaded": {"value": 1e3 / ms_cold, "h2d_bytes_per_step": int(6 * 8 * o * o * v * v),
+                                        "note": "every amplitude a fresh host array (round-1 protocol), 1 step"}},
         "solver_loop": {"value": solver_iters / (ms_solver / 1e3), "unit": "iterations/s",
                         "h2d_bytes_per_iteration": 0, "d2h_bytes_per_iteration": 32,
                         "what": "ecw_cc_b200.Solver_CCSD.SCF (mirror of Solver_GS.Solver_CCSD.SCF) with "
@@ -415,8 +567,9 @@ def run_ours(args):
         "gpu_launches": int(launches * args.steps),
         "roofline": roofline,
     }
-    if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(o, v)
+    if not args.no_cpu and world == 1:
+        # this repo's path at the CPU shapes first (GPU still warm), then the CPU leg itself on the host cores
+        line["cpu_baseline"] = cpu_baseline(o, v, same_shape_gpu(ecw, torch, CPU_SHAPES))
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -397,6 +397,32 @@ class Gccs(object):
         P = ops.trace(d_v[:o, :o]) + ops.dot(d_ts, d_v[:o, o:])
         return ops.to_host(Fjb), E, P
 
+    def Extract_r0(self, r1, ts, fsp, vm):                 # CCS.py:1036-1079
+        """r0 from the R1 and R0 equations for a given r1 — contractions on the device, the scalar quadratic on the
+        host exactly as the reference writes it (roots divided by c, `0` when c == 0., ValueError when both roots are
+        negative; the square root of a negative discriminant is numpy's nan + RuntimeWarning, as there)."""
+        r1 = np.asarray(r1)
+        f = self.fock if fsp is None else fsp
+        Rinter = self.R1inter(ts, f, vm)
+        Fjb, Z, P = self.R0inter(ts, f, vm)
+        R, d_rs = self._r1full(r1, 0.0, Rinter)            # Fab.r1 - Fji.r1 + W.r1 + r1 F + Pia  (r0 = 0: no Zia term)
+        R1 = self.ops.to_host(R)
+        Zia = np.asarray(Rinter[4])
+        c = -self.ops.dot(d_rs, self.ops.to_dev(Fjb)) - P
+        if c == 0.:
+            return 0
+        i, j = np.unravel_index(np.argmax(abs(r1), axis=None), r1.shape)
+        a = Zia[i, j] / r1[i, j]
+        b = R1[i, j] / r1[i, j]
+        b -= Z
+        r0_1 = (-b + np.sqrt((b ** 2) - (4 * a * c))) / c
+        r0_2 = (-b - np.sqrt((b ** 2) - (4 * a * c))) / c
+        if r0_1 > 0:
+            return r0_1
+        elif r0_2 > 0:
+            return r0_2
+        raise ValueError('Both solution for r0 are negative')
+
     def r0update(self, rs, r0, Em, R0inter):               # CCS.py:1081-1096
         Fjb, E, P = R0inter
         F = self.ops.dot(self.ops.to_dev(rs), self.ops.to_dev(Fjb))

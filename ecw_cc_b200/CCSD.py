@@ -25,11 +25,14 @@ def _flags(alpha, equation, antisym=False):
 
 
 class GCC(object):
+    TRACK_MIN_BYTES = 1 << 20   # smaller outputs are not worth a device copy kept alive
+
     def __init__(self, eris, fock=None, device=None, assume_antisym=None, rank=0, world=1, group=None, gemm=None,
-                 int8_digits=None):
+                 int8_digits=None, track_outputs=True):
         """:param eris: a `DeviceEris`, or any object with the reference's
         `Eris.geris` attribute surface (uploaded once).
         :param gemm, int8_digits: GEMM engine of the uploaded container ("int8" default / "dmma"; eris.py)
+        :param track_outputs: returned host arrays are read-only and keep their device copies (see `_to_host`)
         :param assume_antisym: None (default) = measure the antisymmetry of the doubles amplitudes
         on the device at every call and pick the packed or the general path; True/False = force."""
         self.assume_antisym = assume_antisym
@@ -42,8 +45,11 @@ class GCC(object):
             self.fock = eris.fock
         self.nvir = self.fock.shape[0] - self.nocc
         self._pin = {}
+        self._tracked = {}      # id(host array this object returned) -> (weakref, its device copy)
+        self.track_outputs = bool(track_outputs)
         self.h2d_bytes = 0      # bytes staged host->device / device->host by this object
         self.d2h_bytes = 0
+        self.h2d_reused = 0     # bytes NOT copied because the device copy of a returned array was reused
 
     # -- host <-> device staging ---------------------------------------------
     def _torch(self):
@@ -51,13 +57,19 @@ class GCC(object):
         return torch
 
     def _to_dev(self, name, x, shape):
-        """numpy -> device.  Arrays that already live in pinned host memory (e.g. the arrays this
-        class returns) are DMA'd directly; others are staged through a persistent pinned buffer."""
+        """numpy -> device.  An array THIS OBJECT handed out (`_to_host`: read-only, so its contents cannot have
+        changed) is not copied again: its device copy is reused — in the solver loop (Solver_GS.py:683-705) every
+        amplitude a call receives is an array an earlier call returned.  Other arrays that already live in pinned
+        host memory are DMA'd directly; the rest is staged through a persistent pinned buffer."""
         torch = self._torch()
         if isinstance(x, torch.Tensor):
             if x.dtype != torch.float64 or tuple(x.shape) != tuple(shape):
                 raise ValueError("%s: expected float64 tensor of shape %s" % (name, (shape,)))
             return x.contiguous(), True
+        ent = self._tracked.get(id(x)) if isinstance(x, np.ndarray) else None
+        if ent is not None and ent[0]() is x and not x.flags.writeable and x.shape == tuple(shape):
+            self.h2d_reused += x.nbytes
+            return ent[1], False
         a = np.asarray(x, dtype=np.float64)
         if a.shape != tuple(shape):
             raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), a.shape))
@@ -77,7 +89,11 @@ class GCC(object):
         return pin.to(self.eris.device, non_blocking=True), False
 
     def _to_host(self, *ts):
-        """device -> fresh numpy arrays backed by pinned memory (torch's caching host allocator)."""
+        """device -> fresh numpy arrays backed by pinned memory (torch's caching host allocator).  With
+        `track_outputs` (default) the arrays are READ-ONLY and the object remembers their device copies for as long
+        as the caller keeps the arrays (weak references): passing one back costs no transfer.  (The reference
+        returns writable arrays; its solvers never write into them — `GCC(..., track_outputs=False)` restores that.)"""
+        import weakref
         torch = self._torch()
         outs = []
         for t in ts:
@@ -87,7 +103,18 @@ class GCC(object):
             outs.append(h)
         torch.cuda.current_stream(self.eris.device).synchronize()
         outs = [h.numpy() for h in outs]
+        if self.track_outputs:
+            for a, t in zip(outs, ts):
+                if a.nbytes >= self.TRACK_MIN_BYTES:
+                    a.setflags(write=False)
+                    key = id(a)
+                    self._tracked[key] = (weakref.ref(a, lambda _r, k=key, d=self._tracked: d.pop(k, None)), t)
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def to_numpy(self, t):
+        """Download a device tensor the way every method of this class returns its results (pinned, read-only,
+        device copy remembered)."""
+        return self._to_host(t)
 
     def antisym_stats(self, d_x):
         """(max |x[ijab]+x[jiab]|, |x[ijab]+x[ijba]|, max |x|) of a device doubles amplitude."""
@@ -128,9 +155,8 @@ class GCC(object):
         d_l1, _ = self._to_dev("l1", l1, (o, v))
         d_l2, _ = self._to_dev("l2", l2, (o, o, v, v))
         out = torch.empty((o + v, o + v), dtype=torch.float64, device=e.device)
-        e.ensure_workspace("gamma", 0)
-        e.run(lib.ecw_ccsd_gamma(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(), d_l2.data_ptr(),
-                                 out.data_ptr(), e.stream()), "ecw_ccsd_gamma")
+        e.execute("gamma", 0, lambda: lib.ecw_ccsd_gamma(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(),
+                                                         d_l2.data_ptr(), out.data_ptr(), e.stream()), "ecw_ccsd_gamma")
         return out if dev else self._to_host(out)
 
     # -- energy (CCSD.py:224-242) -------------------------------------------------
@@ -142,9 +168,8 @@ class GCC(object):
         d_t2, _ = self._to_dev("t2", t2, (o, o, v, v))
         d_f, _ = self._fsp(fsp)
         out = torch.empty(1, dtype=torch.float64, device=e.device)
-        e.ensure_workspace("energy", 0)
-        e.run(lib.ecw_ccsd_energy(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(), out.data_ptr(),
-                                  e.stream()), "ecw_ccsd_energy")
+        e.execute("energy", 0, lambda: lib.ecw_ccsd_energy(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(),
+                                                           out.data_ptr(), e.stream()), "ecw_ccsd_energy")
         if dev:
             return out[0]
         self.d2h_bytes += 8
@@ -161,10 +186,9 @@ class GCC(object):
         o1 = torch.empty((o, v), dtype=torch.float64, device=e.device)
         o2 = torch.empty((o, o, v, v), dtype=torch.float64, device=e.device)
         fl = _flags(alpha, equation, self._is_antisym(d_t2))
-        e.ensure_workspace("tupdate", fl)
-        e.run(lib.ecw_ccsd_tupdate(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(), e.fock_dev.data_ptr(),
-                                   fl, float(alpha or 0.0), o1.data_ptr(), o2.data_ptr(), e.stream()),
-              "ecw_ccsd_tupdate")
+        e.execute("tupdate", fl, lambda: lib.ecw_ccsd_tupdate(
+            e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_f.data_ptr(), e.fock_dev.data_ptr(), fl, float(alpha or 0.0),
+            o1.data_ptr(), o2.data_ptr(), e.stream()), "ecw_ccsd_tupdate")
         if dev:
             return o1, o2
         return self._to_host(o1, o2)
@@ -182,10 +206,10 @@ class GCC(object):
         o1 = torch.empty((o, v), dtype=torch.float64, device=e.device)
         o2 = torch.empty((o, o, v, v), dtype=torch.float64, device=e.device)
         fl = _flags(alpha, equation, self._is_antisym(d_t2, d_l2))
-        e.ensure_workspace("lupdate", fl)
-        e.run(lib.ecw_ccsd_lupdate(e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(), d_l2.data_ptr(),
-                                   d_f.data_ptr(), e.fock_dev.data_ptr(), fl, float(alpha or 0.0),
-                                   o1.data_ptr(), o2.data_ptr(), e.stream()), "ecw_ccsd_lupdate")
+        e.execute("lupdate", fl, lambda: lib.ecw_ccsd_lupdate(
+            e._h, d_t1.data_ptr(), d_t2.data_ptr(), d_l1.data_ptr(), d_l2.data_ptr(), d_f.data_ptr(),
+            e.fock_dev.data_ptr(), fl, float(alpha or 0.0), o1.data_ptr(), o2.data_ptr(), e.stream()),
+            "ecw_ccsd_lupdate")
         if dev:
             return o1, o2
         return self._to_host(o1, o2)

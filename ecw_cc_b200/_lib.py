@@ -5,7 +5,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libecw_b200.so")
-_SRC = ["gemm.cu", "gemm_tma.cu", "ewise.cu", "ozaki.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp", "ccs_plan.cpp"]
+_SRC = ["gemm.cu", "gemm_tma.cu", "ewise.cu", "ozaki.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp"]
 
 ECW_HAS_ALPHA = 1
 ECW_EQUATION = 2
@@ -73,6 +73,8 @@ class _Lib(object):
             "ecw_resume": (c_i, [c_p, c_p]),
             "ecw_ctx_set_gemm": (c_i, [c_p, c_i, c_d]),
             "ecw_ctx_get_gemm": (c_i, [c_p]),
+            "ecw_int8_error_bound": (c_i, [c_p, ctypes.POINTER(c_d), c_p]),
+            "ecw_ctx_set_engine_override": (c_i, [c_p, c_i]),
             "ecw_ctx_set_int8_splitk": (c_i, [c_p, c_l]),
             "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),
             "ecw_ctx_test_assume_ovvv_planes": (c_i, [c_p]),

@@ -22,6 +22,8 @@ struct ecw_ctx {
   int64_t ws_bytes = 0;
   std::map<std::string, std::unique_ptr<Plan>> plans;
   bool profile = false;
+  bool profile_run = false;   // `profile` latched at the start of the call in flight (ecw_resume keeps it)
+  bool force_dmma = false;    // ecw_ctx_set_engine_override: build the plans without the INT8 route
   // resumable execution (plans with collectives yield to the host)
   const Plan* run_plan_ptr = nullptr;
   size_t pc = 0;
@@ -79,18 +81,29 @@ void ck(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw Fail(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// plans are rebuilt after every change of the configuration: nothing may keep pointing into the old ones
+void drop_plans(ecw_ctx* c) {
+  c->plans.clear();
+  c->run_plan_ptr = nullptr;
+  c->last_plan = nullptr;
+  for (auto e : c->ev) cudaEventDestroy(e);
+  c->ev.clear();
+}
+
 Plan& get_plan(ecw_ctx* c, const std::string& func, int flags) {
-  std::string key = func + "/" + std::to_string(flags);
+  std::string key = func + "/" + std::to_string(flags) + (c->force_dmma ? "/dmma" : "");
   auto it = c->plans.find(key);
   if (it != c->plans.end()) return *it->second;
   std::unique_ptr<Plan> P(new Plan());
+  Sizes zz = c->z;
+  if (c->force_dmma) zz.oz_ns = 0;
   const int ha = (flags & ECW_HAS_ALPHA) ? 1 : 0, eq = (flags & ECW_EQUATION) ? 1 : 0;
   const bool as = (flags & ECW_ANTISYM) != 0;
-  if (func == "tupdate") (as ? build_ccsd_tupdate : build_ccsd_tupdate_general)(*P, c->z, ha, eq);
-  else if (func == "lupdate") (as ? build_ccsd_lupdate : build_ccsd_lupdate_general)(*P, c->z, ha, eq);
-  else if (func == "gamma") build_ccsd_gamma(*P, c->z);
-  else if (func == "energy") build_ccsd_energy(*P, c->z);
-  else if (!build_ccs_plan(*P, c->z, func, flags)) throw Fail("unknown function '" + func + "'");
+  if (func == "tupdate") (as ? build_ccsd_tupdate : build_ccsd_tupdate_general)(*P, zz, ha, eq);
+  else if (func == "lupdate") (as ? build_ccsd_lupdate : build_ccsd_lupdate_general)(*P, zz, ha, eq);
+  else if (func == "gamma") build_ccsd_gamma(*P, zz);
+  else if (func == "energy") build_ccsd_energy(*P, zz);
+  else throw Fail("unknown function '" + func + "'");
   Plan& ref = *P;
   c->plans[key] = std::move(P);
   return ref;
@@ -198,7 +211,7 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
         c->pending[4] = op.i1;             // world
         c->pending[5] = op.i2;             // rank
         ++c->pc;
-        if (c->profile) ck(cudaEventRecord(c->ev[c->pc], st), "cudaEventRecord");
+        if (c->profile_run) ck(cudaEventRecord(c->ev[c->pc], st), "cudaEventRecord");
         return 1;
       }
       case OP_OZ_SPLIT:
@@ -218,13 +231,16 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
                                      op.N, op.K, resolve(c, op.c), op.i1, op.i2, op.alpha, op.beta, (int)op.i0, bt, st,
                                      c->sm_count),
            "ozaki_gemm");
+        if (c->ptr[S_SCAL])
+          ck(launch_ozaki_bound(resolve(c, op.d), resolve(c, op.e), op.M, op.N, op.K, op.alpha, (int)op.i0, bt,
+                                c->ptr[S_SCAL] + 15, st), "ozaki_bound");
         break;
       }
       default:
         throw Fail("unknown op kind");
     }
     ++c->pc;
-    if (c->profile) ck(cudaEventRecord(c->ev[c->pc], st), "cudaEventRecord");
+    if (c->profile_run) ck(cudaEventRecord(c->ev[c->pc], st), "cudaEventRecord");
   }
   if (c->copy_scal_to) {
     ck(cudaMemcpyAsync(c->copy_scal_to, c->ptr[S_SCAL], sizeof(double), cudaMemcpyDeviceToDevice, st), "copy scalar");
@@ -238,7 +254,10 @@ int run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
   if (P.workspace_elems() * 8 > c->ws_bytes)
     throw Fail("workspace too small: need " + std::to_string(P.workspace_elems() * 8) + " bytes, have " +
                std::to_string(c->ws_bytes));
-  if (c->profile) {
+  c->profile_run = c->profile;
+  // run-time error bound of the INT8-route products of this call (scal[15], ecw_int8_error_bound)
+  if (c->ptr[S_SCAL]) ck(cudaMemsetAsync(c->ptr[S_SCAL] + 15, 0, sizeof(double), st), "reset int8 bound");
+  if (c->profile_run) {
     for (auto e : c->ev) cudaEventDestroy(e);
     c->ev.assign(P.ops.size() + 1, nullptr);
     for (auto& e : c->ev) ck(cudaEventCreate(&e), "cudaEventCreate");
@@ -327,8 +346,7 @@ int ecw_ctx_set_shard(ecw_ctx* c, int rank, int world) {
   if (!c || world < 1 || rank < 0 || rank >= world) return -1;
   c->z.rank = rank;
   c->z.world = world;
-  c->plans.clear();
-  c->run_plan_ptr = nullptr;
+  drop_plans(c);
   return 0;
 }
 
@@ -340,31 +358,48 @@ int ecw_ctx_set_gemm(ecw_ctx* c, int int8_digits, double min_flops) {
   }
   c->z.oz_ns = int8_digits;
   c->z.oz_min_flops = min_flops;
-  c->plans.clear();
-  c->run_plan_ptr = nullptr;
+  drop_plans(c);
   return 0;
 }
 
 int ecw_ctx_get_gemm(ecw_ctx* c) { return c ? c->z.oz_ns : -1; }
 
+int ecw_ctx_set_engine_override(ecw_ctx* c, int force_dmma) {
+  if (!c) return -1;
+  c->force_dmma = force_dmma != 0;
+  c->run_plan_ptr = nullptr;
+  return 0;
+}
+
+int ecw_int8_error_bound(ecw_ctx* c, double* bound_out, void* stream) {
+  return guarded(c, [&] {
+    require_device();
+    if (!bound_out) throw Fail("ecw_int8_error_bound: null pointer");
+    if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ck(cudaMemcpyAsync(bound_out, c->ptr[S_SCAL] + 15, sizeof(double), cudaMemcpyDeviceToHost, st), "read int8 bound");
+    ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+  });
+}
+
 int ecw_ctx_set_int8_splitk(ecw_ctx* c, int64_t min_k) {
   if (!c) return -1;
   c->z.oz_splitk_min_k = min_k;
-  c->plans.clear();
+  drop_plans(c);
   return 0;
 }
 
 int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* c) {
   if (!c || c->z.oz_ns <= 0) return -1;
   c->z.vvvv_planes = true;
-  c->plans.clear();
+  drop_plans(c);
   return 0;
 }
 
 int ecw_ctx_test_assume_ovvv_planes(ecw_ctx* c) {
   if (!c || c->z.oz_ns <= 0 || (c->z.nocc % 8) || (c->z.nvir % 8)) return -1;
   c->z.ovvv_planes = true;
-  c->plans.clear();
+  drop_plans(c);
   return 0;
 }
 
@@ -381,7 +416,7 @@ int ecw_eris_vvvv_planes(ecw_ctx* c, const double* rows, int64_t row0, int64_t n
                             c->ptr[S_VVVV_OZS], static_cast<cudaStream_t>(stream), row0, nsh), "ozaki_split(vvvv)");
     if (row0 + nrows == nsh) {          // last chunk: from now on plans read the planes, not "vvvv_p"
       c->z.vvvv_planes = true;
-      c->plans.clear();
+      drop_plans(c);
     }
   });
 }
@@ -401,7 +436,7 @@ int ecw_eris_ovvv_planes(ecw_ctx* c, void* stream) {
     ck(launch_ozaki_split2(c->ptr[S_OVVV_P], pv, o, v, 1, v * pv, pv, c->z.oz_ns,
                            reinterpret_cast<int8_t*>(c->ptr[S_OVVV_OZ2]), c->ptr[S_OVVV_OZ2S], st), "ozaki_split(ovvv 2)");
     c->z.ovvv_planes = true;          // from now on plans read the planes, not "ovvv_p"
-    c->plans.clear();
+    drop_plans(c);
   });
 }
 
@@ -728,7 +763,7 @@ int ecw_op_contract(ecw_ctx* c, double alpha, const ecw_tensor* A, const char* s
   return guarded_rc(c, [&] {
     require_device();
     Plan P;
-    P.oz_ns = c->z.oz_ns; P.oz_min_flops = c->z.oz_min_flops; P.nocc = c->z.nocc; P.nvir = c->z.nvir;
+    P.oz_ns = c->force_dmma ? 0 : c->z.oz_ns; P.oz_min_flops = c->z.oz_min_flops; P.nocc = c->z.nocc; P.nvir = c->z.nvir;
     P.oz_splitk_min_k = c->z.oz_splitk_min_k;
     c->ptr[S_A0] = (double*)A->ptr; c->ptr[S_A1] = (double*)B->ptr; c->ptr[S_B0] = (double*)C->ptr;
     P.contract(alpha, from_desc(A, S_A0), sa, from_desc(B, S_A1), sb, beta, from_desc(C, S_B0), sc, "op");

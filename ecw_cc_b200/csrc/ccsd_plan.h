@@ -37,7 +37,4 @@ void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
 void build_ccsd_gamma(Plan& P, const Sizes& z);
 void build_ccsd_energy(Plan& P, const Sizes& z);
 
-// CCS entry points (ccs_plan.cpp); returns false for an unknown function name
-bool build_ccs_plan(Plan& P, const Sizes& z, const std::string& func, int flags);
-
 }  // namespace ecw

@@ -171,10 +171,11 @@ __global__ void __launch_bounds__(EW_THREADS)
 tau_kernel(const double* __restrict__ t2, const double* __restrict__ t1, double* __restrict__ out, int o, int v,
            double c1, double c2) {
   const uint32_t vv = (uint32_t)v * (uint32_t)v;
-  const int i = blockIdx.y / o, j = blockIdx.y - i * o;
+  for (int64_t ij = blockIdx.y; ij < (int64_t)o * o; ij += gridDim.y) {      // grid-stride over the (i,j) rows
+  const int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
   const double* __restrict__ ti = t1 + (int64_t)i * v;
   const double* __restrict__ tj = t1 + (int64_t)j * v;
-  const int64_t row = (int64_t)blockIdx.y * vv;
+  const int64_t row = ij * vv;
   for (uint32_t ab = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; ab < vv; ab += gridDim.x * blockDim.x * VEC) {
     const uint32_t a = ab / (uint32_t)v, b = ab - a * (uint32_t)v;
     if constexpr (VEC == 2) {
@@ -187,6 +188,7 @@ tau_kernel(const double* __restrict__ t2, const double* __restrict__ t1, double*
     } else {
       out[row + ab] = t2[row + ab] + (c1 * (ti[a] * tj[b]) - c2 * (ti[b] * tj[a]));
     }
+  }
   }
 }
 
@@ -569,10 +571,10 @@ cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, i
                        cudaStream_t st) {
   int64_t total = (int64_t)o * o * v * v;
   if (total <= 0) return cudaSuccess;
-  if ((int64_t)o * o > 65535) return cudaErrorInvalidValue;
   const bool vec = (v % 2 == 0) && (reinterpret_cast<uintptr_t>(t2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const int64_t per = (int64_t)v * v / (vec ? 2 : 1);
-  dim3 grid((unsigned)std::min<int64_t>((per + EW_THREADS - 1) / EW_THREADS, 64), (unsigned)(o * o));
+  dim3 grid((unsigned)std::min<int64_t>((per + EW_THREADS - 1) / EW_THREADS, 64),
+            (unsigned)std::min<int64_t>((int64_t)o * o, 65535));
   if (vec) tau_kernel<2><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
   else tau_kernel<1><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
   return cudaGetLastError();

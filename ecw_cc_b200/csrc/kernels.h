@@ -65,6 +65,11 @@ cudaError_t launch_ozaki_gemm_batched(const int8_t* pa, const double* sa, int64_
                                       int64_t crs, int64_t ccs, double alpha, double beta, int ns, const OzBatch& bt,
                                       cudaStream_t st, int sm_count);
 
+// *out = max(*out, (ns+3) 256^-ns K |alpha| max s_m max s_n): worst-case absolute error of the product(s) above,
+// from the row scales actually present (a NaN scale, i.e. a non-finite operand row, yields NaN)
+cudaError_t launch_ozaki_bound(const double* sa, const double* sb, int64_t M, int64_t N, int64_t K, double alpha, int ns,
+                               const OzBatch& bt, double* out, cudaStream_t st);
+
 constexpr int KMAXD = 6;
 struct PermArgs {
   const double* in;

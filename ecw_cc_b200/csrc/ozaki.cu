@@ -137,8 +137,10 @@ struct OzGemmParams {
   uint32_t lbo, sbo;     // descriptor strides (bytes)
   // batch b = 0..batch-1 of independent products (OzBatch, kernels.h)
   OzBatch bt;
-  int debug;             // tools/oz_experiment.py only: bit 0 = the producer skips the loads (MMA on stale data),
-                         // bit 1 / 2 = A / B planes only, bit 4 = 15 of the 21 products
+#ifdef ECW_OZ_EXPERIMENT
+  int debug;             // tools/oz_experiment.py only (never in the product build): bit 0 = the producer skips the
+                         // loads (MMA on stale data), bit 1 / 2 = A / B planes only, bit 4 = 15 of the 21 products
+#endif
 };
 
 // tile columns: NS accumulators of TN int32 columns must fit the 512 TMEM columns; every MMA needs N % 16 == 0
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
           const uint32_t st = it % STAGES, use = it / STAGES;
           mbar_wait(&empty[st], (use & 1) ^ 1);
           unsigned char* s = smem + st * Cfg::STAGE;
+#ifdef ECW_OZ_EXPERIMENT
           if (p.debug & 1) { mbar_arrive(&full[st]); continue; }
           if (p.debug & 6) {           // experiments: bit 1 = A planes only, bit 2 = B planes only
             mbar_expect_tx(&full[st], NS * ((p.debug & 2) ? Cfg::A_PLANE : Cfg::B_PLANE));
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
             }
             continue;
           }
+#endif
           mbar_expect_tx(&full[st], Cfg::STAGE);
 #pragma unroll
           for (int d = 0; d < NS; ++d) {
@@ -268,7 +272,9 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
             // pd .. NS-1, which are contiguous too.  One MMA per <= 256 columns.
 #pragma unroll
             for (int pd = 0; pd < NS; ++pd) {
+#ifdef ECW_OZ_EXPERIMENT
               if ((p.debug & 16) && pd >= 3) continue;        // experiment: 15 of the 21 products
+#endif
               const uint64_t adesc = desc0 | (uint64_t)(((sa + pd * Cfg::A_PLANE) >> 4) & 0x3fff);
               const int ncols = TN * (NS - pd);
 #pragma unroll
@@ -383,11 +389,18 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
 // (fixed summation order) and, for a two-level contraction index k = (k1, k2), the partial sums per k1.
 // X[r*rs + k1*ks1 + k2*ks2]; stats = [scales (Rp) | row sums (Rp) | row sums per k1 (K1 x Rp) when K1 > 1]
 // with Rp the padded row count of the WHOLE plane set; the pointers passed here are offset to the chunk's first row.
+// A row that holds a NaN or an Inf gets the scale NaN: every product it takes part in is then NaN in the GEMM
+// epilogue (alpha * s_m * s_n * ...), as in an FP64 GEMM — the digits of such a row are meaningless.
 __device__ __forceinline__ double oz_scale_of(double mx) {
+  if (!(mx <= 1.7976931348623157e308)) return __longlong_as_double(0x7ff8000000000000ll);
   int e = 0;
   if (mx > 0.0) frexp(mx, &e);          // mx = f 2^e, f in [0.5, 1)
-  return mx > 0.0 ? ldexp(1.0, e) : 1.0;
+  // an all-zero (or padded) row: a scale so small that s_m s_n underflows to an exact 0 in the epilogue and the row
+  // does not count in the run-time error bound (ozaki_bound_kernel); its digits stand for 2D + c = 0 exactly
+  return mx > 0.0 ? ldexp(1.0, e) : 2.4099198651028841e-181 /* 2^-600 */;
 }
+// max that keeps a NaN once seen (fmax would drop it); a, b >= 0 or NaN
+__device__ __forceinline__ double oz_max(double a, double b) { return (b > a || b != b) ? b : a; }
 // one warp per row (k2 contiguous)
 __global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, int64_t K1, int64_t K2, int64_t rs,
                                       int64_t ks1, int64_t Rp_chunk, int64_t Rp, double* __restrict__ stats) {
@@ -403,12 +416,12 @@ __global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, i
       int64_t k = lane;
       for (; k + 96 < K2; k += 128) {                         // four independent loads in flight per lane
         const double v0 = x[k], v1 = x[k + 32], v2 = x[k + 64], v3 = x[k + 96];
-        mx = fmax(fmax(mx, fabs(v0)), fmax(fabs(v1), fmax(fabs(v2), fabs(v3))));
+        mx = oz_max(oz_max(mx, fabs(v0)), oz_max(oz_max(fabs(v1), fabs(v2)), fabs(v3)));
         sm += v0; s1 += v1; s2 += v2; s3 += v3;
       }
       for (; k < K2; k += 32) {
         const double v = x[k];
-        mx = fmax(mx, fabs(v));
+        mx = oz_max(mx, fabs(v));
         sm += v;
       }
       sm += s1 + s2 + s3;
@@ -419,7 +432,7 @@ __global__ void ozaki_rowstat_kcontig(const double* __restrict__ X, int64_t R, i
     if (K1 > 1 && lane == 0) stats[(2 + k1) * Rp + r] = sm;     // scaled below
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  for (int o = 16; o; o >>= 1) mx = oz_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) {
     const double s = oz_scale_of(mx);
     stats[r] = s;
@@ -447,12 +460,12 @@ __global__ void ozaki_rowstat_rcontig(const double* __restrict__ X, int64_t R, i
     int64_t k = kbeg + wy;
     for (; k + 8 < kend; k += 16) {
       const double v0 = x[k * ks2], v1 = x[(k + 8) * ks2];
-      mx = fmax(mx, fmax(fabs(v0), fabs(v1)));
+      mx = oz_max(oz_max(mx, fabs(v0)), fabs(v1));
       sm += v0; s1 += v1;
     }
     for (; k < kend; k += 8) {
       const double v = x[k * ks2];
-      mx = fmax(mx, fabs(v));
+      mx = oz_max(mx, fabs(v));
       sm += v;
     }
     sm += s1;
@@ -463,10 +476,11 @@ __global__ void ozaki_rowstat_rcontig(const double* __restrict__ X, int64_t R, i
   if (wy == 0 && r < Rp_chunk) {
 #pragma unroll
     for (int i = 1; i < 8; ++i) {
-      mx = fmax(mx, red[i][lane]);
+      mx = oz_max(mx, red[i][lane]);
       sm += reds[i][lane];
     }
-    atomicMax(reinterpret_cast<unsigned long long*>(stats + r), (unsigned long long)__double_as_longlong(mx));
+    // bit patterns of non-negative doubles order like integers; +Inf and (positive) NaN sort above every finite value
+    atomicMax(reinterpret_cast<unsigned long long*>(stats + r), (unsigned long long)__double_as_longlong(fabs(mx)));
     part[(k1 * C2 + c) * Rp + r] = sm;
   }
 }
@@ -562,6 +576,32 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
   }
 }
 
+// Run-time error bound of one (batched) product: (NS+3) 256^-NS K |alpha| max_m s_m max_n s_n over the rows the
+// product reads (header comment: representation + triangular truncation), combined into *out with an atomic max on
+// the bit pattern (non-negative doubles order like integers; a NaN scale — non-finite operand — sorts on top).
+__global__ void __launch_bounds__(1024) ozaki_bound_kernel(const double* __restrict__ sa, int64_t a_row0, int64_t a_rowb,
+                                                           int64_t M, const double* __restrict__ sb, int64_t b_row0,
+                                                           int64_t b_rowb, int64_t N, int64_t batch, double factor,
+                                                           double* out) {
+  __shared__ double ra[32], rb[32];
+  double ma = 0.0, mb = 0.0;
+  const int64_t na = (a_rowb ? batch : 1) * M, nb = (b_rowb ? batch : 1) * N;
+  for (int64_t i = threadIdx.x; i < na; i += blockDim.x) ma = oz_max(ma, fabs(sa[a_row0 + (i / M) * a_rowb + i % M]));
+  for (int64_t i = threadIdx.x; i < nb; i += blockDim.x) mb = oz_max(mb, fabs(sb[b_row0 + (i / N) * b_rowb + i % N]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    ma = oz_max(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    mb = oz_max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+  }
+  if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = ma; rb[threadIdx.x >> 5] = mb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { ma = oz_max(ma, ra[w]); mb = oz_max(mb, rb[w]); }
+    const double bound = fabs(factor * ma * mb);
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(bound));
+  }
+}
+
 template <int NS, int TN>
 cudaError_t launch_gemm_ns_tn(OzGemmParams p, cudaStream_t st, int sm_count) {
   using Cfg = OzCfg<NS, TN>;
@@ -654,8 +694,10 @@ cudaError_t launch_ozaki_gemm_batched(const int8_t* pa, const double* sa, int64_
   p.bt = bt;
   if (bt.batch < 1 || ((bt.a_row0 | bt.a_rowb | bt.b_row0 | bt.b_rowb) & 7)) return cudaErrorInvalidValue;
   if (sm_count <= 0) sm_count = 148;
+#ifdef ECW_OZ_EXPERIMENT
   if (const char* e = getenv("ECW_OZ_DEBUG")) p.debug = atoi(e);
   if (const char* e = getenv("ECW_OZ_GRID")) sm_count = atoi(e);
+#endif
   switch (ns) {
     case 3: return launch_gemm_ns<3>(p, st, sm_count);
     case 4: return launch_gemm_ns<4>(p, st, sm_count);
@@ -665,6 +707,14 @@ cudaError_t launch_ozaki_gemm_batched(const int8_t* pa, const double* sa, int64_
     case 8: return launch_gemm_ns<8>(p, st, sm_count);
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ozaki_bound(const double* sa, const double* sb, int64_t M, int64_t N, int64_t K, double alpha, int ns,
+                               const OzBatch& bt, double* out, cudaStream_t st) {
+  if (!out || bt.batch < 1) return cudaErrorInvalidValue;
+  const double factor = (double)(ns + 3) * ldexp(1.0, -8 * ns) * (double)K * fabs(alpha);
+  ozaki_bound_kernel<<<1, 1024, 0, st>>>(sa, bt.a_row0, bt.a_rowb, M, sb, bt.b_row0, bt.b_rowb, N, bt.batch, factor, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_ozaki_gemm(const int8_t* pa, const double* sa, const int8_t* pb, const double* sb, int64_t M, int64_t N,

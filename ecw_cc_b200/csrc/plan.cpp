@@ -619,6 +619,10 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
                           cut + 2e-5;
       // the DMMA kernels reach ~30 TFLOP/s on large plain GEMMs, ~18 on split-K / few-tile shapes
       oz = fl >= oz_min_flops && t_oz < 0.8 * fl / (S > 1 ? 1.8e13 : 3.0e13);
+    } else if (oz && oz_min_flops < -1.5) {
+      // test configuration: a pure flop threshold -oz_min_flops without the time model, so that small shapes can be
+      // given the routing the benchmark shape has (ladders, rings, R4/R6/R9 on the INT8 pipe, the rest on DMMA)
+      oz = fl >= -oz_min_flops;
     }
     if (const_planes && !(oz_ns > 0 && ch.bcls == 0 && ch.a_dir && ch.b_dir))
       throw PlanError("contract: an operand is bound as digit planes but the contraction is not a plain GEMM: " + tag);

@@ -92,8 +92,22 @@ class DevOps(object):
             out = self.empty(*[dims[ch] for ch in sc])
             beta = 0.0
         da, db, dc = _desc(A), _desc(B), _desc(out)
-        self._call(lib.ecw_op_contract, _scalar(alpha), _ref(da), sa.encode(), _ref(db), sb.encode(), _scalar(beta),
-                   _ref(dc), sc.encode())
+        args = (_scalar(alpha), _ref(da), sa.encode(), _ref(db), sb.encode(), _scalar(beta), _ref(dc), sc.encode())
+        self._call(lib.ecw_op_contract, *args)
+        e = self.e
+        if e.int8_digits and e.int8_tol > 0.0 and 2.0 * A.numel() * B.numel() >= e.int8_min_flops >= 0.0:
+            # a contraction this large may have taken the INT8 route (2MNK <= 2|A||B|): accuracy guard (eris.py)
+            b = e.last_bound = e.int8_bound()
+            if b == b and b > e.int8_tol:
+                e.guard_trips += 1
+                if _scalar(beta) != 0.0:
+                    raise EcwError("ecw_op_contract: INT8 error bound %.2e > %.1e on an accumulating contraction; "
+                                   "use more digits (int8_digits) or gemm='dmma'" % (b, e.int8_tol))
+                e.check(lib.ecw_ctx_set_engine_override(e._h, 1), "ecw_ctx_set_engine_override")
+                try:
+                    self._call(lib.ecw_op_contract, *args)
+                finally:
+                    lib.ecw_ctx_set_engine_override(e._h, 0)
         return out
 
     def axpby(self, alpha, A, sa, beta, C, sc):

@@ -28,6 +28,11 @@ SYNTH_KIND = dict(oooo=0, ooov=1, oovv=2, oovv_ph=3, ovov_ph=4, ovvv=5, oooo_p=6
 # Environment overrides for experiments: ECW_GEMM, ECW_INT8_DIGITS, ECW_INT8_MIN_FLOPS (-1: every GEMM).
 INT8_MIN_FLOPS = 2e10
 AUTO_DIGIT_BOUND = 5e-11
+# Run-time guard (include/ecw_b200.h, ecw_int8_error_bound): after every call the worst-case absolute error of its INT8
+# products, (NS+3) 256^-NS K |alpha| max s_m max s_n from the row scales actually cut, is read back.  Above INT8_TOL the
+# call is repeated on the FP64 DMMA kernels when the FP64 integral layouts are on the device (containers built with
+# from_geris, or synthetic(..., keep_fp64_vvvv=True)); otherwise it fails loudly (rebuild with more digits).
+INT8_TOL = 1e-11
 
 
 def auto_digits(nvir, eri_max):
@@ -57,11 +62,28 @@ def _torch():
     return torch
 
 
+class TorchDistComm(object):
+    """Collectives of a sharded call over torch.distributed (NCCL over NVLink between the GPUs of one box)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def all_gather(self, eris, recv, send):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+
+    def max_scalar(self, eris, x):
+        """max over ranks of a one-element device tensor -> float"""
+        import torch.distributed as dist
+        dist.all_reduce(x, op=dist.ReduceOp.MAX, group=self.group)
+        return float(x.cpu()[0])
+
+
 class DeviceEris(object):
     """Owns the C context, the bound integral layouts and the workspace."""
 
     def __init__(self, nocc, nvir, device=None, rank=0, world=1, group=None, gemm=None, int8_digits=None,
-                 int8_min_flops=None, eri_max=1.0, ovvv_planes=None):
+                 int8_min_flops=None, eri_max=1.0, ovvv_planes=None, int8_tol=None):
         """rank/world/group: one process per GPU; `vvvv_p` is then row-sharded over the packed
         virtual pair index and the heavy contractions are distributed (include/ecw_b200.h).
         gemm: "int8" | "dmma"; int8_digits: None = chosen from eri_max = max |<pq||rs>| (module header)."""
@@ -69,6 +91,7 @@ class DeviceEris(object):
         self.nocc = int(nocc)
         self.nvir = int(nvir)
         self.rank, self.world, self.group = int(rank), int(world), group
+        self.comm = TorchDistComm(group)     # who performs the collectives of a sharded call (tests: virtual ranks)
         self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
         self._h = ctypes.c_void_p()
         if lib.ecw_ctx_create(ctypes.byref(self._h), self.nocc, self.nvir) != 0:
@@ -81,6 +104,9 @@ class DeviceEris(object):
         if ovvv_planes is None:
             ovvv_planes = os.environ.get("ECW_OVVV_PLANES", "1") != "0"
         self.use_ovvv_planes = bool(ovvv_planes and self.int8_digits and self.nocc % 8 == 0 and self.nvir % 8 == 0)
+        self.int8_tol = float(os.environ.get("ECW_INT8_TOL", INT8_TOL) if int8_tol is None else int8_tol)
+        self.guard_trips = 0      # calls whose INT8 error bound exceeded int8_tol (each was repeated on DMMA)
+        self.last_bound = 0.0
         self.buf = {}
         self._ws = None
         self._scal = torch.zeros(16, dtype=torch.float64, device=self.device)
@@ -132,7 +158,7 @@ class DeviceEris(object):
 
     def run(self, rc, what):
         """Drive a (possibly distributed) call to completion: while the library reports a pending
-        collective, perform it with torch.distributed (NCCL) on the workspace and resume."""
+        collective, perform it through `self.comm` (default: torch.distributed / NCCL on the workspace) and resume."""
         torch = _torch()
         while rc == 1:
             desc = (ctypes.c_int64 * 6)()
@@ -141,11 +167,51 @@ class DeviceEris(object):
             kind, soff, count, roff, world, rank = [int(x) for x in desc]
             if kind != 1 or world != self.world:
                 raise EcwError("%s: unexpected collective %r" % (what, list(desc)))
-            import torch.distributed as dist
             ws = self._ws.view(torch.float64)
-            dist.all_gather_into_tensor(ws[roff: roff + world * count], ws[soff: soff + count], group=self.group)
+            self.comm.all_gather(self, ws[roff: roff + world * count], ws[soff: soff + count])
             rc = lib.ecw_resume(self._h, self.stream())
         self.check(rc, what)
+
+    # -- guarded execution of one C entry point ----------------------------------------
+    def int8_bound(self):
+        """Worst-case absolute error of the INT8 products of the last call (max over ranks); NaN when an operand
+        held a non-finite value."""
+        torch = _torch()
+        if self.world > 1:
+            b = self._scal[15:16].clone()
+            b = torch.where(torch.isnan(b), torch.full_like(b, float("inf")), b)
+            v = self.comm.max_scalar(self, b)
+            return float("nan") if v == float("inf") else v
+        out = ctypes.c_double(0.0)
+        self.check(lib.ecw_int8_error_bound(self._h, ctypes.byref(out), self.stream()), "ecw_int8_error_bound")
+        return out.value
+
+    def can_dmma(self):
+        """The FP64 layouts the DMMA plans read are on the device."""
+        return "vvvv_p" in self.buf and "ovvv_p" in self.buf
+
+    def execute(self, func, flags, launch, what):
+        """ensure_workspace + launch() (a closure around the C entry point, returns its rc) + the INT8 accuracy
+        guard: when the bound of the call exceeds int8_tol the same call is repeated without the INT8 route."""
+        self.ensure_workspace(func, flags)
+        self.run(launch(), what)
+        if not self.int8_digits or not self.int8_tol > 0.0:
+            return
+        b = self.last_bound = self.int8_bound()
+        if b != b or b <= self.int8_tol:        # NaN: non-finite operands; the outputs are NaN as in the reference
+            return
+        self.guard_trips += 1
+        if not self.can_dmma():
+            raise EcwError("%s: the INT8 engine cannot guarantee its accuracy for these operands (worst-case error "
+                           "bound %.2e > %.1e with %d digits) and the FP64 integral layouts are not on the device: "
+                           "build the container with int8_digits=%d or gemm='dmma'"
+                           % (what, b, self.int8_tol, self.int8_digits, min(self.int8_digits + 1, 8)))
+        self.check(lib.ecw_ctx_set_engine_override(self._h, 1), "ecw_ctx_set_engine_override")
+        try:
+            self.ensure_workspace(func, flags)
+            self.run(launch(), what + " (FP64 DMMA after the INT8 guard)")
+        finally:
+            lib.ecw_ctx_set_engine_override(self._h, 0)
 
     def set_fock(self, fock):
         torch = _torch()
@@ -155,7 +221,7 @@ class DeviceEris(object):
     # -- constructors ----------------------------------------------------------
     @classmethod
     def from_geris(cls, eris, device=None, rank=0, world=1, group=None, gemm=None, int8_digits=None,
-                   int8_min_flops=None, ovvv_planes=None):
+                   int8_min_flops=None, ovvv_planes=None, int8_tol=None):
         """Upload a reference-style container (numpy blocks, Eris.py:132-150)."""
         torch = _torch()
         fock = np.asarray(eris.fock)
@@ -163,7 +229,8 @@ class DeviceEris(object):
         eri_max = max(float(np.abs(np.asarray(getattr(eris, k))).max()) if np.asarray(getattr(eris, k)).size else 0.0
                       for k in ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv"))
         self = cls(nocc, fock.shape[0] - nocc, device, gemm=gemm, int8_digits=int8_digits,
-                   int8_min_flops=int8_min_flops, eri_max=eri_max, ovvv_planes=ovvv_planes)   # packed whole, sharded below
+                   int8_min_flops=int8_min_flops, eri_max=eri_max, ovvv_planes=ovvv_planes,
+                   int8_tol=int8_tol)   # packed whole, sharded below
         self.set_fock(fock)
         for name in ("oooo", "ooov", "oovv", "ovvv"):
             t = torch.from_numpy(np.ascontiguousarray(getattr(eris, name), dtype=np.float64)).to(self.device)
@@ -178,6 +245,7 @@ class DeviceEris(object):
         torch.cuda.current_stream(self.device).synchronize()
         if world > 1:
             self.rank, self.world, self.group = int(rank), int(world), group
+            self.comm = TorchDistComm(group)
             if lib.ecw_ctx_set_shard(self._h, self.rank, self.world) != 0:
                 raise EcwError("ecw_ctx_set_shard failed")
             pv = self.nvir * (self.nvir - 1) // 2
@@ -201,13 +269,13 @@ class DeviceEris(object):
 
     @classmethod
     def synthetic(cls, nocc, nvir, device=None, scale=0.01, rank=0, world=1, group=None, gemm=None,
-                  int8_digits=None, int8_min_flops=None, keep_fp64_vvvv=False, ovvv_planes=None):
+                  int8_digits=None, int8_min_flops=None, keep_fp64_vvvv=False, ovvv_planes=None, int8_tol=None):
         """Function-defined synthetic integrals generated in place on the device (each rank
         generates only its own rows of the packed vvvv).  With the INT8 engine the packed vvvv is
         generated in row chunks and kept as digit planes only (keep_fp64_vvvv: also the FP64 layout)."""
         torch = _torch()
         self = cls(nocc, nvir, device, rank=rank, world=world, group=group, gemm=gemm, int8_digits=int8_digits,
-                   int8_min_flops=int8_min_flops, eri_max=abs(float(scale)), ovvv_planes=ovvv_planes)
+                   int8_min_flops=int8_min_flops, eri_max=abs(float(scale)), ovvv_planes=ovvv_planes, int8_tol=int8_tol)
         planes_only = bool(self.int8_digits) and not keep_fp64_vvvv
         for name in _LAYOUTS:
             if name == "vvvv_p" and planes_only:

@@ -55,12 +55,23 @@ const char* ecw_version(void);
 int ecw_ctx_set_shard(ecw_ctx* ctx, int rank, int world);
 int ecw_resume(ecw_ctx* ctx, void* stream);
 /* GEMM engine.  int8_digits = 0: every contraction runs on the FP64 DMMA kernels.  int8_digits = 3..8:
- * unbatched GEMMs with 2MNK >= min_flops (negative: all of them) run on the INT8 tcgen05 tensor pipe by
+ * unbatched GEMMs with 2MNK >= min_flops for which the time model of the engine prefers it (min_flops = -1: all of
+ * them; min_flops = -t < -1.5: those with 2MNK >= t, no time model — tests) run on the INT8 tcgen05 tensor pipe by
  * splitting the operands into that many base-256 int8 digits (csrc/ozaki.cu; 6 digits = 48 bits,
  * |err| <= 2^-42.8 K max|A_row| max|B_row| worst case, the size of an FP64 dot product's own rounding error).  Replaces the BLAS dgemm behind numpy/pyscf einsum
  * (CCSD.py:25).  A context starts with int8_digits = 0. */
 int ecw_ctx_set_gemm(ecw_ctx* ctx, int int8_digits, double min_flops);
 int ecw_ctx_get_gemm(ecw_ctx* ctx);
+/* Run-time accuracy guard of the INT8 route.  Every INT8 product of a call adds (max) its worst-case absolute error
+ *   (int8_digits + 3) 256^-int8_digits K |alpha| max_m s_m max_n s_n
+ * — computed on the device from the power-of-two row scales s_r > max|row| of the operands actually multiplied — to a
+ * device scalar that is reset when a call starts; ecw_int8_error_bound reads it back (synchronises the stream).  NaN:
+ * an operand held a non-finite value (its rows get the scale NaN, so the affected outputs are NaN as in FP64).
+ * ecw_ctx_set_engine_override(ctx, 1) makes the following calls run their plans without the INT8 route (FP64 DMMA
+ * kernels; needs the FP64 layouts "vvvv_p" / "ovvv_p" bound) — the host re-runs a call this way when the bound
+ * exceeds its tolerance (ecw_cc_b200/eris.py: INT8_TOL); 0 restores the configured engine. */
+int ecw_int8_error_bound(ecw_ctx* ctx, double* bound_out, void* stream);
+int ecw_ctx_set_engine_override(ecw_ctx* ctx, int force_dmma);
 /* INT8 products with fewer output tiles than SMs and a contraction length >= min_k (a multiple of 32) are cut into
  * equal K chunks, one product each, summed in a fixed order (default 65536; <= 0: never). */
 int ecw_ctx_set_int8_splitk(ecw_ctx* ctx, int64_t min_k);

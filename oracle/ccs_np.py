@@ -284,6 +284,27 @@ class OracleGccs(object):
         P = np.trace(vm[:no, :no]) + _e('jb,jb', ts, vm[:no, no:])
         return Fjb, E, P
 
+    def Extract_r0(self, r1, ts, fsp, vm):                     # CCS.py:1036-1079
+        """r0 from the R1 and R0 equations for a given r1.  Kept as the reference has it: the roots are divided by c
+        (not 2a), `return 0` when c == 0., ValueError when both roots are negative."""
+        f = self.fock if fsp is None else fsp.copy()
+        Fab, Fji, W, F, Zia, Pia = self.R1inter(ts, f, vm)
+        Fjb, Z, P = self.R0inter(ts, f, vm)
+        R1 = self._r1core(r1, Fab, Fji, W) + r1 * F + Pia
+        c = -_e('jb,jb', r1, Fjb) - P
+        if c == 0.:
+            return 0
+        i, j = np.unravel_index(np.argmax(abs(r1), axis=None), r1.shape)
+        a = Zia[i, j] / r1[i, j]
+        b = R1[i, j] / r1[i, j] - Z
+        r0_1 = (-b + np.sqrt((b ** 2) - (4 * a * c))) / c
+        r0_2 = (-b - np.sqrt((b ** 2) - (4 * a * c))) / c
+        if r0_1 > 0:
+            return r0_1
+        elif r0_2 > 0:
+            return r0_2
+        raise ValueError('Both solution for r0 are negative')
+
     def r0update(self, rs, r0, Em, R0inter):                   # CCS.py:1081-1096
         Fjb, E, P = R0inter
         return (_e('jb,jb', rs, Fjb) + P + r0 * E) / Em

@@ -21,16 +21,17 @@ SWEEPS = [("plain", None), ("l1", 2e-4)]                           # (tag, alpha
 CONV, MAXITER = 1e-8, 25
 
 
-def sweep(Solver_CCSD, GCC, Exp, er, alpha, device=False):
+def sweep(Solver_CCSD, GCC, Exp, er, alpha, device=False, larray=None, maxiter=MAXITER):
     """The L loop of Main.CCSD_GS; `device` keeps the amplitudes on the GPU between L values (product only)."""
+    larray = LARRAY if larray is None else larray
     o, v = er.nocc, er.fock.shape[0] - er.nocc
     hf = np.diag(er.mo_occ)
-    vx = Exp(LARRAY[0], [[["mat", target_rdm1(o, v)]]], None, None, HF_prop=[[hf]])
+    vx = Exp(larray[0], [[["mat", target_rdm1(o, v)]]], None, None, HF_prop=[[hf]])
     solver = Solver_CCSD(GCC(er), vx, conv="tl", conv_thres=CONV, tsini=np.zeros((o, v)), lsini=np.zeros((o, v)),
-                         diis="tl", maxdiis=15, maxiter=MAXITER)
+                         diis="tl", maxdiis=15, maxiter=maxiter)
     ts, ls, td, ld = np.zeros((o, v)), np.zeros((o, v)), None, None
     out = []
-    for L in LARRAY:
+    for L in larray:
         kw = {"return_device": True} if device else {}
         res = solver.SCF(L, ts=ts, ls=ls, td=td, ld=ld, alpha=alpha, **kw)
         ts, ls, td, ld = res[5]
@@ -48,9 +49,9 @@ def pack(results, tag, out):
         out[tag + "_final_" + name] = np.asarray(a.cpu().numpy() if hasattr(a, "cpu") else a)
 
 
-def acetylene(scf=None):
+def acetylene(scf=None, basis="6-31g"):
     from ecw_cc_b200 import molint
-    mol = molint.Molecule(C2H2, "6-31g")
+    mol = molint.Molecule(C2H2, basis)
     ints = molint.integrals(mol)
     if scf is None:
         scf = molint.rhf(mol, ints)

@@ -22,11 +22,14 @@ def pair_decode(n):
 
 
 # ---- INT8-pipe GEMM (csrc/ozaki.cu): numpy statement of the digit cut and the device plane order
+ZERO_ROW_SCALE = 2.0 ** -600
+
+
 def oz_scale(X):
-    """power-of-two row scales s_r > max|X[r,:]| (1 for an all-zero row)."""
+    """power-of-two row scales s_r > max|X[r,:]| (2^-600 for an all-zero row: its products underflow to exact zeros)."""
     mx = np.abs(X).max(axis=1) if X.shape[1] else np.zeros(X.shape[0])
     _, e = np.frexp(mx)
-    return np.where(mx > 0, np.ldexp(1.0, e), 1.0)
+    return np.where(mx > 0, np.ldexp(1.0, e), ZERO_ROW_SCALE)
 
 
 def oz_cprime(ns):
@@ -74,7 +77,7 @@ def oz_stats(X, s, K1=1):
     R = X.shape[0]
     Rp = (R + 127) // 128 * 128
     st = np.zeros((2 + K1 if K1 > 1 else 2) * Rp)
-    st[:Rp] = 1.0
+    st[:Rp] = ZERO_ROW_SCALE
     st[:R] = s
     st[Rp: Rp + R] = X.sum(axis=1) / s
     if K1 > 1:

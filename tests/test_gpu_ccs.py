@@ -99,3 +99,22 @@ def test_ccs_gs_loop_tracks_oracle(built_lib):
                 outs.append((ts, ls, cc.gamma(ts, ls), cc.energy_ccs(ts, fsp)))
             for x, y in zip(outs[0], outs[1]):
                 assert np.abs(np.asarray(x) - np.asarray(y)).max() < TOL, (alpha, it)
+
+
+def test_extract_r0_matches_reference_fixture(built_lib, engine):
+    """`Gccs.Extract_r0` (CCS.py:1036-1079) against outputs of the unmodified reference: same values
+    (relative 1e-10: the roots divide by a small c), same ValueError cases."""
+    import ecw_cc_b200 as ecw
+    from oracle import synth
+    from oracle.make_golden import ccs_inputs
+    from oracle.make_golden_ccs_r0 import SIZES, call, r1_variants
+    g = load_golden("ccs_extract_r0.npz")
+    for o, v in SIZES:
+        cc = ecw.Gccs(synth.SynthEris(o, v))
+        d = ccs_inputs(o, v)
+        got = [call(cc, r1, d, vm) for vm in (d["vm"], d["vm2"]) for r1 in r1_variants(d)]
+        got.append(call(cc, d["rs"], dict(d, fsp=None), d["vm"]))
+        want, stat = g["r0_o%dv%d" % (o, v)], g["status_o%dv%d" % (o, v)]
+        assert [s for _, s in got] == list(stat)
+        for (x, s), w in zip(got, want):
+            assert s == 1 or abs(x - w) < TOL * max(1.0, abs(w))

@@ -72,3 +72,21 @@ def test_l0_fromE_energy_argument_quirk():
         en = np.array([0.3])
         l0 = cc.l0_fromE(en, ts, ls, None)
         assert abs(en[0] - (0.3 - shift)) < 1e-15 and abs(float(np.ravel(l0)[0]) - float(cc.l0_fromE(0.3, ts, ls, None))) < 1e-14
+
+
+def test_extract_r0_oracle_matches_reference_fixture():
+    """`Gccs.Extract_r0` (CCS.py:1036-1079): the oracle against outputs of the unmodified reference
+    (tests/golden/ccs_extract_r0.npz, oracle/make_golden_ccs_r0.py), both root branches and the ValueError."""
+    from oracle import ccs_np, synth
+    from oracle.make_golden import ccs_inputs
+    from oracle.make_golden_ccs_r0 import SIZES, call, r1_variants
+    g = load_golden("ccs_extract_r0.npz")
+    for o, v in SIZES:
+        cc = ccs_np.OracleGccs(synth.SynthEris(o, v))
+        d = ccs_inputs(o, v)
+        got = [call(cc, r1, d, vm) for vm in (d["vm"], d["vm2"]) for r1 in r1_variants(d)]
+        got.append(call(cc, d["rs"], dict(d, fsp=None), d["vm"]))
+        want, stat = g["r0_o%dv%d" % (o, v)], g["status_o%dv%d" % (o, v)]
+        assert [s for _, s in got] == list(stat) and 0 in stat and 1 in stat
+        for (x, s), w in zip(got, want):
+            assert s == 1 or abs(x - w) < 1e-10 * max(1.0, abs(w))
