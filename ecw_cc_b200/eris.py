@@ -31,8 +31,10 @@ AUTO_DIGIT_BOUND = 5e-11
 # Run-time guard (include/ecw_b200.h, ecw_int8_error_bound): after every call the worst-case absolute error of its INT8
 # products, (NS+3) 256^-NS K |alpha| max s_m max s_n from the row scales actually cut, is read back.  Above INT8_TOL the
 # call is repeated on the FP64 DMMA kernels when the FP64 integral layouts are on the device (containers built with
-# from_geris, or synthetic(..., keep_fp64_vvvv=True)); otherwise it fails loudly (rebuild with more digits).
-INT8_TOL = 1e-11
+# from_geris, or synthetic(..., keep_fp64_vvvv=True)); otherwise it fails loudly (rebuild with more digits).  The bound
+# is a strict worst case (every digit error aligned): half the 1e-10 parity bar; observed errors are >= 100x smaller
+# (they add like a random walk over K: profiles/r1_engine_check_40_400.json, 1.8e-12 at the benchmark shape).
+INT8_TOL = 5e-11
 
 
 def auto_digits(nvir, eri_max):
@@ -106,7 +108,8 @@ class DeviceEris(object):
         self.use_ovvv_planes = bool(ovvv_planes and self.int8_digits and self.nocc % 8 == 0 and self.nvir % 8 == 0)
         self.int8_tol = float(os.environ.get("ECW_INT8_TOL", INT8_TOL) if int8_tol is None else int8_tol)
         self.guard_trips = 0      # calls whose INT8 error bound exceeded int8_tol (each was repeated on DMMA)
-        self.last_bound = 0.0
+        self.last_bound = 0.0     # bound of the last guarded call / the largest one seen so far
+        self.max_bound = 0.0
         self.buf = {}
         self._ws = None
         self._scal = torch.zeros(16, dtype=torch.float64, device=self.device)
@@ -199,6 +202,7 @@ class DeviceEris(object):
             return
         b = self.last_bound = self.int8_bound()
         if b != b or b <= self.int8_tol:        # NaN: non-finite operands; the outputs are NaN as in the reference
+            self.max_bound = max(self.max_bound, b) if b == b else self.max_bound
             return
         self.guard_trips += 1
         if not self.can_dmma():
