@@ -5,7 +5,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libecw_b200.so")
-_SRC = ["gemm.cu", "gemm_tma.cu", "ewise.cu", "ozaki.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp"]
+_SRC = ["gemm.cu", "gemm_tma.cu", "ewise.cu", "ozaki.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp", "ccsd_plan_slab.cpp"]
 
 ECW_HAS_ALPHA = 1
 ECW_EQUATION = 2
@@ -21,7 +21,7 @@ def build(force=False, verbose=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU).
     One object per source under csrc/build/ (recompiled only when stale), then one link."""
     csrc = os.path.join(_HERE, "csrc")
-    hdrs = [os.path.join(csrc, h) for h in ("plan.h", "kernels.h", "ccsd_plan.h")]
+    hdrs = [os.path.join(csrc, h) for h in ("plan.h", "kernels.h", "ccsd_plan.h", "ccsd_plan_detail.h")]
     hdrs.append(os.path.join(_HERE, "..", "include", "ecw_b200.h"))
     hdr_mt = max(os.path.getmtime(h) for h in hdrs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -75,6 +75,7 @@ class _Lib(object):
             "ecw_ctx_get_gemm": (c_i, [c_p]),
             "ecw_int8_error_bound": (c_i, [c_p, ctypes.POINTER(c_d), c_p]),
             "ecw_ctx_set_engine_override": (c_i, [c_p, c_i]),
+            "ecw_ctx_set_plan_variant": (c_i, [c_p, c_i]),
             "ecw_ctx_set_int8_splitk": (c_i, [c_p, c_l]),
             "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),
             "ecw_ctx_test_assume_ovvv_planes": (c_i, [c_p]),

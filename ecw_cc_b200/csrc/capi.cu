@@ -155,7 +155,11 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
         break;
       case OP_TAU:
         ck(launch_tau(resolve(c, op.a), resolve(c, op.b), resolve(c, op.c), (int)op.b.dim[0], (int)op.b.dim[1],
-                      op.alpha, op.beta, st), "tau");
+                      op.alpha, op.beta, st, op.i2 ? (int)op.i0 : 0, op.i2 ? (int)op.i1 : -1), "tau");
+        break;
+      case OP_ASYM4:
+        ck(launch_asym4(op.b.valid() ? resolve(c, op.b) : nullptr, op.alpha, resolve(c, op.a), resolve(c, op.c), op.beta,
+                        (int)op.c.dim[0], (int)op.c.dim[2], st), "asym4");
         break;
       case OP_PACK: {
         PackArgs a{};
@@ -202,9 +206,10 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
       case OP_EWISE:
         exec_ewise(c, op, st);
         break;
-      case OP_ALLGATHER: {
+      case OP_ALLGATHER:
+      case OP_ALLTOALL: {
         if (op.a.slot != S_WS || op.c.slot != S_WS) throw Fail("collective operands must live in the workspace");
-        c->pending[0] = 1;                 // kind: all-gather
+        c->pending[0] = op.kind == OP_ALLTOALL ? 2 : 1;     // kind: 1 all-gather, 2 all-to-all
         c->pending[1] = op.a.off;          // element offset of this rank's contribution in the workspace
         c->pending[2] = op.i0;             // elements per rank
         c->pending[3] = op.c.off;          // element offset of the gathered buffer (world * count elements)
@@ -368,6 +373,13 @@ int ecw_ctx_set_engine_override(ecw_ctx* c, int force_dmma) {
   if (!c) return -1;
   c->force_dmma = force_dmma != 0;
   c->run_plan_ptr = nullptr;
+  return 0;
+}
+
+int ecw_ctx_set_plan_variant(ecw_ctx* c, int legacy_packed) {
+  if (!c) return -1;
+  c->z.legacy_packed = legacy_packed != 0;
+  drop_plans(c);
   return 0;
 }
 
@@ -649,7 +661,8 @@ int64_t ecw_plan_launches(ecw_ctx* c, const char* func, int flags) {
   guarded(c, [&] {
     const Plan& P = get_plan(c, func, flags);
     int64_t n = 0;
-    for (auto& op : P.ops) n += (op.kind == OP_DOT || op.kind == OP_OZ_SPLIT) ? 2 : (op.kind == OP_ALLGATHER ? 0 : 1);
+    for (auto& op : P.ops)
+      n += (op.kind == OP_DOT || op.kind == OP_OZ_SPLIT) ? 2 : ((op.kind == OP_ALLGATHER || op.kind == OP_ALLTOALL) ? 0 : 1);
     r = n;
   });
   return r;
@@ -904,7 +917,8 @@ int64_t ecw_profile_dump(ecw_ctx* c, char* buf, int64_t buflen) {
     if (!c->last_plan || c->ev.empty()) throw Fail("no profiled run");
     ck(cudaEventSynchronize(c->ev.back()), "cudaEventSynchronize");
     static const char* kn[] = {"gemm", "reduce", "permute", "fill", "tau", "pack", "unpack", "finish",
-                               "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather", "oz_split", "oz_gemm"};
+                               "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather", "oz_split", "oz_gemm",
+                               "asym4", "alltoall"};
     std::ostringstream o;
     o << "[";
     for (size_t i = 0; i < c->last_plan->ops.size(); ++i) {

@@ -169,11 +169,12 @@ reduce_kernel(const double* __restrict__ part, int64_t nz, int64_t M, int64_t N,
 template <int VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 tau_kernel(const double* __restrict__ t2, const double* __restrict__ t1, double* __restrict__ out, int o, int v,
-           double c1, double c2) {
+           double c1, double c2, int i0, int ni) {
+  // t2 / out hold the rows i0 .. i0+ni-1 of the leading occupied index (a slab; i0 = 0, ni = o: everything)
   const uint32_t vv = (uint32_t)v * (uint32_t)v;
-  for (int64_t ij = blockIdx.y; ij < (int64_t)o * o; ij += gridDim.y) {      // grid-stride over the (i,j) rows
+  for (int64_t ij = blockIdx.y; ij < (int64_t)ni * o; ij += gridDim.y) {     // grid-stride over the (i,j) rows
   const int i = (int)(ij / o), j = (int)(ij - (int64_t)i * o);
-  const double* __restrict__ ti = t1 + (int64_t)i * v;
+  const double* __restrict__ ti = t1 + (int64_t)(i + i0) * v;
   const double* __restrict__ tj = t1 + (int64_t)j * v;
   const int64_t row = ij * vv;
   for (uint32_t ab = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; ab < vv; ab += gridDim.x * blockDim.x * VEC) {
@@ -567,16 +568,89 @@ cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, 
   return cudaGetLastError();
 }
 
+// out[ijab] = c0 base[ijab] + z[ijab] - z[jiab] - z[ijba] + z[jiba] + beta out[ijab]   (P(ij)P(ab) z, CCSD.py:306-310,
+// 475-477: the antisymmetriser of the doubles residuals).  One block per (pair i <= j, 32x32 tile pair A <= B of (a,b)):
+// with D = z_ij - z_ji the four images are out_ij[A,B] = +D[A,B] - D[B,A]^T, out_ij[B,A] = -(that)^T, out_ji = -out_ij,
+// so every element of z is read once and every element of out written once.
+__global__ void __launch_bounds__(256) asym4_kernel(const double* __restrict__ base, double c0, const double* __restrict__ z,
+                                                    double* __restrict__ out, double beta, int o, int v) {
+  __shared__ double tAB[32][33], tBA[32][33];
+  const int nt = (v + 31) / 32;
+  // blockIdx.x -> tile pair (A <= B); blockIdx.y -> occupied pair (i <= j), grid-stride
+  int tA = 0, rem = blockIdx.x;
+  while (rem >= nt - tA) { rem -= nt - tA; ++tA; }
+  const int tB = tA + rem;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+  const int64_t vv = (int64_t)v * v;
+  const int64_t npair = (int64_t)o * (o + 1) / 2;
+  for (int64_t pr = blockIdx.y; pr < npair; pr += gridDim.y) {
+    int j = (int)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(j + 1) * (j + 2) / 2 <= pr) ++j;
+    while ((int64_t)j * (j + 1) / 2 > pr) --j;
+    const int i = (int)(pr - (int64_t)j * (j + 1) / 2);             // i <= j
+    const int64_t rij = ((int64_t)i * o + j) * vv, rji = ((int64_t)j * o + i) * vv;
+    // D tiles: tAB[r][c] = D[A*32+r, B*32+c], tBA[r][c] = D[B*32+r, A*32+c]
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int a = tA * 32 + r, b = tB * 32 + tx;
+      tAB[r][tx] = (a < v && b < v) ? z[rij + (int64_t)a * v + b] - z[rji + (int64_t)a * v + b] : 0.0;
+      const int a2 = tB * 32 + r, b2 = tA * 32 + tx;
+      tBA[r][tx] = (a2 < v && b2 < v) ? z[rij + (int64_t)a2 * v + b2] - z[rji + (int64_t)a2 * v + b2] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      {  // tile (A,B)
+        const int a = tA * 32 + r, b = tB * 32 + tx;
+        if (a < v && b < v) {
+          const double d = (i == j) ? 0.0 : tAB[r][tx] - tBA[tx][r];
+          const int64_t e1 = rij + (int64_t)a * v + b, e2 = rji + (int64_t)a * v + b;
+          double w1 = d, w2 = -d;
+          if (c0 != 0.0) { w1 += c0 * base[e1]; w2 += c0 * base[e2]; }
+          if (beta != 0.0) { w1 += beta * out[e1]; w2 += beta * out[e2]; }
+          out[e1] = w1;
+          if (i != j) out[e2] = w2;
+        }
+      }
+      if (tA != tB) {  // mirror tile (B,A): D[B,A] - D[A,B]^T
+        const int a = tB * 32 + r, b = tA * 32 + tx;
+        if (a < v && b < v) {
+          const double d = (i == j) ? 0.0 : tBA[r][tx] - tAB[tx][r];
+          const int64_t e1 = rij + (int64_t)a * v + b, e2 = rji + (int64_t)a * v + b;
+          double w1 = d, w2 = -d;
+          if (c0 != 0.0) { w1 += c0 * base[e1]; w2 += c0 * base[e2]; }
+          if (beta != 0.0) { w1 += beta * out[e1]; w2 += beta * out[e2]; }
+          out[e1] = w1;
+          if (i != j) out[e2] = w2;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_asym4(const double* base, double c0, const double* z, double* out, double beta, int o, int v,
+                         cudaStream_t st) {
+  if ((int64_t)o * o * v * v <= 0) return cudaSuccess;
+  if (!base) c0 = 0.0;
+  const int nt = (v + 31) / 32;
+  const int64_t npair = (int64_t)o * (o + 1) / 2;
+  dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)std::min<int64_t>(npair, 65535));
+  asym4_kernel<<<grid, 256, 0, st>>>(base, c0, z, out, beta, o, v);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double c1, double c2,
-                       cudaStream_t st) {
-  int64_t total = (int64_t)o * o * v * v;
+                       cudaStream_t st, int i0, int ni) {
+  if (ni < 0) ni = o - i0;
+  int64_t total = (int64_t)ni * o * v * v;
   if (total <= 0) return cudaSuccess;
   const bool vec = (v % 2 == 0) && (reinterpret_cast<uintptr_t>(t2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const int64_t per = (int64_t)v * v / (vec ? 2 : 1);
   dim3 grid((unsigned)std::min<int64_t>((per + EW_THREADS - 1) / EW_THREADS, 64),
-            (unsigned)std::min<int64_t>((int64_t)o * o, 65535));
-  if (vec) tau_kernel<2><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
-  else tau_kernel<1><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2);
+            (unsigned)std::min<int64_t>((int64_t)ni * o, 65535));
+  if (vec) tau_kernel<2><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2, i0, ni);
+  else tau_kernel<1><<<grid, EW_THREADS, 0, st>>>(t2, t1, out, o, v, c1, c2, i0, ni);
   return cudaGetLastError();
 }
 

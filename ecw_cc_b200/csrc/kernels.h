@@ -95,8 +95,12 @@ cudaError_t launch_ew2(const Ew2Args& a, cudaStream_t st);
 cudaError_t launch_reduce(const double* part, int64_t nz, int64_t M, int64_t N, double* C, int64_t sr,
                           int64_t sc, double alpha, double beta, cudaStream_t st);
 // out[ijab] = t2[ijab] + c1*t1[ia]t1[jb] - c2*t1[ib]t1[ja]
+// i0 / ni: t2 and out hold only the rows i0 .. i0+ni-1 of the leading occupied index (ni < 0: all from i0)
 cudaError_t launch_tau(const double* t2, const double* t1, double* out, int o, int v, double c1, double c2,
-                       cudaStream_t st);
+                       cudaStream_t st, int i0 = 0, int ni = -1);
+// out[ijab] = c0 base[ijab] + z[ijab] - z[jiab] - z[ijba] + z[jiba] + beta out[ijab]  (base may be null)
+cudaError_t launch_asym4(const double* base, double c0, const double* z, double* out, double beta, int o, int v,
+                         cudaStream_t st);
 // out[0] = max(|x[ijab]+x[jiab]|, |x[ijab]+x[ijba]|)  (0 for exactly antisymmetric doubles amplitudes), out[1] = max|x|
 cudaError_t launch_antisym_defect(const double* x, int o, int v, double* out, cudaStream_t st);
 

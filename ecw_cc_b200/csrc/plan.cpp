@@ -162,6 +162,46 @@ void Plan::allgather(const Tensor& chunk, int64_t count, const Tensor& full, con
   ops.push_back(op);
 }
 
+void Plan::alltoall(const Tensor& send, int64_t count, const Tensor& recv, const char* note) {
+  if (world == 1) {
+    Tensor a = make_tensor(send.slot, send.off, {count}), c = make_tensor(recv.slot, recv.off, {count});
+    permute(1.0, a, "p", 0.0, c, "p", note);
+    return;
+  }
+  Op op;
+  op.kind = OP_ALLTOALL;
+  op.a = send;
+  op.c = recv;
+  op.i0 = count;
+  op.i1 = world;
+  op.i2 = rank;
+  op.note = note;
+  ops.push_back(op);
+}
+
+void Plan::sum_ranks_add(const Tensor& part, const Tensor& C, const char* note) {
+  const int64_t n = part.size();
+  if (world == 1) {
+    axpby(1.0, part, 1.0, C, note);
+    return;
+  }
+  if (part.slot != S_WS) throw PlanError("sum_ranks_add: the partial result must live in the workspace");
+  Tensor G = tmp({(int64_t)world, n});
+  allgather(part, n, G, note);
+  Op r;
+  r.kind = OP_REDUCE;
+  r.a = G;
+  r.i0 = world;
+  // C as an M x N matrix: any contiguous C is [n, 1]; a strided 2-D C keeps its own strides
+  if (C.nd == 2 && C.size() == n) { r.M = C.dim[0]; r.N = C.dim[1]; r.i1 = C.str[0]; r.i2 = C.str[1]; }
+  else { r.M = n; r.N = 1; r.i1 = 1; r.i2 = 0; }
+  r.c = C;
+  r.alpha = 1.0; r.beta = 1.0;
+  r.note = std::string(note) + " [sum over ranks]";
+  ops.push_back(r);
+  release(G);
+}
+
 void Plan::contract_split(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
                           const Tensor& C, const char* sc, char lab, const char* note) {
   if (world == 1) {
@@ -265,6 +305,34 @@ void Plan::tau(const Tensor& t2, const Tensor& t1, double c1, double c2, const T
   op.c = out;
   op.alpha = c1;
   op.beta = c2;
+  ops.push_back(op);
+}
+
+void Plan::tau_rows(const Tensor& t2_rows, const Tensor& t1, int64_t i0, double c1, double c2, const Tensor& out_rows) {
+  Op op;
+  op.kind = OP_TAU;
+  op.a = t2_rows;
+  op.b = t1;
+  op.c = out_rows;
+  op.alpha = c1;
+  op.beta = c2;
+  op.i0 = i0;
+  op.i1 = out_rows.dim[0];
+  op.i2 = 1;               // row-range form
+  ops.push_back(op);
+}
+
+void Plan::asym4(double c0, const Tensor* base, const Tensor& z, double beta, const Tensor& out, const char* note) {
+  if (z.nd != 4 || out.nd != 4) throw PlanError("asym4: needs [o,o,v,v] tensors");
+  Op op;
+  op.kind = OP_ASYM4;
+  op.a = z;
+  if (base) op.b = *base;
+  op.c = out;
+  op.alpha = base ? c0 : 0.0;
+  op.beta = beta;
+  op.note = note;
+  perm_bytes += 8.0 * (double)out.size() * (2.0 + (base ? 1.0 : 0.0) + (beta != 0.0 ? 1.0 : 0.0));
   ops.push_back(op);
 }
 
@@ -990,7 +1058,8 @@ static void dump_tensor(std::ostringstream& o, const char* key, const Tensor& t)
 
 std::string Plan::dump_json() const {
   static const char* kn[] = {"gemm", "reduce", "permute", "fill", "tau", "pack", "unpack", "finish",
-                             "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather", "oz_split", "oz_gemm"};
+                             "dot", "scale_dev", "diag_add", "rdm1", "ewise", "allgather", "oz_split", "oz_gemm",
+                             "asym4", "alltoall"};
   std::ostringstream o;
   o.precision(17);
   o << "{\"workspace_elems\":" << arena.peak << ",\"gemm_flops\":" << gemm_flops << ",\"oz_flops\":" << oz_flops

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <algorithm>
 
 namespace ecw {
 
@@ -75,6 +76,8 @@ enum OpKind : int {
   OP_OZ_SPLIT,    // a = X[R=M, (K1=i1, K2=K)] (element strides lda, ldc, ldb) -> c = i0 int8 digit planes, d = statistics
   OP_OZ_GEMM,     // C_b[m*i1 + n*i2] = alpha sum_k A_b[m,k] B_b[n,k] + beta C_b from plane sets a (stats d, lda rows)
                   // and b (stats e, ldb rows); sub-blocks per batch in oz[] (OzBatch order), sC = C offset per batch
+  OP_ASYM4,       // c[ijab] = alpha b[ijab] + a[ijab] - a[jiab] - a[ijba] + a[jiba] + beta c[ijab]  (b may be unset)
+  OP_ALLTOALL,    // collective: block q (i0 elements) of `a` goes to rank q; block q of `c` comes from rank q
 };
 
 struct Op {
@@ -144,6 +147,17 @@ class Plan {
   void contract_lead_dist(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
                           const Tensor& C, const char* sc, const char* note = "");
   void allgather(const Tensor& chunk, int64_t count, const Tensor& full, const char* note = "");
+  // send / recv: world blocks of `count` elements each (workspace); no-op copy when world == 1
+  void alltoall(const Tensor& send, int64_t count, const Tensor& recv, const char* note = "");
+  // C += sum over ranks of `part` (same shape, contiguous; all-gathered and added in rank order on every rank:
+  // bit-identical replicas).  world == 1: C += part.
+  void sum_ranks_add(const Tensor& part, const Tensor& C, const char* note = "");
+  // this rank's range of an index of extent L that is distributed in chunks of lead_chunk(L)
+  void my_range(int64_t L, int64_t* i0, int64_t* ni) const {
+    const int64_t ch = lead_chunk(L);
+    *i0 = std::min<int64_t>(L, (int64_t)rank * ch);
+    *ni = std::min<int64_t>(L, *i0 + ch) - *i0;
+  }
   // C (contiguous) += alpha * sum_K A.B with the range of the contracted label `lab` split across ranks
   // (partial sums are all-gathered and added in rank order on every rank: bit-identical replicas)
   void contract_split(double alpha, const Tensor& A, const char* sa, const Tensor& B, const char* sb,
@@ -160,6 +174,10 @@ class Plan {
   void fill(const Tensor& C, double value);
   // out = t2 + c1 t1[ia]t1[jb] - c2 t1[ib]t1[ja]
   void tau(const Tensor& t2, const Tensor& t1, double c1, double c2, const Tensor& out);
+  // the same for the rows i0 .. i0+ni-1 of the leading occupied index: t2 and out are [ni, o, v, v] views
+  void tau_rows(const Tensor& t2_rows, const Tensor& t1, int64_t i0, double c1, double c2, const Tensor& out_rows);
+  // out[ijab] = c0 base[ijab] + z[ijab] - z[jiab] - z[ijba] + z[jiba] + beta out[ijab]; all contiguous [o,o,v,v]
+  void asym4(double c0, const Tensor* base, const Tensor& z, double beta, const Tensor& out, const char* note = "");
   // pack/unpack: flags bit0 = first pair packed, bit1 = second pair packed,
   //              bit2 = antisymmetrise second pair while packing (x[..rs]-x[..sr])
   //              bit3 = antisymmetrise first pair while packing  (x[pq..]-x[qp..])

@@ -74,6 +74,11 @@ class TorchDistComm(object):
         import torch.distributed as dist
         dist.all_gather_into_tensor(recv, send, group=self.group)
 
+    def all_to_all(self, eris, recv, send):
+        """block q of `send` goes to rank q, block q of `recv` comes from rank q"""
+        import torch.distributed as dist
+        dist.all_to_all_single(recv, send, group=self.group)
+
     def max_scalar(self, eris, x):
         """max over ranks of a one-element device tensor -> float"""
         import torch.distributed as dist
@@ -100,6 +105,9 @@ class DeviceEris(object):
             raise EcwError("ecw_ctx_create failed")
         if self.world > 1 and lib.ecw_ctx_set_shard(self._h, self.rank, self.world) != 0:
             raise EcwError("ecw_ctx_set_shard failed")
+        # experiments: ECW_PLAN_VARIANT=legacy selects the round-1 lowering of the packed plans (include/ecw_b200.h)
+        if os.environ.get("ECW_PLAN_VARIANT", "") == "legacy":
+            self.check(lib.ecw_ctx_set_plan_variant(self._h, 1), "ecw_ctx_set_plan_variant")
         self.int8_digits, self.int8_min_flops = _gemm_config(gemm, int8_digits, int8_min_flops, self.nvir, eri_max)
         self.check(lib.ecw_ctx_set_gemm(self._h, self.int8_digits, self.int8_min_flops), "ecw_ctx_set_gemm")
         # constant digit planes of ovvv_p (both orientations): sub-blocks of a plane set start on 8-row groups
@@ -168,10 +176,13 @@ class DeviceEris(object):
             if lib.ecw_pending_collective(self._h, desc) != 0:
                 raise EcwError("%s: no pending collective" % what)
             kind, soff, count, roff, world, rank = [int(x) for x in desc]
-            if kind != 1 or world != self.world:
+            if kind not in (1, 2) or world != self.world:
                 raise EcwError("%s: unexpected collective %r" % (what, list(desc)))
             ws = self._ws.view(torch.float64)
-            self.comm.all_gather(self, ws[roff: roff + world * count], ws[soff: soff + count])
+            if kind == 1:
+                self.comm.all_gather(self, ws[roff: roff + world * count], ws[soff: soff + count])
+            else:
+                self.comm.all_to_all(self, ws[roff: roff + world * count], ws[soff: soff + world * count])
             rc = lib.ecw_resume(self._h, self.stream())
         self.check(rc, what)
 

@@ -49,7 +49,7 @@ const char* ecw_version(void);
 /* Multi-GPU (one process per GPU): rank r of `world` keeps rows [r*ceil(P_v/world), ...) of "vvvv_p"
  * (the packed virtual pair index) and computes its share of the heavy contractions.  Calls then
  * return 1 whenever a collective is due: the host reads it with ecw_pending_collective
- * (desc = {kind 1=all-gather, send offset, elements per rank, recv offset, world, rank}; offsets
+ * (desc = {kind 1=all-gather | 2=all-to-all, send offset, elements per rank / per block, recv offset, world, rank}; offsets
  * are FP64-element offsets into the workspace), performs it (torch.distributed / NCCL) and calls
  * ecw_resume until it returns 0. */
 int ecw_ctx_set_shard(ecw_ctx* ctx, int rank, int world);
@@ -72,6 +72,10 @@ int ecw_ctx_get_gemm(ecw_ctx* ctx);
  * exceeds its tolerance (ecw_cc_b200/eris.py: INT8_TOL); 0 restores the configured engine. */
 int ecw_int8_error_bound(ecw_ctx* ctx, double* bound_out, void* stream);
 int ecw_ctx_set_engine_override(ecw_ctx* ctx, int force_dmma);
+/* Lowering of the antisymmetric-amplitude (packed) T / Lambda plans: 0 (default) = o^2v^2 work on slabs of the leading
+ * occupied index with one fused antisymmetriser (csrc/ccsd_plan_slab.cpp), 1 = the round-1 lowering with replicated
+ * intermediates (csrc/ccsd_plan.cpp) — kept for A/B measurements. */
+int ecw_ctx_set_plan_variant(ecw_ctx* ctx, int legacy_packed);
 /* INT8 products with fewer output tiles than SMs and a contraction length >= min_k (a multiple of 32) are cut into
  * equal K chunks, one product each, summed in a fixed order (default 65536; <= 0: never). */
 int ecw_ctx_set_int8_splitk(ecw_ctx* ctx, int64_t min_k);

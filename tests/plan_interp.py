@@ -193,6 +193,28 @@ class Interp(object):
         assert self.allgather is not None, "multi-rank plan needs an allgather callable"
         self.allgather(send, recv)
 
+    def op_alltoall(self, op):
+        """emulated through the all-gather callable (test infrastructure: every rank sees every send buffer)"""
+        ws = self.slots["ws"]
+        count, world, rank = op["i0"], op["i1"], op["i2"]
+        send = ws[op["a"]["off"]: op["a"]["off"] + world * count]
+        allsend = np.empty(world * world * count)
+        assert self.allgather is not None, "multi-rank plan needs an allgather callable"
+        self.allgather(send, allsend)
+        recv = ws[op["c"]["off"]: op["c"]["off"] + world * count]
+        for q in range(world):
+            recv[q * count:(q + 1) * count] = allsend[(q * world + rank) * count:(q * world + rank + 1) * count]
+
+    def op_asym4(self, op):
+        z, out = self.view(op["a"]), self.view(op["c"])
+        assert not np.isnan(z).any(), op["note"]
+        res = z - z.transpose(1, 0, 2, 3) - z.transpose(0, 1, 3, 2) + z.transpose(1, 0, 3, 2)
+        if op["b"] is not None and op["alpha"] != 0.0:
+            res = res + op["alpha"] * self.view(op["b"])
+        if op["beta"] != 0.0:
+            res = res + op["beta"] * out
+        out[...] = res
+
     def _bytes(self, t):
         return self.slots[t["slot"]].reshape(-1).view(np.int8)[8 * t["off"]:]
 
@@ -244,7 +266,10 @@ class Interp(object):
     def op_tau(self, op):
         t2, t1, out = self.view(op["a"]), self.view(op["b"]), self.view(op["c"])
         x = np.einsum('ia,jb->ijab', t1, t1)
-        out[...] = t2 + (op["alpha"] * x - op["beta"] * x.transpose(0, 1, 3, 2))
+        full = op["alpha"] * x - op["beta"] * x.transpose(0, 1, 3, 2)
+        if op["i2"]:                                     # rows i0 .. i0+ni-1 of the leading occupied index
+            full = full[op["i0"]: op["i0"] + op["i1"]]
+        out[...] = t2 + full
 
     def op_pack(self, op):
         A, C = self.view(op["a"]), self.view(op["c"])

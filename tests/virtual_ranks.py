@@ -24,6 +24,16 @@ class ThreadComm(object):
             self.gathers += 1
         self.barrier.wait()                      # nobody overwrites a contribution before everyone has copied it
 
+    def all_to_all(self, eris, recv, send):
+        r, n = eris.rank, send.numel() // self.world
+        self.send[r] = send
+        self.barrier.wait()
+        for q in range(self.world):
+            recv[q * n:(q + 1) * n].copy_(self.send[q][r * n:(r + 1) * n])
+        if r == 0:
+            self.gathers += 1
+        self.barrier.wait()
+
     def max_scalar(self, eris, x):
         self.vals[eris.rank] = float(x.cpu()[0])
         self.barrier.wait()
