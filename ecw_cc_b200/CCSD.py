@@ -26,6 +26,7 @@ def _flags(alpha, equation, antisym=False):
 
 class GCC(object):
     TRACK_MIN_BYTES = 1 << 20   # smaller outputs are not worth a device copy kept alive
+    POOL_DEPTH = 4              # pinned result blocks kept per shape
 
     def __init__(self, eris, fock=None, device=None, assume_antisym=None, rank=0, world=1, group=None, gemm=None,
                  int8_digits=None, track_outputs=True):
@@ -46,6 +47,7 @@ class GCC(object):
         self.nvir = self.fock.shape[0] - self.nocc
         self._pin = {}
         self._tracked = {}      # id(host array this object returned) -> (weakref, its device copy)
+        self._pool = {}         # (shape, dtype) -> pinned blocks of returned arrays the caller has dropped
         self.track_outputs = bool(track_outputs)
         self.h2d_bytes = 0      # bytes staged host->device / device->host by this object
         self.d2h_bytes = 0
@@ -97,19 +99,32 @@ class GCC(object):
         torch = self._torch()
         outs = []
         for t in ts:
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h = self._pinned(t.shape, t.dtype)
             h.copy_(t, non_blocking=True)
             self.d2h_bytes += t.numel() * 8
             outs.append(h)
         torch.cuda.current_stream(self.eris.device).synchronize()
-        outs = [h.numpy() for h in outs]
-        if self.track_outputs:
-            for a, t in zip(outs, ts):
-                if a.nbytes >= self.TRACK_MIN_BYTES:
+        arrs = [h.numpy() for h in outs]
+        for a, h, t in zip(arrs, outs, ts):
+            if a.nbytes >= self.TRACK_MIN_BYTES:
+                # the pinned block goes back to this object's pool when the caller drops the array
+                weakref.finalize(a, self._pool.setdefault((tuple(h.shape), h.dtype), []).append, h)
+                if self.track_outputs:
                     a.setflags(write=False)
                     key = id(a)
                     self._tracked[key] = (weakref.ref(a, lambda _r, k=key, d=self._tracked: d.pop(k, None)), t)
-        return outs[0] if len(outs) == 1 else tuple(outs)
+        return arrs[0] if len(arrs) == 1 else tuple(arrs)
+
+    def _pinned(self, shape, dtype):
+        """A pinned host buffer for one result.  Page-locking gigabytes costs far more than the transfer itself
+        (cudaHostAlloc), so blocks of arrays the caller has dropped are reused (per shape, at most POOL_DEPTH kept)."""
+        torch = self._torch()
+        free = self._pool.get((tuple(shape), dtype))
+        if free:
+            h = free.pop()
+            del free[self.POOL_DEPTH:]
+            return h
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
 
     def to_numpy(self, t):
         """Download a device tensor the way every method of this class returns its results (pinned, read-only,

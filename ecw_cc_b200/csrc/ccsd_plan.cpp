@@ -760,18 +760,38 @@ void build_ccsd_gamma(Plan& P, const Sizes& z) {
   Slots s(z);
   const int64_t o = s.o, v = s.v;
   const Tensor &t1 = s.t1, &t2 = s.t2, &l1 = s.l1, &l2 = s.l2;
-  // gamma_inter, CCSD.py:165-182
+  // gamma_inter, CCSD.py:165-182.  The three products over the doubles run on this rank's part of an occupied index
+  // (no symmetry of the amplitudes is used: the rdm1 is also taken of L1-regularised, non-antisymmetric amplitudes)
+  // and are summed over ranks in a fixed order.
+  int64_t i0, ni;
+  P.my_range(o, &i0, &ni);
   Tensor D = P.tmp({o, o});
-  P.contract(1.0, l2, "imef", t2, "jmef", 0.0, D, "ij", "rdm1 oo");
+  P.fill(D, 0.0);
+  Tensor dvv = P.tmp({v, v});
+  P.fill(dvv, 0.0);
+  Tensor dvoT = P.tmp({o, v});
+  P.axpby(1.0, t1, 0.0, dvoT);
+  {
+    Tensor p = P.tmp({o, o});
+    P.fill(p, 0.0);
+    if (ni > 0) P.contract(1.0, slice_dim(l2, 1, i0, ni), "imef", slice_dim(t2, 1, i0, ni), "jmef", 1.0, p, "ij", "rdm1 oo");
+    P.sum_ranks_add(p, D, "rdm1 oo");
+    P.release(p);
+    Tensor q = P.tmp({v, v});
+    P.fill(q, 0.0);
+    if (ni > 0) P.contract(0.5, slice0(t2, i0, ni), "mnea", slice0(l2, i0, ni), "mneb", 1.0, q, "ab", "rdm1 vv");
+    P.sum_ranks_add(q, dvv, "rdm1 vv");
+    P.release(q);
+    Tensor r = P.tmp({o, v});
+    P.fill(r, 0.0);
+    if (ni > 0) P.contract(1.0, slice0(t2, i0, ni), "imae", l1, "me", 1.0, slice0(r, i0, ni), "ia", "rdm1 vo");
+    P.sum_ranks_add(r, dvoT, "rdm1 vo");
+    P.release(r);
+  }
   Tensor doo = P.tmp({o, o});
   P.axpby(-0.5, D, 0.0, doo);
   P.contract(-1.0, l1, "ie", t1, "je", 1.0, doo, "ij");
-  Tensor dvv = P.tmp({v, v});
-  P.contract(0.5, t2, "mnea", l2, "mneb", 0.0, dvv, "ab", "rdm1 vv");
   P.contract(1.0, t1, "ma", l1, "mb", 1.0, dvv, "ab");
-  Tensor dvoT = P.tmp({o, v});
-  P.axpby(1.0, t1, 0.0, dvoT);
-  P.contract(1.0, t2, "imae", l1, "me", 1.0, dvoT, "ia", "rdm1 vo");
   P.contract(-0.5, D, "mi", t1, "ma", 1.0, dvoT, "ia");
   P.contract(-1.0, t1, "ie", dvv, "ae", 1.0, dvoT, "ia");
   P.rdm1(doo, dvoT, l1, dvv, s.rdm1);   // CCSD.py:154-160

@@ -286,7 +286,7 @@ void build_ccsd_tupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   if (mine) {
     Tensor zg = g.rows(zf);
     Tensor ringT = P.tmp({ni, v, o, v});                          // ring^T[(j in slab, b),(i,a)]
-    P.contract(1.0, WcT, "jbme", t2ph, "meia", 0.0, ringT, "jbia", "R2 ring");
+    P.contract(1.0, WcT, "jbme", t2ph, "iame", 0.0, ringT, "jbia", "R2 ring");          // t2ph symmetric
     P.release(WcT);
     P.permute(1.0, ringT, "jbia", 1.0, zg, "jiba", "ring -> z");
     P.release(ringT);
@@ -372,7 +372,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
   Tensor v4T;
   if (mine) {
     v4T = P.tmp({ni, v, o, v});
-    P.contract(1.0, g.rows(s.oovv_ph), "jbld", t2ph, "ldkc", 0.0, v4T, "jbkc", "R3 v4");
+    P.contract(1.0, g.rows(s.oovv_ph), "jbld", t2ph, "kcld", 0.0, v4T, "jbkc", "R3 v4");   // same view of t2ph as below: one cut
     P.axpby(-1.0, g.rows(s.ovov_ph), 1.0, v4T);
   }
 
@@ -502,7 +502,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
     Tensor zg = g.rows(zf);
     // ring^T[(j in slab, b),(i,a)] = w^T . l2ph + fov1[jb] l1[ia]
     Tensor ringT = P.tmp({ni, v, o, v});
-    P.contract(1.0, wT, "jbkc", l2ph, "kcia", 0.0, ringT, "jbia", "R7 ring");
+    P.contract(1.0, wT, "jbkc", l2ph, "iakc", 0.0, ringT, "jbia", "R7 ring");           // l2ph symmetric; same view as R8: one cut
     P.release(wT);
     P.contract(1.0, g.rows(Fov), "jb", l1, "ia", 1.0, ringT, "jbia");
     P.permute(1.0, ringT, "jbia", 0.0, zg, "jiba", "ring -> z");
@@ -564,7 +564,7 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
       if (planes) pair_ovvv_rows(P, s, -0.5, l2, p, i0, ni, "wvvvo: ovvv");
       else P.contract(-0.5, g.at(l2, 1), "ikbc", g.rows(s.ovvv), "kabc", 1.0, p, "ia", "wvvvo: ovvv");
       Tensor XT = P.tmp({ni, v, o, v});                            // X^T[(k in slab, d),(i,b)] = sum_jc t2ph[(kd),(jc)] l2ph[(jc),(ib)]
-      P.contract(1.0, g.rows(t2ph), "kdjc", l2ph, "jcib", 0.0, XT, "kdib", "R8 l2.t2");
+      P.contract(1.0, g.rows(t2ph), "kdjc", l2ph, "ibjc", 0.0, XT, "kdib", "R8 l2.t2");
       P.contract(1.0, XT, "kdib", g.rows(s.ovvv), "kbda", 1.0, p, "ia", "wvvvo: ovvv.t2 (K4 refactored)");
       P.release(XT);
       P.contract(1.0, g.rows(r2), "ijab", t1, "jb", 1.0, pr, "ia", "m3.t1");

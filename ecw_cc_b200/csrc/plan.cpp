@@ -255,6 +255,13 @@ void Plan::contract_lead_dist(double alpha, const Tensor& A, const char* sa, con
 
 void Plan::release(const Tensor& t) {
   if (t.slot != S_WS) throw PlanError("release of non-workspace tensor");
+  if (!cut_cache.empty()) {
+    // the planes cut from this buffer go with it (the arena block is the unit: its whole extent)
+    int64_t lo = t.off, hi = t.off;
+    for (const auto& b : arena.blks)
+      if (b.off == t.off && b.used) { hi = b.off + b.size - 1; break; }
+    drop_cuts_of(S_WS, lo, hi);
+  }
   arena.release(t.off);
 }
 
@@ -910,12 +917,108 @@ static int64_t oz_pick_splits(int ns, int sm_count, int64_t M, int64_t N, int64_
   return best;
 }
 
+namespace {
+// element range [lo, hi] a strided view can touch
+void view_range(const Tensor& t, int64_t* lo, int64_t* hi) {
+  int64_t a = t.off, b = t.off;
+  for (int i = 0; i < t.nd; ++i) {
+    if (t.dim[i] <= 0) { *lo = t.off; *hi = t.off - 1; return; }
+    const int64_t span = (t.dim[i] - 1) * t.str[i];
+    if (span >= 0) b += span; else a += span;
+  }
+  *lo = a; *hi = b;
+}
+}  // namespace
+
+// has any op after `op_index` written into [lo, hi] of `slot`?  (conservative: ranges of strided views)
+bool Plan::written_since(size_t op_index, int slot, int64_t lo, int64_t hi) const {
+  auto hits = [&](const Tensor& t, int64_t extra = 0) {
+    if (!t.valid() || t.slot != slot) return false;
+    int64_t a, b;
+    view_range(t, &a, &b);
+    b += extra;
+    return !(b < lo || a > hi);
+  };
+  for (size_t k = op_index + 1; k < ops.size(); ++k) {
+    const Op& op = ops[k];
+    switch (op.kind) {
+      case OP_OZ_SPLIT: if (hits(op.c) || hits(op.d)) return true; break;
+      case OP_DOT: break;                                   // writes only its scratch partials (released at once) and scal
+      case OP_GEMM: {                                       // batched / split-K outputs: batch * sC beyond the first matrix
+        Tensor c = op.c;
+        int64_t a, b;
+        view_range(c, &a, &b);
+        const int64_t ext = (op.M - 1) * std::max<int64_t>(op.ldc, 1) + op.N - 1 + (op.batch - 1) * op.sC;
+        if (c.slot == slot && !(a + std::max<int64_t>(ext, b - a) < lo || a > hi)) return true;
+        break;
+      }
+      case OP_OZ_GEMM: {
+        if (op.c.slot != slot) break;
+        const int64_t a = op.c.off;
+        const int64_t ext = (op.M - 1) * std::max<int64_t>(op.i1, 0) + (op.N - 1) * std::max<int64_t>(op.i2, 0) +
+                            (op.batch - 1) * op.sC;
+        if (!(a + ext < lo || a > hi)) return true;
+        break;
+      }
+      case OP_REDUCE: {
+        if (op.c.slot != slot) break;
+        const int64_t a = op.c.off, ext = (op.M - 1) * op.i1 + (op.N - 1) * op.i2;
+        if (!(a + ext < lo || a > hi)) return true;
+        break;
+      }
+      case OP_ALLGATHER: case OP_ALLTOALL:
+        if (op.c.slot == slot && !(op.c.off + op.i0 * op.i1 - 1 < lo || op.c.off > hi)) return true;
+        break;
+      default:
+        if (hits(op.c)) return true;
+    }
+  }
+  return false;
+}
+
+void Plan::drop_cuts_of(int slot, int64_t lo, int64_t hi) {
+  for (size_t i = 0; i < cut_cache.size();) {
+    CutEntry& e = cut_cache[i];
+    if (e.slot == slot && !(e.hi < lo || e.lo > hi)) {
+      arena.release(e.set.stats.off);
+      arena.release(e.set.planes.off);
+      cut_cache.erase(cut_cache.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+}
+
 OzSet Plan::oz_cut(const Tensor& X, int64_t R, int64_t rs, int64_t K1, int64_t ks1, int64_t K2, int64_t ks2,
                    const std::string& note) {
   if (oz_ns <= 0) throw PlanError("oz_cut: the INT8 engine is off");
+  // the element range the cut reads
+  int64_t lo = X.off, hi = X.off + (R - 1) * rs + (K1 - 1) * ks1 + (K2 - 1) * ks2;
+  const bool cacheable = R * K1 * K2 >= cut_cache_min_elems && rs >= 0 && ks1 >= 0 && ks2 >= 0;
+  if (cacheable) {
+    for (CutEntry& e : cut_cache) {
+      if (e.slot == X.slot && e.off == X.off && e.R == R && e.rs == rs && e.K1 == K1 && e.ks1 == (K1 > 1 ? ks1 : e.ks1) &&
+          e.K2 == K2 && e.ks2 == ks2 && e.ns == oz_ns && !written_since(e.op_index, e.slot, e.lo, e.hi)) {
+        ++cut_cache_hits;
+        return e.set;
+      }
+    }
+    // a stale entry of the same source is useless from now on
+    for (size_t i = 0; i < cut_cache.size();) {
+      CutEntry& e = cut_cache[i];
+      if (e.slot == X.slot && !(e.hi < lo || e.lo > hi) && written_since(e.op_index, e.slot, e.lo, e.hi)) {
+        arena.release(e.set.stats.off);
+        arena.release(e.set.planes.off);
+        cut_cache.erase(cut_cache.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+  }
   OzSet s;
   s.R = R; s.K1 = K1; s.K2 = K2;
-  s.owned = true;
+  s.owned = !cacheable;
+  s.cached = cacheable;
   s.planes = tmp({oz_plane_elems(R, K1, K2, oz_ns)});
   s.stats = tmp({oz_stat_elems(R, K1)});
   Op sp;
@@ -928,6 +1031,10 @@ OzSet Plan::oz_cut(const Tensor& X, int64_t R, int64_t rs, int64_t K1, int64_t k
   sp.i0 = oz_ns;
   sp.note = note;
   ops.push_back(sp);
+  if (cacheable) {
+    CutEntry e{X.slot, X.off, R, rs, K1, ks1, K2, ks2, oz_ns, lo, hi, ops.size() - 1, s};
+    cut_cache.push_back(e);
+  }
   return s;
 }
 

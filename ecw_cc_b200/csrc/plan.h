@@ -100,7 +100,8 @@ struct Op {
 struct OzSet {
   Tensor planes, stats;
   int64_t R = 0, K1 = 1, K2 = 0;
-  bool owned = false;          // lives in the workspace arena
+  bool owned = false;          // lives in the workspace arena and is released by oz_release
+  bool cached = false;         // lives in the workspace arena, owned by the cut cache of the plan
   int64_t rp() const { return (R + 127) / 128 * 128; }
   int64_t nkb2() const { return (K2 + 31) / 32; }
 };
@@ -198,6 +199,10 @@ class Plan {
   OzSet oz_cut(const Tensor& X, int64_t R, int64_t rs, int64_t K1, int64_t ks1, int64_t K2, int64_t ks2,
                const std::string& note);
   void oz_release(const OzSet& s);
+ private:
+  bool written_since(size_t op_index, int slot, int64_t lo, int64_t hi) const;
+  void drop_cuts_of(int slot, int64_t lo, int64_t hi);
+ public:
   OzSet oz_const_vvvv(int64_t rows) const;     // this rank's shard of vvvv_p: rows x P_v
   OzSet oz_const_ovvv1() const;                // rows (m,a), k = ef_p
   OzSet oz_const_ovvv2() const;                // rows ef_p, k = (m, a)
@@ -205,6 +210,18 @@ class Plan {
   // the role assignment (which operand feeds the 128-row side of the tile) is chosen here
   void oz_mm(double alpha, const OzSet& A, const OzSel& a, const OzSet& B, const OzSel& b, int64_t M, int64_t N,
              int64_t batch, double beta, const Tensor& C, int64_t crs, int64_t ccs, int64_t c_b, const std::string& note);
+
+  // ---- cut cache: a large operand view that is cut twice while nothing has written into it in between (t2 / l2 in
+  // particle-hole layout feed several ring products) keeps its planes; they are dropped when the source is released.
+  struct CutEntry {
+    int slot; int64_t off, R, rs, K1, ks1, K2, ks2; int ns;
+    int64_t lo, hi;          // element range of the source view
+    size_t op_index;         // the OP_OZ_SPLIT that made the planes
+    OzSet set;
+  };
+  std::vector<CutEntry> cut_cache;
+  int64_t cut_cache_min_elems = 1 << 20;
+  int64_t cut_cache_hits = 0;
 
   int64_t workspace_elems() const { return arena.peak; }
   std::string dump_json() const;

@@ -26,7 +26,7 @@ def ecw(built_lib):
 
 
 # ---------------------------------------------------------------------------------------- (a) the benchmark shape
-PAIRS_40_400 = [(3, 17), (17, 250), (250, 399), (399, 3), (17, 3), (250, 250)]
+PAIRS_40_400 = [(3, 250), (250, 399), (399, 3), (250, 250)]       # a < b, a > b, a == b; three distinct virtuals
 
 
 def test_benchmark_shape_against_sampled_oracle(ecw, monkeypatch):
@@ -54,7 +54,8 @@ def test_benchmark_shape_against_sampled_oracle(ecw, monkeypatch):
             assert any(want in s for s in notes), (fn, want)
     pairs = PAIRS_40_400
     got = {}
-    for tag, alpha in (("upd", None), ("l1upd", 1e-3)):
+    modes = (("upd", None),)           # the mode the benchmark runs; the L1 modes are element-wise on top of it
+    for tag, alpha in modes:
         a1, a2 = cc.tupdate(d_t1, d_t2, fsp=d_f, alpha=alpha)
         got["T1" + tag] = a1.cpu().numpy()
         got["T2" + tag] = np.stack([a2[:, :, a, b].cpu().numpy() for a, b in pairs])
@@ -75,7 +76,7 @@ def test_benchmark_shape_against_sampled_oracle(ecw, monkeypatch):
     fsp = synth.fsp(o, v)
     col = ColumnOracle(prov, pairs)
     worst = {}
-    for tag, alpha in (("upd", None), ("l1upd", 1e-3)):
+    for tag, alpha in modes:
         r1, r2 = col.tupdate(t1, t2, fsp=fsp, alpha=alpha)
         worst["T1" + tag] = np.abs(got["T1" + tag] - r1).max()
         worst["T2" + tag] = np.abs(got["T2" + tag] - r2).max()

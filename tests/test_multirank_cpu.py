@@ -67,6 +67,14 @@ def _worker(rank, world, port, o, v, antisym, q, int8=0):
                 ref = (orc.tupdate(t1, t2, fsp=fsp, alpha=alpha, equation=eq) if fn == "tupdate"
                        else orc.lupdate(t1, t2, l1, l2, fsp=fsp, alpha=alpha, equation=eq))
                 worst = max(worst, np.abs(sl["out1"] - ref[0]).max(), np.abs(sl["out2"] - ref[1]).max())
+        # the rdm1 plan: the products over the doubles are split over an occupied index and summed over ranks
+        pl = plan_json(lib, o, v, "gamma", 0, rank=rank, world=world, int8_digits=int8, vvvv_planes=bool(int8),
+                       ovvv_planes=bool(int8) and o % 8 == 0 and v % 8 == 0)
+        ncoll += sum(1 for op in pl["ops"] if op["kind"] == "allgather")
+        sl = dict(base)
+        sl["rdm1"] = np.full((o + v, o + v), np.nan)
+        Interp(pl, sl, allgather=allgather).run()
+        worst = max(worst, np.abs(sl["rdm1"] - orc.gamma(t1, t2, l1, l2)).max())
         q.put((rank, float(worst), ncoll))
     finally:
         dist.destroy_process_group()
