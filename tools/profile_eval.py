@@ -10,7 +10,15 @@ o, v = int(sys.argv[1]), int(sys.argv[2])
 t0 = time.time()
 gemm = sys.argv[4] if len(sys.argv) > 4 else None
 digits = int(sys.argv[5]) if len(sys.argv) > 5 else None
-de = ecw.DeviceEris.synthetic(o, v, gemm=gemm, int8_digits=digits)
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:                        # torchrun: one rank per GPU, rank 0 reports (its ops include the waits on the others)
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    if rank != 0:
+        sys.stdout = open(os.devnull, "w")
+de = ecw.DeviceEris.synthetic(o, v, gemm=gemm, int8_digits=digits, rank=rank, world=world)
+print("ranks: %d" % world)
 print("gemm engine: %s" % ("int8, %d digits" % de.int8_digits if de.int8_digits else "dmma"), flush=True)
 torch.cuda.synchronize()
 print("eris ready %.1fs, mem %.1f GB" % (time.time() - t0, torch.cuda.memory_allocated() / 1e9), flush=True)
@@ -42,5 +50,8 @@ for name, fn in (("tupdate", lambda: cc.tupdate(t1, t2, fsp=fsp)), ("lupdate", l
         print("   %8.2f ms %-8s M%-7d N%-7d K%-8d b%-5d %6.1f TF  %s" % (x["ms"], x["kind"], x["M"], x["N"], x["K"], x["batch"], fl / max(x["ms"], 1e-9) / 1e9, x["note"]))
     res[name] = {"ms": s.elapsed_time(e), "ops": ops}
 print("peak mem %.1f GB" % (torch.cuda.max_memory_allocated() / 1e9))
-if len(sys.argv) > 3 and sys.argv[3] != "-":
+if len(sys.argv) > 3 and sys.argv[3] != "-" and rank == 0:
     json.dump(res, open(sys.argv[3], "w"))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
