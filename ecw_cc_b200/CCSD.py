@@ -52,6 +52,7 @@ class GCC(object):
         self.h2d_bytes = 0      # bytes staged host->device / device->host by this object
         self.d2h_bytes = 0
         self.h2d_reused = 0     # bytes NOT copied because the device copy of a returned array was reused
+        self.host_seconds = {"to_host_alloc": 0.0, "to_host_copy": 0.0}    # wall time of the result downloads
 
     # -- host <-> device staging ---------------------------------------------
     def _torch(self):
@@ -97,13 +98,19 @@ class GCC(object):
         returns writable arrays; its solvers never write into them — `GCC(..., track_outputs=False)` restores that.)"""
         import weakref
         torch = self._torch()
+        import time
         outs = []
+        torch.cuda.current_stream(self.eris.device).synchronize()          # the results are complete
+        t0 = time.perf_counter()
         for t in ts:
-            h = self._pinned(t.shape, t.dtype)
+            outs.append(self._pinned(t.shape, t.dtype))
+        t1 = time.perf_counter()
+        for h, t in zip(outs, ts):
             h.copy_(t, non_blocking=True)
             self.d2h_bytes += t.numel() * 8
-            outs.append(h)
         torch.cuda.current_stream(self.eris.device).synchronize()
+        self.host_seconds["to_host_alloc"] += t1 - t0
+        self.host_seconds["to_host_copy"] += time.perf_counter() - t1
         arrs = [h.numpy() for h in outs]
         for a, h, t in zip(arrs, outs, ts):
             if a.nbytes >= self.TRACK_MIN_BYTES:

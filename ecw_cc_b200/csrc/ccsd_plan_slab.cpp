@@ -570,7 +570,12 @@ void build_ccsd_lupdate(Plan& P, const Sizes& z, int has_alpha, int equation) {
       P.contract(1.0, g.rows(r2), "ijab", t1, "jb", 1.0, pr, "ia", "m3.t1");
       P.contract(1.0, g.rows(l2ph), "iajb", w3T, "jb", 1.0, pr, "ia");
       P.contract(1.0, g.rows(s.oovv_ph), "iajb", zz, "jb", 1.0, pr, "ia");
-      P.contract(-1.0, g.rows(s.ovvv), "icba", x_vv, "bc", 1.0, pr, "ia", "L1 ovvv.x_vv");
+      // ovvv[icba] x_vv[bc]: one matrix-vector product per i (K = v^2 split over the SMs; a batched lowering would run
+      // one CTA column per i)
+      for (int64_t i = 0; i < ni; ++i) {
+        Tensor oi = slice0(g.rows(s.ovvv), i, 1), ri = slice0(pr, i, 1);
+        P.contract(-1.0, reshape(oi, {v, v, v}), "cba", x_vv, "bc", 1.0, reshape(ri, {v}), "a", "L1 ovvv.x_vv");
+      }
     }
     P.sum_ranks_add(p, r1, "L1 slab terms");
     P.release(p);

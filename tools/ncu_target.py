@@ -1,8 +1,9 @@
 """Smallest program that launches the hot kernels at the benchmark shape, for ncu:
 one `GCC.tupdate` at (nocc, nvir) = (40, 400) on synthetic integrals (INT8 engine by default).
     python tools/ncu_target.py [int8|dmma] [nocc nvir]
-Order of the ozaki_gemm_kernel launches in a packed-path tupdate: 0 [ijae,be->ijab], 1 Woooo tau.oovv,
-2 hh ladder, 3 K1 pp ladder (79800 x 780 x 79800), 4 R9, 5 R1 ring, 6 R2 ring."""
+Order of the ozaki_gemm_kernel launches in a packed-path tupdate (csrc/ccsd_plan_slab.cpp, one GPU): 0 cc_Fvv tau~
+(split-K), 1 T1 ovvv (batched), 2 Woooo tau.oovv, 3 hh ladder, 4 K1 pp ladder (79800 x 780 x 79800), 5 R9, 6 [ijae,be->ijab],
+7 t1.ovvv (batched), 8 R1 Wovvo 16000^3, 9 R2 ring 16000^3."""
 import os
 import sys
 
