@@ -11,8 +11,8 @@ from .CCSD import GCC, gamma_CCSD  # noqa: F401
 from .CCS import Gccs  # noqa: F401
 from .devops import DevOps  # noqa: F401
 from .utilities import subdiff  # noqa: F401
-from .Solver_GS import Solver_CCSD, Solver_CCS  # noqa: F401
-from .Solver_ES import Solver_ES  # noqa: F401
+from .Solver_GS import Solver_CCSD  # noqa: F401
+from .harness import Solver_CCS, Solver_ES  # noqa: F401  (test harness: callers of the path, see harness/__init__.py)
 from . import exp_pot  # noqa: F401
 from . import molint  # noqa: F401
 

@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
     if jobs or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB_PATH]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-ldl", "-o", LIB_PATH]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
@@ -71,6 +71,9 @@ class _Lib(object):
             "ecw_version": (c_s, []),
             "ecw_ctx_set_shard": (c_i, [c_p, c_i, c_i]),
             "ecw_resume": (c_i, [c_p, c_p]),
+            "ecw_nccl_unique_id": (c_i, [c_s, c_p]),
+            "ecw_ctx_init_nccl": (c_i, [c_p, c_s, c_p, c_i, c_i]),
+            "ecw_ctx_nccl_ops": (c_l, [c_p]),
             "ecw_ctx_set_gemm": (c_i, [c_p, c_i, c_d]),
             "ecw_ctx_get_gemm": (c_i, [c_p]),
             "ecw_int8_error_bound": (c_i, [c_p, ctypes.POINTER(c_d), c_p]),

@@ -2,6 +2,8 @@
 // declared in include/ecw_b200.h.
 #include "../../include/ecw_b200.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -15,8 +17,27 @@
 
 using namespace ecw;
 
+// NCCL, resolved at run time from the library the process already has (torch's bundled libnccl.so.2): the product
+// library itself has no link-time dependency on it.  Only the handful of entry points the executor needs.
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: */ struct NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char internal[128]; };
+constexpr int kNcclDouble = 8;     // ncclFloat64
+
 struct ecw_ctx {
   Sizes z;
+  NcclApi nccl;
+  void* nccl_comm = nullptr;       // ncclComm_t of this context; null: collectives yield to the host
   std::string err;
   double* ptr[S_COUNT];
   int64_t ws_bytes = 0;
@@ -35,6 +56,7 @@ struct ecw_ctx {
   std::vector<cudaEvent_t> ev;
   const Plan* last_plan = nullptr;
   int sm_count = 0;        // 0: launchers query / assume 148
+  int64_t nccl_ops = 0;    // collectives the executor enqueued itself
   ecw_ctx() { for (auto& p : ptr) p = nullptr; }
 };
 
@@ -209,6 +231,27 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
       case OP_ALLGATHER:
       case OP_ALLTOALL: {
         if (op.a.slot != S_WS || op.c.slot != S_WS) throw Fail("collective operands must live in the workspace");
+        if (c->nccl_comm) {
+          // stream-ordered on the caller's stream: no return to the host
+          const double* snd = resolve(c, op.a);
+          double* rcv = resolve(c, op.c);
+          const size_t count = (size_t)op.i0;
+          int rc = 0;
+          if (op.kind == OP_ALLGATHER) {
+            rc = c->nccl.AllGather(snd, rcv, count, kNcclDouble, c->nccl_comm, st);
+          } else {
+            c->nccl.GroupStart();
+            for (int q = 0; q < (int)op.i1 && rc == 0; ++q) {
+              rc = c->nccl.Send(snd + (size_t)q * count, count, kNcclDouble, q, c->nccl_comm, st);
+              if (rc == 0) rc = c->nccl.Recv(rcv + (size_t)q * count, count, kNcclDouble, q, c->nccl_comm, st);
+            }
+            const int rc2 = c->nccl.GroupEnd();
+            if (rc == 0) rc = rc2;
+          }
+          if (rc != 0) throw Fail(std::string("NCCL: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(rc) : "error"));
+          ++c->nccl_ops;
+          break;
+        }
         c->pending[0] = op.kind == OP_ALLTOALL ? 2 : 1;     // kind: 1 all-gather, 2 all-to-all
         c->pending[1] = op.a.off;          // element offset of this rank's contribution in the workspace
         c->pending[2] = op.i0;             // elements per rank
@@ -342,8 +385,64 @@ int ecw_ctx_create(ecw_ctx** out, int nocc, int nvir) {
 void ecw_ctx_destroy(ecw_ctx* c) {
   if (!c) return;
   for (auto e : c->ev) cudaEventDestroy(e);
+  if (c->nccl_comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->nccl_comm);
   delete c;
 }
+
+namespace {
+bool load_nccl(NcclApi& api, const char* libpath, std::string& err) {
+  if (api.handle) return true;
+  const char* names[] = {libpath, "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n || !*n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) { err = std::string("cannot load NCCL: ") + (dlerror() ? dlerror() : "not found"); return false; }
+  auto sym = [&](const char* name) { return dlsym(h, name); };
+  api.GetUniqueId = reinterpret_cast<int (*)(void*)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(sym("ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(sym("ncclCommDestroy"));
+  api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(sym("ncclAllGather"));
+  api.Send = reinterpret_cast<int (*)(const void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclSend"));
+  api.Recv = reinterpret_cast<int (*)(void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclRecv"));
+  api.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd) {
+    err = "NCCL library lacks a required entry point";
+    return false;
+  }
+  api.handle = h;
+  return true;
+}
+}  // namespace
+
+int ecw_nccl_unique_id(const char* libpath, void* id128) {
+  NcclApi api;
+  std::string err;
+  if (!id128 || !load_nccl(api, libpath, err)) return -1;
+  return api.GetUniqueId(id128) == 0 ? 0 : -1;
+}
+
+int ecw_ctx_init_nccl(ecw_ctx* c, const char* libpath, const void* id128, int rank, int world) {
+  return guarded(c, [&] {
+    require_device();
+    if (!id128 || world < 2 || rank < 0 || rank >= world) throw Fail("ecw_ctx_init_nccl: bad arguments");
+    if (c->z.world != world || c->z.rank != rank) throw Fail("ecw_ctx_init_nccl: rank / world differ from ecw_ctx_set_shard");
+    std::string err;
+    if (!load_nccl(c->nccl, libpath, err)) throw Fail(err);
+    NcclId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    void* comm = nullptr;
+    const int rc = c->nccl.CommInitRank(&comm, world, id, rank);
+    if (rc != 0) throw Fail(std::string("ncclCommInitRank: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(rc) : "error"));
+    c->nccl_comm = comm;
+  });
+}
+
+int64_t ecw_ctx_nccl_ops(ecw_ctx* c) { return c ? c->nccl_ops : -1; }
 
 const char* ecw_last_error(ecw_ctx* c) { return c ? c->err.c_str() : "null context"; }
 

@@ -99,6 +99,7 @@ class DeviceEris(object):
         self.nvir = int(nvir)
         self.rank, self.world, self.group = int(rank), int(world), group
         self.comm = TorchDistComm(group)     # who performs the collectives of a sharded call (tests: virtual ranks)
+        self.own_nccl = False                # the context holds its own ncclComm_t (init_nccl)
         self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
         self._h = ctypes.c_void_p()
         if lib.ecw_ctx_create(ctypes.byref(self._h), self.nocc, self.nvir) != 0:
@@ -185,6 +186,31 @@ class DeviceEris(object):
                 self.comm.all_to_all(self, ws[roff: roff + world * count], ws[soff: soff + world * count])
             rc = lib.ecw_resume(self._h, self.stream())
         self.check(rc, what)
+
+    def init_nccl(self):
+        """Give the context its own NCCL communicator (include/ecw_b200.h): rank 0 draws the unique id, torch.distributed
+        broadcasts it, every rank joins.  The executor then enqueues the collectives itself.  Returns False (and keeps
+        the host-driven protocol) when torch.distributed is not running on NCCL or ECW_HOST_COLLECTIVES=1."""
+        torch = _torch()
+        if self.world < 2 or os.environ.get("ECW_HOST_COLLECTIVES", "0") == "1":
+            return False
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_backend(self.group) == "nccl"):
+            return False
+        libdir = os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib")
+        path = os.path.join(libdir, "libnccl.so.2")
+        path = path.encode() if os.path.exists(path) else b""
+        ident = (ctypes.c_char * 128)()
+        if self.rank == 0:
+            self.check(lib.ecw_nccl_unique_id(path, ident), "ecw_nccl_unique_id")
+        t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).to(self.device)
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(t, src=src, group=self.group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        torch.cuda.current_stream(self.device).synchronize()
+        self.check(lib.ecw_ctx_init_nccl(self._h, path, raw, self.rank, self.world), "ecw_ctx_init_nccl")
+        self.own_nccl = True
+        return True
 
     # -- guarded execution of one C entry point ----------------------------------------
     def int8_bound(self):
@@ -280,6 +306,7 @@ class DeviceEris(object):
         for attr in ("mo_occ", "EHF", "orbspin"):
             if hasattr(eris, attr):
                 setattr(self, attr, getattr(eris, attr))
+        self.init_nccl()
         return self
 
     @classmethod
@@ -320,6 +347,7 @@ class DeviceEris(object):
         self.fock_dev = self.synth_tensor("fock", (n, n))
         self.fock = self.fock_dev.cpu().numpy()
         torch.cuda.current_stream(self.device).synchronize()
+        self.init_nccl()
         return self
 
     def _pv(self):

@@ -7,6 +7,11 @@ Targets (exp_pot.py:131-345): 'mat' (ground or excited state rdm1), 'trmat' (lef
 AO pairs (PySCF `ft_ao`) and is not provided.  Property targets take their AO integrals from `mol`, which may be a PySCF
 `Mole` or `ecw_cc_b200.molint.Molecule` (same `intor_symmetric` / `with_common_orig` / `atom_charges` / `atom_coords`).
 
+Scope: only the 'mat' ground-state target is part of the product (`mat_update_device`, `ecw_vexp_mat`).
+The other targets are n x n host code kept as test HARNESS (callers of the path, SURVEY §2 "out of scope"): they let the
+excited-state configuration of BASELINE.json be driven on a box without PySCF, and are pinned to the reference class
+in tests/test_exp_pot_cpu.py.
+
 n x n work on the host, except for the case `Main.CCSD_GS` runs — one density-matrix target for the ground state —
 which `mat_update_device` evaluates on the GPU (`ecw_vexp_mat`): the device-resident solver (`ecw_cc_b200.Solver_CCSD`)
 then moves only scalars per iteration; for every other target it sends the rdm1 (n x n) to the host once per iteration

@@ -1,4 +1,4 @@
-"""Mirror of the reference's excited-state ECW-CCS solver `Solver_ES.Solver_ES` (Solver_ES.py:26-500, the `SCF`
+"""HARNESS, not part of the drop-in (see ecw_cc_b200/harness/__init__.py).  Mirror of the reference's excited-state ECW-CCS solver `Solver_ES.Solver_ES` (Solver_ES.py:26-500, the `SCF`
 method): coupled T / Lambda / R_n / L_n iteration for a ground state and N excited states with state (V_nn) and
 ground-to-excited transition (V_0n, V_n0) experimental potentials.
 
@@ -12,8 +12,8 @@ import copy
 
 import numpy as np
 
-from . import utilities
-from .diis import DIIS
+from .. import utilities
+from ..diis import DIIS
 
 
 class Solver_ES(object):

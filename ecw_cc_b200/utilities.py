@@ -1,5 +1,8 @@
 """Host-side mirror of `utilities.subdiff` (reference utilities.py:26-73) over
-the CUDA soft-threshold kernel (`ecw_subdiff`)."""
+the CUDA soft-threshold kernel (`ecw_subdiff`).
+Scope: `subdiff` is on the hot path.  Everything else here (AO-integral helpers, Koopmans guesses) serves
+the harness solvers and the property targets of `exp_pot.Exp` (ecw_cc_b200/harness/__init__.py), not the product path.
+"""
 import numpy as np
 
 from ._lib import lib, EcwError

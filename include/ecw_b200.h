@@ -54,6 +54,16 @@ const char* ecw_version(void);
  * ecw_resume until it returns 0. */
 int ecw_ctx_set_shard(ecw_ctx* ctx, int rank, int world);
 int ecw_resume(ecw_ctx* ctx, void* stream);
+/* The context's own NCCL communicator.  The library resolves NCCL at run time (dlopen of `libpath`, or of
+ * the libnccl.so.2 the process already has); rank 0 makes the 128-byte unique id with ecw_nccl_unique_id, the host
+ * hands it to every rank (any channel: the Python side broadcasts it with torch.distributed), and each rank calls
+ * ecw_ctx_init_nccl after ecw_ctx_set_shard.  From then on the collectives of a call (all-gathers of slab results,
+ * the all-to-all of Wovvo, the rank sums) are enqueued by the executor itself on the caller's stream — calls never
+ * return 1, nothing round-trips through the host.  Without it the yield protocol above stays in force (used by the
+ * single-GPU "virtual ranks" tests). */
+int ecw_nccl_unique_id(const char* libpath, void* id128);
+int ecw_ctx_init_nccl(ecw_ctx* ctx, const char* libpath, const void* id128, int rank, int world);
+int64_t ecw_ctx_nccl_ops(ecw_ctx* ctx);   /* collectives enqueued by the executor so far */
 /* GEMM engine.  int8_digits = 0: every contraction runs on the FP64 DMMA kernels.  int8_digits = 3..8:
  * unbatched GEMMs with 2MNK >= min_flops for which the time model of the engine prefers it (min_flops = -1: all of
  * them; min_flops = -t < -1.5: those with 2MNK >= t, no time model — tests) run on the INT8 tcgen05 tensor pipe by

@@ -37,6 +37,8 @@ for (o, v) in [(5, 9), (8, 20), (10, 33), (8, 16), (16, 24)]:     # the last two
             worst = max(worst, np.abs(a - c).max(), np.abs(b - d).max())
         worst = max(worst, np.abs(cc.gamma(t1, t2, l1, l2) - orc.gamma(t1, t2, l1, l2)).max())
         worst = max(worst, abs(cc.energy(t1, t2, fsp) - orc.energy(t1, t2, fsp)))
+# the collectives were enqueued by the library's own executor on its own ncclComm_t (no return to Python)
+assert cc.eris.own_nccl and ecw.lib.ecw_ctx_nccl_ops(cc.eris._h) > 20, (cc.eris.own_nccl, ecw.lib.ecw_ctx_nccl_ops(cc.eris._h))
 t = torch.tensor([worst], dtype=torch.float64, device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
