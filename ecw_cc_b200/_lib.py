@@ -82,6 +82,7 @@ class _Lib(object):
             "ecw_ctx_set_int8_splitk": (c_i, [c_p, c_l]),
             "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),
             "ecw_ctx_test_assume_ovvv_planes": (c_i, [c_p]),
+            "ecw_ctx_test_cut_cache_min": (c_i, [c_p, c_l]),
             "ecw_eris_ovvv_planes": (c_i, [c_p, c_p]),
             "ecw_ozaki_plane_bytes2": (c_l, [c_l, c_l, c_l, c_i]),
             "ecw_ozaki_stat_elems2": (c_l, [c_l, c_l]),

@@ -514,6 +514,13 @@ int ecw_ctx_test_assume_ovvv_planes(ecw_ctx* c) {
   return 0;
 }
 
+int ecw_ctx_test_cut_cache_min(ecw_ctx* c, int64_t min_elems) {
+  if (!c || min_elems < 1) return -1;
+  c->z.cut_cache_min_elems = min_elems;
+  drop_plans(c);
+  return 0;
+}
+
 int ecw_eris_vvvv_planes(ecw_ctx* c, const double* rows, int64_t row0, int64_t nrows, void* stream) {
   return guarded(c, [&] {
     require_device();

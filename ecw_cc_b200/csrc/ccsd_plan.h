@@ -21,12 +21,14 @@ struct Sizes {
   // packed-path lowering: false = ccsd_plan_slab.cpp (o^2v^2 work on slabs of the leading occupied index, fused
   // antisymmetriser), true = the round-1 builders (ccsd_plan.cpp, *_v1) — kept for A/B measurements and tests
   bool legacy_packed = false;
+  int64_t cut_cache_min_elems = 1 << 20;   // operands at least this large keep their digit planes for a second use
   void apply(Plan& P) const {
     P.rank = rank; P.world = world;
     P.nocc = nocc; P.nvir = nvir;
     P.oz_ns = oz_ns; P.oz_min_flops = oz_min_flops; P.oz_splitk_min_k = oz_splitk_min_k;
     P.vvvv_planes = vvvv_planes && oz_ns > 0;
     P.ovvv_planes = ovvv_planes && oz_ns > 0;
+    P.cut_cache_min_elems = cut_cache_min_elems;
   }
 };
 

@@ -976,16 +976,24 @@ bool Plan::written_since(size_t op_index, int slot, int64_t lo, int64_t hi) cons
   return false;
 }
 
+// entry i leaves the cache: its planes are freed now, or — when a product that was handed the set has not been
+// emitted yet (oz_cut without its oz_release) — by that oz_release
+void Plan::retire_cut(size_t i) {
+  CutEntry& e = cut_cache[i];
+  if (e.users > 0) {
+    cut_orphans.push_back(e);
+  } else {
+    arena.release(e.set.stats.off);
+    arena.release(e.set.planes.off);
+  }
+  cut_cache.erase(cut_cache.begin() + i);
+}
+
 void Plan::drop_cuts_of(int slot, int64_t lo, int64_t hi) {
   for (size_t i = 0; i < cut_cache.size();) {
     CutEntry& e = cut_cache[i];
-    if (e.slot == slot && !(e.hi < lo || e.lo > hi)) {
-      arena.release(e.set.stats.off);
-      arena.release(e.set.planes.off);
-      cut_cache.erase(cut_cache.begin() + i);
-    } else {
-      ++i;
-    }
+    if (e.slot == slot && !(e.hi < lo || e.lo > hi)) retire_cut(i);
+    else ++i;
   }
 }
 
@@ -1000,19 +1008,15 @@ OzSet Plan::oz_cut(const Tensor& X, int64_t R, int64_t rs, int64_t K1, int64_t k
       if (e.slot == X.slot && e.off == X.off && e.R == R && e.rs == rs && e.K1 == K1 && e.ks1 == (K1 > 1 ? ks1 : e.ks1) &&
           e.K2 == K2 && e.ks2 == ks2 && e.ns == oz_ns && !written_since(e.op_index, e.slot, e.lo, e.hi)) {
         ++cut_cache_hits;
+        ++e.users;
         return e.set;
       }
     }
     // a stale entry of the same source is useless from now on
     for (size_t i = 0; i < cut_cache.size();) {
       CutEntry& e = cut_cache[i];
-      if (e.slot == X.slot && !(e.hi < lo || e.lo > hi) && written_since(e.op_index, e.slot, e.lo, e.hi)) {
-        arena.release(e.set.stats.off);
-        arena.release(e.set.planes.off);
-        cut_cache.erase(cut_cache.begin() + i);
-      } else {
-        ++i;
-      }
+      if (e.slot == X.slot && !(e.hi < lo || e.lo > hi) && written_since(e.op_index, e.slot, e.lo, e.hi)) retire_cut(i);
+      else ++i;
     }
   }
   OzSet s;
@@ -1032,16 +1036,34 @@ OzSet Plan::oz_cut(const Tensor& X, int64_t R, int64_t rs, int64_t K1, int64_t k
   sp.note = note;
   ops.push_back(sp);
   if (cacheable) {
-    CutEntry e{X.slot, X.off, R, rs, K1, ks1, K2, ks2, oz_ns, lo, hi, ops.size() - 1, s};
+    CutEntry e{X.slot, X.off, R, rs, K1, ks1, K2, ks2, oz_ns, lo, hi, ops.size() - 1, s, 1};
     cut_cache.push_back(e);
   }
   return s;
 }
 
 void Plan::oz_release(const OzSet& s) {
-  if (!s.owned) return;
-  release(s.stats);
-  release(s.planes);
+  if (s.owned) {
+    release(s.stats);
+    release(s.planes);
+    return;
+  }
+  if (!s.cached) return;                     // constant plane sets
+  for (CutEntry& e : cut_cache)
+    if (e.set.planes.off == s.planes.off) {
+      if (e.users > 0) --e.users;
+      return;
+    }
+  for (size_t i = 0; i < cut_orphans.size(); ++i) {
+    CutEntry& e = cut_orphans[i];
+    if (e.set.planes.off != s.planes.off) continue;
+    if (--e.users <= 0) {
+      arena.release(e.set.stats.off);
+      arena.release(e.set.planes.off);
+      cut_orphans.erase(cut_orphans.begin() + i);
+    }
+    return;
+  }
 }
 
 OzSet Plan::oz_const_vvvv(int64_t rows) const {

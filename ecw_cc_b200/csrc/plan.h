@@ -218,8 +218,11 @@ class Plan {
     int64_t lo, hi;          // element range of the source view
     size_t op_index;         // the OP_OZ_SPLIT that made the planes
     OzSet set;
+    int users = 0;           // oz_cut calls not yet matched by oz_release: the planes must stay allocated
   };
   std::vector<CutEntry> cut_cache;
+  std::vector<CutEntry> cut_orphans;   // dropped from the cache (source released / overwritten) while still in use
+  void retire_cut(size_t i);
   int64_t cut_cache_min_elems = 1 << 20;
   int64_t cut_cache_hits = 0;
 

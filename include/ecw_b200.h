@@ -208,6 +208,9 @@ int64_t ecw_op_workspace_needed(ecw_ctx* ctx);
  * digit-plane ladders can be dumped and replayed on a box without a GPU). */
 int ecw_ctx_test_assume_vvvv_planes(ecw_ctx* ctx);
 int ecw_ctx_test_assume_ovvv_planes(ecw_ctx* ctx);
+/* Host-only test hook: operands of at least min_elems elements keep their digit planes for a second use within a
+ * plan (default 2^20); small values let CPU-sized plans exercise that cache. */
+int ecw_ctx_test_cut_cache_min(ecw_ctx* ctx, int64_t min_elems);
 /* JSON dump of the op list a call would launch (host only, no CUDA). */
 int64_t ecw_plan_dump(ecw_ctx* ctx, const char* func, int mode_flags, char* buf, int64_t buflen);
 /* the same for one ecw_op_contract call (operands appear as slots "a0", "a1", "b0"; host only, pointers unused) */

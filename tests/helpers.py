@@ -14,7 +14,7 @@ def load_golden(name):
 
 
 def plan_json(lib, o, v, func, flags, rank=0, world=1, int8_digits=0, min_flops=-1.0, vvvv_planes=False,
-              ovvv_planes=False, splitk_min_k=None):
+              ovvv_planes=False, splitk_min_k=None, cut_cache_min=None):
     """Plan of one call.  int8_digits > 0: INT8 tensor-core engine for every unbatched GEMM with
     2MNK >= min_flops; vvvv_planes: the packed vvvv is bound as digit planes (needs a device for the
     real entry point, so the flag is flipped through the test hook ecw_ctx_test_assume_vvvv_planes)."""
@@ -30,6 +30,8 @@ def plan_json(lib, o, v, func, flags, rank=0, world=1, int8_digits=0, min_flops=
             assert lib.ecw_ctx_test_assume_vvvv_planes(h) == 0
         if ovvv_planes:
             assert lib.ecw_ctx_test_assume_ovvv_planes(h) == 0
+        if cut_cache_min is not None:
+            assert lib.ecw_ctx_test_cut_cache_min(h, cut_cache_min) == 0
     try:
         n = 1 << 24
         buf = ctypes.create_string_buffer(n)

@@ -245,6 +245,13 @@ class Interp(object):
         nka, nkb_b = (8 * op["a"]["dim"][0] - 4096) // (ns * Ap * 32), (8 * op["b"]["dim"][0] - 4096) // (ns * Bp * 32)
         DA, DB = oz_from_planes(ba, ns, Ap, nka), oz_from_planes(bb, ns, Bp, nkb_b)
         c = op["c"]
+        # the product must not write over the planes / statistics it reads (workspace lifetimes of the plan)
+        c_lo = c["off"]
+        c_hi = c["off"] + (op["batch"] - 1) * op["sC"] + (M - 1) * op["i1"] + (N - 1) * op["i2"]
+        for k in "abde":
+            t = op[k]
+            if t and t["slot"] == c["slot"]:
+                assert c_hi < t["off"] or c_lo > t["off"] + t["dim"][0] - 1, "oz_gemm output overlaps operand %s: %s" % (k, op["note"])
         for b in range(op["batch"]):
             ar, br = a_row0 + b * a_rowb, b_row0 + b * b_rowb
             ka, kb = (a_kb0 + b * a_kbb) * 32, (b_kb0 + b * b_kbb) * 32

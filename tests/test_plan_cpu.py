@@ -144,7 +144,7 @@ from plan_interp import oz_const_slots
 
 
 def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_planes=True, ovvv_planes=False,
-               splitk_min_k=None):
+               splitk_min_k=None, cut_cache_min=None):
     orc = OracleGCC(er)
     base = eris_slots(er)
     base.update(t1=t1, t2=t2, l1=l1, l2=l2, fsp=fsp, fock=er.fock.copy())
@@ -162,7 +162,8 @@ def _run_modes(built_lib, o, v, t1, t2, l1, l2, fsp, er, antisym, ns, tol, vvvv_
     for tag, alpha, eq in MODES:
         for fn in ("tupdate", "lupdate"):
             pl = plan_json(built_lib, o, v, fn, flags_of(alpha, eq, antisym=antisym), int8_digits=ns, min_flops=-1.0,
-                           vvvv_planes=vvvv_planes, ovvv_planes=ovvv_planes, splitk_min_k=splitk_min_k)
+                           vvvv_planes=vvvv_planes, ovvv_planes=ovvv_planes, splitk_min_k=splitk_min_k,
+                           cut_cache_min=cut_cache_min)
             if splitk_min_k:
                 assert any(op["kind"] == "oz_gemm" and "split-K" in op["note"] for op in pl["ops"]), fn
             if ovvv_planes:
@@ -252,3 +253,21 @@ def test_int8_engine_split_k(built_lib):
     er = synth.SynthEris(o, v)
     t1, t2, l1, l2 = synth.amplitudes(o, v)
     _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, True, 6, 1e-12, splitk_min_k=64)
+
+
+@pytest.mark.parametrize("antisym", [True, False])
+def test_int8_engine_cut_cache(built_lib, antisym):
+    """Operands that are cut twice keep their digit planes (Plan::oz_cut cache).  The threshold is lowered so that
+    every cut of this small case goes through the cache: planes must survive until the last product that was handed
+    them, also when their source buffer is released first (the (16,96) regression of round 2)."""
+    o, v = 8, 16
+    er = synth.SynthEris(o, v)
+    if antisym:
+        t1, t2, l1, l2 = synth.amplitudes(o, v)
+    else:
+        rng = np.random.default_rng(10)
+        t1, l1 = 0.05 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, v))
+        t2, l2 = 0.02 * rng.standard_normal((o, o, v, v)), 0.02 * rng.standard_normal((o, o, v, v))
+    for ovvv_planes in (True, False):
+        _run_modes(built_lib, o, v, t1, t2, l1, l2, synth.fsp(o, v), er, antisym, 6, 1e-12, ovvv_planes=ovvv_planes,
+                   cut_cache_min=1)
