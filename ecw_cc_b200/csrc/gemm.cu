@@ -111,7 +111,7 @@ struct SmemLayout {
 };
 
 template <int BM, int BN, int WM, int WN, int BK, int TA, int TB, int STAGES, int ILV>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 128 * 48) ? 2 : 1)
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BK == 8) ? ((BM * BN <= 80 * 80) ? 3 : 2) : ((BM * BN <= 128 * 48) ? 2 : 1))
 dgemm_kernel(GemmArgs p) {
   constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
   constexpr int MI = WM / 8, NI = WN / 8;
@@ -212,36 +212,178 @@ dgemm_kernel(GemmArgs p) {
   }
   cp_async_wait<0>();
 
-  // ---- epilogue
+  // ---- epilogue.  With beta != 0 the old values of a group of fragment rows are all fetched before the first store of
+  // the group (RG * NI independent loads in flight per thread): a load-add-store chain per fragment would serialise on
+  // the memory latency, which is the whole run time of the K = nocc rank updates (huge M*N, three k-tiles).
   const double alpha = p.alpha, beta = p.beta;
   const bool vecC = p.vecC;
+  constexpr int RG = (MI >= 2 && THREADS < 512) ? 2 : 1;     // 512-thread tiles run under a 128-register cap
 #pragma unroll
-  for (int i = 0; i < MI; ++i) {
-    const int64_t m = m0 + wm0 + i * 8 + g;
-    if (m >= p.M) continue;
+  for (int i0 = 0; i0 < MI; i0 += RG) {
+    double2 old[RG][NI];
+    if (beta != 0.0) {
 #pragma unroll
-    for (int j = 0; j < NI; ++j) {
-      const int64_t n = n0 + wn0 + j * 8 + 2 * tig;
-      if (n >= p.N) continue;
-      double* c = C + m * p.ldc + n;
-      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-      if (vecC && n + 1 < p.N) {
-        if (beta != 0.0) {
-          double2 old = *reinterpret_cast<const double2*>(c);
-          v0 += beta * old.x;
-          v1 += beta * old.y;
+      for (int ii = 0; ii < RG; ++ii) {
+        const int64_t m = m0 + wm0 + (i0 + ii) * 8 + g;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int64_t n = n0 + wn0 + j * 8 + 2 * tig;
+          old[ii][j] = make_double2(0.0, 0.0);
+          if (i0 + ii < MI && m < p.M && n < p.N) {
+            const double* c = C + m * p.ldc + n;
+            if (vecC && n + 1 < p.N) {
+              old[ii][j] = *reinterpret_cast<const double2*>(c);
+            } else {
+              old[ii][j].x = c[0];
+              if (n + 1 < p.N) old[ii][j].y = c[1];
+            }
+          }
         }
-        *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
-      } else {
-        if (beta != 0.0) v0 += beta * c[0];
-        c[0] = v0;
-        if (n + 1 < p.N) {
-          if (beta != 0.0) v1 += beta * c[1];
-          c[1] = v1;
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < RG; ++ii) {
+      if (i0 + ii >= MI) continue;
+      const int i = i0 + ii;
+      const int64_t m = m0 + wm0 + i * 8 + g;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int64_t n = n0 + wn0 + j * 8 + 2 * tig;
+        if (n >= p.N) continue;
+        double* c = C + m * p.ldc + n;
+        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+        if (beta != 0.0) {
+          v0 += beta * old[ii][j].x;
+          v1 += beta * old[ii][j].y;
+        }
+        if (vecC && n + 1 < p.N) {
+          *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
+        } else {
+          c[0] = v0;
+          if (n + 1 < p.N) c[1] = v1;
         }
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// N == 1: matrix-vector products (the ovvv / oovv_ph contractions with a singles-sized operand, CCSD.py:363, 377, 499
+// and the rdm1 'vo' block).  Bound by the one pass over A: every thread keeps 8 independent 16-byte loads in flight.
+// x[k] = B[k * xs]; partial sums of the batch / split-K slices are written like the GEMM kernel writes them
+// (C + zb * sC), the plan's OP_REDUCE adds them in a fixed order.
+// ta == 1: A[k * lda + m].  CTA = 4 k-lanes x 64 threads, thread = two adjacent m.
+__global__ void __launch_bounds__(256) dgemv_mcontig_kernel(GemmArgs p, int64_t xs) {
+  __shared__ double2 red[4][64];
+  const int tx = threadIdx.x & 63, ky = threadIdx.x >> 6;
+  const int64_t zb = blockIdx.y, r = zb / p.splitk, s = zb % p.splitk;
+  const int64_t kbeg = s * p.kchunk, kend = min(p.K, kbeg + p.kchunk);
+  const double* __restrict__ A = p.A + r * p.sA;
+  const double* __restrict__ x = p.B + r * p.sB;
+  const int64_t m = ((int64_t)blockIdx.x * 64 + tx) * 2;
+  double2 acc = make_double2(0.0, 0.0);
+  if (m < p.M) {
+    const bool pair = m + 1 < p.M;
+    if (p.vecA && pair) {
+      int64_t k = kbeg + ky;
+      for (; k + 28 < kend; k += 32) {
+        double2 a[8];
+        double xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          a[u] = *reinterpret_cast<const double2*>(A + (k + 4 * u) * p.lda + m);
+          xv[u] = x[(k + 4 * u) * xs];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc.x = fma(a[u].x, xv[u], acc.x);
+          acc.y = fma(a[u].y, xv[u], acc.y);
+        }
+      }
+      for (; k < kend; k += 4) {
+        const double2 a = *reinterpret_cast<const double2*>(A + k * p.lda + m);
+        const double xv = x[k * xs];
+        acc.x = fma(a.x, xv, acc.x);
+        acc.y = fma(a.y, xv, acc.y);
+      }
+    } else {
+      for (int64_t k = kbeg + ky; k < kend; k += 4) {
+        const double xv = x[k * xs];
+        acc.x = fma(A[k * p.lda + m], xv, acc.x);
+        if (pair) acc.y = fma(A[k * p.lda + m + 1], xv, acc.y);
+      }
+    }
+  }
+  red[ky][tx] = acc;
+  __syncthreads();
+  if (ky == 0 && m < p.M) {
+    double sx = red[0][tx].x, sy = red[0][tx].y;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      sx += red[q][tx].x;
+      sy += red[q][tx].y;
+    }
+    double* c = p.C + zb * p.sC + m * p.ldc;
+    c[0] = p.alpha * sx + (p.beta != 0.0 ? p.beta * c[0] : 0.0);
+    if (m + 1 < p.M) c[p.ldc] = p.alpha * sy + (p.beta != 0.0 ? p.beta * c[p.ldc] : 0.0);
+  }
+}
+// ta == 0: A[m * lda + k].  One warp per row, lanes along k (two adjacent k per lane).
+__global__ void __launch_bounds__(256) dgemv_kcontig_kernel(GemmArgs p, int64_t xs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t zb = blockIdx.y, r = zb / p.splitk, s = zb % p.splitk;
+  const int64_t kbeg = s * p.kchunk, kend = min(p.K, kbeg + p.kchunk);
+  if (m >= p.M) return;
+  const double* __restrict__ a = p.A + r * p.sA + m * p.lda;
+  const double* __restrict__ x = p.B + r * p.sB;
+  double s0 = 0.0, s1 = 0.0;
+  if (p.vecA && xs == 1 && (kbeg & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // 512 k per pass: eight independent (predicated) 16-byte loads of A and of x per lane
+    for (int64_t k0 = kbeg; k0 < kend; k0 += 512) {
+      double2 av[8], xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t k = k0 + 2 * lane + 64 * u;
+        av[u] = make_double2(0.0, 0.0);
+        xv[u] = make_double2(0.0, 0.0);
+        if (k + 1 < kend) {
+          av[u] = *reinterpret_cast<const double2*>(a + k);
+          xv[u] = *reinterpret_cast<const double2*>(x + k);
+        } else if (k < kend) {
+          av[u].x = a[k];
+          xv[u].x = x[k];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s0 = fma(av[u].x, xv[u].x, s0);
+        s1 = fma(av[u].y, xv[u].y, s1);
+      }
+    }
+  } else {
+    for (int64_t k = kbeg + lane; k < kend; k += 32) s0 = fma(a[k], x[k * xs], s0);
+  }
+  s0 += s1;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+  if (lane == 0) {
+    double* c = p.C + zb * p.sC + m * p.ldc;
+    c[0] = p.alpha * s0 + (p.beta != 0.0 ? p.beta * c[0] : 0.0);
+  }
+}
+
+cudaError_t launch_gemv(const GemmArgs& p, cudaStream_t st) {
+  const int64_t xs = p.tb ? 1 : p.ldb;             // B[k*ldb + 0] (tb == 0) or B[0*ldb + k] (tb == 1)
+  if (p.ta) {
+    dim3 grid((unsigned)((p.M + 127) / 128), (unsigned)p.batch, 1);
+    dgemv_mcontig_kernel<<<grid, 256, 0, st>>>(p, xs);
+  } else {
+    dim3 grid((unsigned)((p.M + 7) / 8), (unsigned)p.batch, 1);
+    dgemv_kcontig_kernel<<<grid, 256, 0, st>>>(p, xs);
+  }
+  return cudaGetLastError();
 }
 
 template <int BM, int BN, int WM, int WN, int BK, int STAGES, int ILV>
@@ -267,17 +409,33 @@ cudaError_t launch_cfg(const GemmArgs& p, cudaStream_t st) {
 
 }  // namespace
 
-int gemm_pick_config(int64_t M, int64_t N) {
+int gemm_pick_config(int64_t M, int64_t N, int64_t K) {
   // 1: 32x128  2: 128x32  3: 128x8  4: 64x64  8: 128x128 (16 warps, interleaved loads)
   // 10: 112x128  11: 96x128 (8 warps) — chosen when they cut the padded-row waste of the M dimension
   // 12: 48x128  13: 128x48 — one tile covers a whole occupied index of up to 48 (no operand re-read)
+  // 14: 40x40  15: 48x48 — both extents an occupied index
+  // 16: 128x40 — N an occupied index of 33..40 (ovvv.t1 products: no DMMA work on padding columns)
+  // 17: 40x200 — measured slower than 48x128 for ovvv.t2 (5 warps per SM do not cover the loads); kept for A/B only
+  // 18: 40x128  19: 80x80, both with BK = 8 and six stages — short-K rank updates (see below)
+  // (tried and dropped: issuing the old-C loads of a short-K tile before the operand wait — 2-3x slower, gemm per-op
+  //  logs profiles/r2_perop_dmma_variants.md)
   if (N <= 8) return 3;
+  auto padded = [](int64_t x, int64_t b) { return (x + b - 1) / b * b; };
+  if (K > 0 && K <= 40 && K % 8 == 0 && N >= 80) {
+    // rank updates over an occupied index (K = nocc, huge M*N): BK = 8 tiles carry no K padding, exact 40 / 80 extents
+    // no M/N padding (a 48x128x48 tile spends 1.44x the DMMA work of 40x128x40), and the small stages leave room for
+    // three CTAs per SM — these launches are bound by the memory round trips of a tile, not by a pipe
+    if (M > 16 && M <= 40) return 18;
+    if (M > 40 && padded(N, 80) <= padded(N, 128) && padded(M, 80) <= padded(M, 128)) return 19;
+  }
+  if (M <= 40 && N <= 40 && M > 16 && N > 16) return 14;     // Gram products over a long index ([mnef,inef->mi], ...):
+  if (M <= 48 && N <= 48 && M > 16 && N > 16) return 15;     // one exact tile, no DMMA work on padding columns
   if (M <= 32) return 1;
   if (M <= 48) return 12;
   if (N <= 32) return 2;
+  if (N <= 40) return 16;
   if (N <= 48) return 13;
   if (M <= 96 || N <= 96) return 4;
-  auto padded = [](int64_t x, int64_t b) { return (x + b - 1) / b * b; };
   double w128 = (double)padded(M, 128) * padded(N, 128);
   double w64 = (double)padded(M, 64) * padded(N, 64);
   if (w64 * 1.15 < w128) return 4;
@@ -297,9 +455,17 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
   p.vecB = aligned(p.B) && (p.ldb % 2 == 0) && (p.sB % 2 == 0);
   p.vecC = aligned(p.C) && (p.ldc % 2 == 0) && (p.sC % 2 == 0);
   if (p.batch > 65535) return cudaErrorInvalidValue;
-  int cfg = force_cfg >= 0 ? force_cfg : gemm_pick_config(p.M, p.N);
+  // matrix-vector products with long rows / many rows; short rows (K = nvir) and M-contiguous A with few rows and many
+  // K slices keep the GEMM route, which measured faster there (profiles/r2_perop_dmma_variants.md)
+  if (p.N == 1 && force_cfg < 0 && (p.M + 7) / 8 < 0x7fffffff && (p.ta ? p.M >= 1024 : p.kchunk >= 2048))
+    return launch_gemv(p, st);
+  int cfg = force_cfg >= 0 ? force_cfg : gemm_pick_config(p.M, p.N, p.kchunk);
   // large aligned problems: TMA producer + mbarrier ring + DMMA consumers (gemm_tma.cu)
-  static const bool no_tma = getenv("ECW_NO_TMA") != nullptr;
+#ifdef ECW_OZ_EXPERIMENT
+  static const bool no_tma = getenv("ECW_NO_TMA") != nullptr;      // experiment builds only (tools/)
+#else
+  constexpr bool no_tma = false;
+#endif
   if (cfg >= 20 || (force_cfg < 0 && !no_tma && (cfg == 8 || cfg == 10 || cfg == 11))) {
     if (gemm_tma_eligible(p)) {
       int tcfg = cfg >= 20 ? cfg : ((cfg != 8 && p.ta == 0) ? 21 : 20);
@@ -324,6 +490,12 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
     case 12: return launch_cfg<48, 128, 48, 16, 16, 4, 1>(p, st);
     case 13: return launch_cfg<128, 48, 32, 24, 16, 4, 1>(p, st);
     case 11: return launch_cfg<96, 128, 48, 32, 16, 4, 1>(p, st);
+    case 14: return launch_cfg<40, 40, 40, 8, 16, 4, 1>(p, st);
+    case 15: return launch_cfg<48, 48, 48, 8, 16, 4, 1>(p, st);
+    case 16: return launch_cfg<128, 40, 32, 40, 16, 4, 1>(p, st);
+    case 17: return launch_cfg<40, 200, 40, 40, 16, 3, 1>(p, st);
+    case 18: return launch_cfg<40, 128, 40, 16, 8, 6, 1>(p, st);
+    case 19: return launch_cfg<80, 80, 40, 40, 8, 6, 1>(p, st);
     default: return cudaErrorInvalidValue;
   }
 }

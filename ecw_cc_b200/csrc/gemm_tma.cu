@@ -211,24 +211,48 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) mbar_arrive(&empty[st]);
   }
 
-  // ---- epilogue: logical fragment coordinates -> tile coordinates through the same permutations
+  // ---- epilogue: logical fragment coordinates -> tile coordinates through the same permutations.  With beta != 0 the
+  // old values of two fragment rows (4 NI scalars) are fetched before the first store (see gemm.cu).
   const double alpha = p.alpha, beta = p.beta;
   double* __restrict__ C = p.C + zb * p.sC;
+  auto row_of = [&](int i) { return m0 + wm0 + (TA == 0 ? i * 8 + rho(g) : (i >> 1) * 16 + mu(g) + (i & 1) * 4); };
+  auto col_of = [&](int j, int e) {
+    const int nl = 2 * tig + e;
+    return n0 + wn0 + (TB == 1 ? j * 8 + rho(nl) : (j >> 1) * 16 + mu(nl) + (j & 1) * 4);
+  };
 #pragma unroll
-  for (int i = 0; i < MI; ++i) {
-    const int64_t m = m0 + wm0 + (TA == 0 ? i * 8 + rho(g) : (i >> 1) * 16 + mu(g) + (i & 1) * 4);
-    if (m >= p.M) continue;
+  for (int i0 = 0; i0 < MI; i0 += 2) {
+    double old[2][NI][2];
+    if (beta != 0.0) {
 #pragma unroll
-    for (int j = 0; j < NI; ++j) {
+      for (int ii = 0; ii < 2; ++ii) {
+        if (i0 + ii >= MI) continue;
+        const int64_t m = row_of(i0 + ii);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int nl = 2 * tig + e;
-        const int64_t n = n0 + wn0 + (TB == 1 ? j * 8 + rho(nl) : (j >> 1) * 16 + mu(nl) + (j & 1) * 4);
-        if (n >= p.N) continue;
-        double* c = C + m * p.ldc + n;
-        double v = alpha * acc[i][j][e];
-        if (beta != 0.0) v += beta * *c;
-        *c = v;
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int64_t n = col_of(j, e);
+            old[ii][j][e] = (m < p.M && n < p.N) ? C[m * p.ldc + n] : 0.0;
+          }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = i0 + ii;
+      if (i >= MI) continue;
+      const int64_t m = row_of(i);
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t n = col_of(j, e);
+          if (n >= p.N) continue;
+          double v = alpha * acc[i][j][e];
+          if (beta != 0.0) v += beta * old[ii][j][e];
+          C[m * p.ldc + n] = v;
+        }
       }
     }
   }

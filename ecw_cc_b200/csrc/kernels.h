@@ -15,7 +15,7 @@ struct GemmArgs {
   int vecA, vecB, vecC;   // filled by launch_gemm (16-byte cp.async / double2 stores allowed)
 };
 
-int gemm_pick_config(int64_t M, int64_t N);
+int gemm_pick_config(int64_t M, int64_t N, int64_t K = 0);
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st, int force_cfg = -1);
 // warp-specialised TMA + mbarrier variant (gemm_tma.cu); cfg 20: 128x128, 21: 112x128
 bool gemm_tma_eligible(const GemmArgs& a);

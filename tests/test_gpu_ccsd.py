@@ -23,13 +23,16 @@ def _dev(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 20, 21])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_dgemm_all_layouts(ecw, cfg, ta, tb):
     import torch
     rng = np.random.default_rng(10 * ta + tb + 100)
     for (M, N, K) in [(1, 1, 1), (7, 5, 3), (33, 17, 129), (130, 131, 67), (256, 128, 64), (45, 300, 1000),
-                      (300, 258, 520), (112, 128, 48), (2100, 517, 40)]:
+                      (300, 258, 520), (112, 128, 48), (2100, 517, 40), (2100, 40, 40), (40, 2100, 24), (2100, 400, 40), (400, 400, 40), (300, 161, 24),
+                      # exact-extent tiles for an occupied index of 33..48 and the matrix-vector kernels (cfg < 0)
+                      (1000, 40, 400), (40, 400, 5000), (37, 600, 4100), (40, 40, 20000), (48, 44, 3000),
+                      (999, 1, 777), (130, 1, 4098), (2, 1, 5), (1500, 1, 300), (64, 1, 2500)]:
         A = rng.standard_normal((K, M) if ta else (M, K))
         B = rng.standard_normal((N, K) if tb else (K, N))
         C0 = rng.standard_normal((M, N))
