@@ -416,6 +416,7 @@ int gemm_pick_config(int64_t M, int64_t N, int64_t K) {
   // 14: 40x40  15: 48x48 — both extents an occupied index
   // 16: 128x40 — N an occupied index of 33..40 (ovvv.t1 products: no DMMA work on padding columns)
   // 17: 40x200 — measured slower than 48x128 for ovvv.t2 (5 warps per SM do not cover the loads); kept for A/B only
+  // 22: 40x80 — like 17 measured slower than 48x128 on ovvv.t2 (16.2 vs 12.5 ms): five-warp CTAs; A/B only
   // 18: 40x128  19: 80x80, both with BK = 8 and six stages — short-K rank updates (see below)
   // (tried and dropped: issuing the old-C loads of a short-K tile before the operand wait — 2-3x slower, gemm per-op
   //  logs profiles/r2_perop_dmma_variants.md)
@@ -445,6 +446,15 @@ int gemm_pick_config(int64_t M, int64_t N, int64_t K) {
   return 8;
 }
 
+void gemm_tile_of(int64_t M, int64_t N, int64_t K, int* bm, int* bn) {
+  static const int dims[23][2] = {{128, 128}, {32, 128}, {128, 32}, {128, 8}, {64, 64}, {128, 128}, {128, 128}, {128, 128},
+                                  {128, 128}, {128, 128}, {112, 128}, {96, 128}, {48, 128}, {128, 48}, {40, 40}, {48, 48},
+                                  {128, 40}, {40, 200}, {40, 128}, {80, 80}, {128, 128}, {112, 128}, {40, 80}};
+  const int cfg = gemm_pick_config(M, N, K);
+  *bm = dims[cfg][0];
+  *bn = dims[cfg][1];
+}
+
 cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
   GemmArgs p = args;
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return cudaSuccess;
@@ -466,14 +476,15 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
 #else
   constexpr bool no_tma = false;
 #endif
-  if (cfg >= 20 || (force_cfg < 0 && !no_tma && (cfg == 8 || cfg == 10 || cfg == 11))) {
+  const bool tma_cfg = cfg == 20 || cfg == 21;
+  if (tma_cfg || (force_cfg < 0 && !no_tma && (cfg == 8 || cfg == 10 || cfg == 11))) {
     if (gemm_tma_eligible(p)) {
-      int tcfg = cfg >= 20 ? cfg : ((cfg != 8 && p.ta == 0) ? 21 : 20);
+      int tcfg = tma_cfg ? cfg : ((cfg != 8 && p.ta == 0) ? 21 : 20);
       cudaError_t e = launch_gemm_tma(p, st, tcfg);
       if (e != cudaErrorNotSupported) return e;
       cudaGetLastError();
     }
-    if (cfg >= 20) cfg = 8;
+    if (tma_cfg) cfg = 8;
   }
   switch (cfg) {
     case 0: return launch_cfg<128, 128, 32, 32, 16, 4, 0>(p, st);
@@ -496,6 +507,7 @@ cudaError_t launch_gemm(const GemmArgs& args, cudaStream_t st, int force_cfg) {
     case 17: return launch_cfg<40, 200, 40, 40, 16, 3, 1>(p, st);
     case 18: return launch_cfg<40, 128, 40, 16, 8, 6, 1>(p, st);
     case 19: return launch_cfg<80, 80, 40, 40, 8, 6, 1>(p, st);
+    case 22: return launch_cfg<40, 80, 40, 16, 16, 4, 1>(p, st);
     default: return cudaErrorInvalidValue;
   }
 }

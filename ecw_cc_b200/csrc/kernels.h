@@ -16,6 +16,8 @@ struct GemmArgs {
 };
 
 int gemm_pick_config(int64_t M, int64_t N, int64_t K = 0);
+// CTA tile the automatic choice uses for this problem (the plan sizes its split-K by the real tile count)
+void gemm_tile_of(int64_t M, int64_t N, int64_t K, int* bm, int* bn);
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st, int force_cfg = -1);
 // warp-specialised TMA + mbarrier variant (gemm_tma.cu); cfg 20: 128x128, 21: 112x128
 bool gemm_tma_eligible(const GemmArgs& a);

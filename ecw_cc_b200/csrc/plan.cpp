@@ -1,6 +1,7 @@
 // plan.cpp — plan container, workspace arena and the binary-contraction
 // lowering (TTGT with batch / split-K / layout search).  Host-only C++.
 #include "plan.h"
+#include "kernels.h"
 
 #include <algorithm>
 #include <cmath>
@@ -795,7 +796,11 @@ void Plan::contract(double alpha, const Tensor& A, const char* sa, const Tensor&
   int64_t R = (ch.bcls == 3) ? nb : 1;
   int64_t S = 1;
   if (ch.bcls == 0 || ch.bcls == 3) {
-    int64_t tiles = ((Md + 127) / 128) * ((Nd + 127) / 128) * R;
+    int bm = 128, bn = 128;
+    gemm_tile_of(Md, Nd, Kd, &bm, &bn);
+    bm = std::max(bm, 48);                       // the small Gram tiles keep the split count of the 48-wide ones
+    bn = std::max(bn, 48);
+    int64_t tiles = ((Md + bm - 1) / bm) * ((Nd + bn - 1) / bn) * R;
     if (tiles < 2 * sm_count && Kd >= 1024) {
       S = std::min<int64_t>((2 * sm_count + tiles - 1) / tiles, Kd / 512);
       while (S > 1 && (double)S * R * Md * Nd * 8.0 > 512e6) --S;
