@@ -55,6 +55,7 @@ struct ecw_ctx {
   int64_t need_ws = 0;
   std::vector<cudaEvent_t> ev;
   const Plan* last_plan = nullptr;
+  bool call_has_oz = false;      // the plan of the last call contains INT8 products (ecw_int8_error_bound)
   int sm_count = 0;        // 0: launchers query / assume 148
   int64_t nccl_ops = 0;    // collectives the executor enqueued itself
   ecw_ctx() { for (auto& p : ptr) p = nullptr; }
@@ -305,6 +306,9 @@ int run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
   c->profile_run = c->profile;
   // run-time error bound of the INT8-route products of this call (scal[15], ecw_int8_error_bound)
   if (c->ptr[S_SCAL]) ck(cudaMemsetAsync(c->ptr[S_SCAL] + 15, 0, sizeof(double), st), "reset int8 bound");
+  c->call_has_oz = false;
+  for (const Op& op : P.ops)
+    if (op.kind == OP_OZ_GEMM) { c->call_has_oz = true; break; }
   if (c->profile_run) {
     for (auto e : c->ev) cudaEventDestroy(e);
     c->ev.assign(P.ops.size() + 1, nullptr);
@@ -488,6 +492,10 @@ int ecw_int8_error_bound(ecw_ctx* c, double* bound_out, void* stream) {
     if (!bound_out) throw Fail("ecw_int8_error_bound: null pointer");
     if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!c->call_has_oz) {          // the last call launched no INT8 product: nothing to read, no synchronisation
+      *bound_out = 0.0;
+      return;
+    }
     ck(cudaMemcpyAsync(bound_out, c->ptr[S_SCAL] + 15, sizeof(double), cudaMemcpyDeviceToHost, st), "read int8 bound");
     ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
   });

@@ -55,8 +55,29 @@ class DevOps(object):
     def empty(self, *shape):
         return self.torch.empty(shape, dtype=self.torch.float64, device=self.dev)
 
+    POOL_MIN_BYTES = 1 << 20    # larger downloads go through pooled pinned blocks (a pageable D2H runs at ~2.5 GB/s)
+    POOL_DEPTH = 3
+
     def to_host(self, t):
-        return t.cpu().numpy()
+        """device -> fresh numpy array.  Large results (the o^2v^2 intermediates Wbija / Wakic) are DMA'd into pinned
+        blocks that return to a per-shape pool when the caller drops the array, as in GCC._to_host."""
+        if t.numel() * 8 < self.POOL_MIN_BYTES:
+            return t.cpu().numpy()
+        import weakref
+        torch = self.torch
+        pool = self.__dict__.setdefault("_pool", {})
+        key = tuple(t.shape)
+        free = pool.setdefault(key, [])
+        if free:
+            h = free.pop()
+            del free[self.POOL_DEPTH:]
+        else:
+            h = torch.empty(key, dtype=torch.float64, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        a = h.numpy()
+        weakref.finalize(a, free.append, h)
+        return a
 
     def scalar(self, t):
         """Device scalar -> Python float (one synchronising D2H read)."""
