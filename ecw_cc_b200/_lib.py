@@ -80,6 +80,8 @@ class _Lib(object):
             "ecw_ctx_set_engine_override": (c_i, [c_p, c_i]),
             "ecw_ctx_set_plan_variant": (c_i, [c_p, c_i]),
             "ecw_ctx_set_int8_splitk": (c_i, [c_p, c_l]),
+            "ecw_ctx_set_graphs": (c_i, [c_p, c_i]),
+            "ecw_ctx_graph_stats": (c_i, [c_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
             "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),
             "ecw_ctx_test_assume_ovvv_planes": (c_i, [c_p]),
             "ecw_ctx_test_cut_cache_min": (c_i, [c_p, c_l]),

@@ -56,6 +56,15 @@ struct ecw_ctx {
   std::vector<cudaEvent_t> ev;
   const Plan* last_plan = nullptr;
   bool call_has_oz = false;      // the plan of the last call contains INT8 products (ecw_int8_error_bound)
+  // CUDA-graph replay of the cached plans (tupdate / lupdate / gamma / energy on one GPU): a call whose plan and
+  // pointer bindings were seen before is ONE cudaGraphLaunch instead of several hundred kernel launches — the small
+  // molecular shapes (configs 1-3) are launch bound.  Captured on a private stream, launched on the caller's.
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t stamp = 0; };
+  std::map<std::string, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graphs = true;
+  uint64_t graph_clock = 0;
+  int64_t graph_hits = 0, graph_captures = 0;
   int sm_count = 0;        // 0: launchers query / assume 148
   int64_t nccl_ops = 0;    // collectives the executor enqueued itself
   ecw_ctx() { for (auto& p : ptr) p = nullptr; }
@@ -105,7 +114,14 @@ void ck(cudaError_t e, const char* what) {
 }
 
 // plans are rebuilt after every change of the configuration: nothing may keep pointing into the old ones
+void drop_graphs(ecw_ctx* c) {
+  for (auto& kv : c->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  c->graphs.clear();
+}
+
 void drop_plans(ecw_ctx* c) {
+  drop_graphs(c);
   c->plans.clear();
   c->run_plan_ptr = nullptr;
   c->last_plan = nullptr;
@@ -299,16 +315,66 @@ int run_plan_resume(ecw_ctx* c, cudaStream_t st) {
   return 0;
 }
 
-int run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st) {
+int run_plan(ecw_ctx* c, const Plan& P, double alpha_rt, cudaStream_t st, bool cached_plan = false) {
   if (P.workspace_elems() * 8 > c->ws_bytes)
     throw Fail("workspace too small: need " + std::to_string(P.workspace_elems() * 8) + " bytes, have " +
                std::to_string(c->ws_bytes));
   c->profile_run = c->profile;
+  c->call_has_oz = false;
+  bool collectives = false;
+  for (const Op& op : P.ops) {
+    if (op.kind == OP_OZ_GEMM) c->call_has_oz = true;
+    if (op.kind == OP_ALLGATHER || op.kind == OP_ALLTOALL) collectives = true;
+  }
+  if (cached_plan && c->use_graphs && !c->profile_run && !collectives && c->z.world == 1 && P.ops.size() >= 8) {
+    // key: the plan, the run-time scalar and every pointer a launch can resolve
+    std::string key(reinterpret_cast<const char*>(c->ptr), sizeof(c->ptr));
+    const void* pp = &P;
+    key.append(reinterpret_cast<const char*>(&pp), sizeof(pp));
+    key.append(reinterpret_cast<const char*>(&alpha_rt), sizeof(alpha_rt));
+    key.append(reinterpret_cast<const char*>(&c->copy_scal_to), sizeof(c->copy_scal_to));
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+      if (!c->cap_stream) ck(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+      ck(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+      cudaGraph_t graph = nullptr;
+      try {
+        if (c->ptr[S_SCAL]) ck(cudaMemsetAsync(c->ptr[S_SCAL] + 15, 0, sizeof(double), c->cap_stream), "reset int8 bound");
+        c->run_plan_ptr = &P;
+        c->pc = 0;
+        c->run_alpha = alpha_rt;
+        run_plan_resume(c, c->cap_stream);
+      } catch (...) {
+        cudaStreamEndCapture(c->cap_stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        c->run_plan_ptr = nullptr;
+        throw;
+      }
+      ck(cudaStreamEndCapture(c->cap_stream, &graph), "cudaStreamEndCapture");
+      ecw_ctx::GraphEntry ge;
+      cudaError_t e = cudaGraphInstantiate(&ge.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      ck(e, "cudaGraphInstantiate");
+      if (c->graphs.size() >= 24) {                 // least recently used entry goes
+        auto old = c->graphs.begin();
+        for (auto jt = c->graphs.begin(); jt != c->graphs.end(); ++jt)
+          if (jt->second.stamp < old->second.stamp) old = jt;
+        cudaGraphExecDestroy(old->second.exec);
+        c->graphs.erase(old);
+      }
+      it = c->graphs.emplace(key, ge).first;
+      ++c->graph_captures;
+    } else {
+      ++c->graph_hits;
+      c->copy_scal_to = nullptr;
+    }
+    it->second.stamp = ++c->graph_clock;
+    ck(cudaGraphLaunch(it->second.exec, st), "cudaGraphLaunch");
+    return 0;
+  }
   // run-time error bound of the INT8-route products of this call (scal[15], ecw_int8_error_bound)
   if (c->ptr[S_SCAL]) ck(cudaMemsetAsync(c->ptr[S_SCAL] + 15, 0, sizeof(double), st), "reset int8 bound");
-  c->call_has_oz = false;
-  for (const Op& op : P.ops)
-    if (op.kind == OP_OZ_GEMM) { c->call_has_oz = true; break; }
   if (c->profile_run) {
     for (auto e : c->ev) cudaEventDestroy(e);
     c->ev.assign(P.ops.size() + 1, nullptr);
@@ -389,6 +455,8 @@ int ecw_ctx_create(ecw_ctx** out, int nocc, int nvir) {
 void ecw_ctx_destroy(ecw_ctx* c) {
   if (!c) return;
   for (auto e : c->ev) cudaEventDestroy(e);
+  drop_graphs(c);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->nccl_comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->nccl_comm);
   delete c;
 }
@@ -499,6 +567,20 @@ int ecw_int8_error_bound(ecw_ctx* c, double* bound_out, void* stream) {
     ck(cudaMemcpyAsync(bound_out, c->ptr[S_SCAL] + 15, sizeof(double), cudaMemcpyDeviceToHost, st), "read int8 bound");
     ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
   });
+}
+
+int ecw_ctx_set_graphs(ecw_ctx* c, int on) {
+  if (!c) return -1;
+  c->use_graphs = on != 0;
+  if (!on) drop_graphs(c);
+  return 0;
+}
+
+int ecw_ctx_graph_stats(ecw_ctx* c, int64_t* hits, int64_t* captures) {
+  if (!c) return -1;
+  if (hits) *hits = c->graph_hits;
+  if (captures) *captures = c->graph_captures;
+  return 0;
 }
 
 int ecw_ctx_set_int8_splitk(ecw_ctx* c, int64_t min_k) {
@@ -673,7 +755,7 @@ int ecw_ccsd_tupdate(ecw_ctx* c, const double* t1, const double* t2, const doubl
     c->ptr[S_T1] = const_cast<double*>(t1); c->ptr[S_T2] = const_cast<double*>(t2);
     c->ptr[S_FSP] = const_cast<double*>(fsp); c->ptr[S_FOCK] = const_cast<double*>(fock);
     c->ptr[S_OUT1] = t1new; c->ptr[S_OUT2] = t2new;
-    return run_plan(c, get_plan(c, "tupdate", flags), alpha, static_cast<cudaStream_t>(stream));
+    return run_plan(c, get_plan(c, "tupdate", flags), alpha, static_cast<cudaStream_t>(stream), true);
   });
 }
 
@@ -686,7 +768,7 @@ int ecw_ccsd_lupdate(ecw_ctx* c, const double* t1, const double* t2, const doubl
     c->ptr[S_L1] = const_cast<double*>(l1); c->ptr[S_L2] = const_cast<double*>(l2);
     c->ptr[S_FSP] = const_cast<double*>(fsp); c->ptr[S_FOCK] = const_cast<double*>(fock);
     c->ptr[S_OUT1] = l1new; c->ptr[S_OUT2] = l2new;
-    return run_plan(c, get_plan(c, "lupdate", flags), alpha, static_cast<cudaStream_t>(stream));
+    return run_plan(c, get_plan(c, "lupdate", flags), alpha, static_cast<cudaStream_t>(stream), true);
   });
 }
 
@@ -697,7 +779,7 @@ int ecw_ccsd_gamma(ecw_ctx* c, const double* t1, const double* t2, const double*
     c->ptr[S_T1] = const_cast<double*>(t1); c->ptr[S_T2] = const_cast<double*>(t2);
     c->ptr[S_L1] = const_cast<double*>(l1); c->ptr[S_L2] = const_cast<double*>(l2);
     c->ptr[S_RDM1] = rdm1;
-    return run_plan(c, get_plan(c, "gamma", 0), 0.0, static_cast<cudaStream_t>(stream));
+    return run_plan(c, get_plan(c, "gamma", 0), 0.0, static_cast<cudaStream_t>(stream), true);
   });
 }
 
@@ -708,7 +790,7 @@ int ecw_ccsd_energy(ecw_ctx* c, const double* t1, const double* t2, const double
     c->ptr[S_FSP] = const_cast<double*>(fsp);
     if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
     c->copy_scal_to = e_out;
-    return run_plan(c, get_plan(c, "energy", 0), 0.0, static_cast<cudaStream_t>(stream));
+    return run_plan(c, get_plan(c, "energy", 0), 0.0, static_cast<cudaStream_t>(stream), true);
   });
 }
 

@@ -89,6 +89,13 @@ int ecw_ctx_set_plan_variant(ecw_ctx* ctx, int legacy_packed);
 /* INT8 products with fewer output tiles than SMs and a contraction length >= min_k (a multiple of 32) are cut into
  * equal K chunks, one product each, summed in a fixed order (default 65536; <= 0: never). */
 int ecw_ctx_set_int8_splitk(ecw_ctx* ctx, int64_t min_k);
+/* CUDA-graph replay (default on): on one GPU a call of ecw_ccsd_tupdate / lupdate / gamma / energy whose plan and
+ * pointer arguments were seen before is one cudaGraphLaunch on the caller's stream (captured on a private stream at the
+ * first such call; up to 24 graphs are kept, least recently used first out).  The small shapes of the molecular
+ * configurations are bound by the launch rate of the several hundred kernels of a residual evaluation.  Off while
+ * ecw_profile_enable is on and for sharded contexts.  ecw_ctx_graph_stats: replays / captures so far. */
+int ecw_ctx_set_graphs(ecw_ctx* ctx, int on);
+int ecw_ctx_graph_stats(ecw_ctx* ctx, int64_t* hits, int64_t* captures);
 int ecw_pending_collective(ecw_ctx* ctx, int64_t* desc6);
 
 /* ---- integral container (consumed type `Eris.geris`, Eris.py:132-154) ---- */

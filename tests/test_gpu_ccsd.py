@@ -342,3 +342,53 @@ def _check_properties(ecw, o, v, asym):
     del a0, an
     g = cc.gamma(t1, t2, l1, l2)
     assert abs(float(torch.trace(g)) - o) < 1e-10 and float((g - g.T).abs().max()) < 1e-14
+
+
+def test_graph_replay_equals_direct_launches(ecw, engine):
+    """CUDA-graph replay of the cached plans (ecw_ctx_set_graphs, default on): the same calls with the same pointer
+    arguments are replayed as one graph launch; results are bit-identical to direct launches, the guard scalar
+    is still produced, and a change of any pointer (here: new amplitudes) captures a new graph instead of replaying a
+    stale one."""
+    import torch
+    lib = ecw.lib
+    o, v = 8, 16
+    n = o + v
+    de = ecw.DeviceEris.synthetic(o, v)
+    cc = ecw.GCC(de)
+    t1, t2 = de.synth_tensor("t1", (o, v)), de.synth_tensor("t2", (o, o, v, v))
+    l1, l2 = de.synth_tensor("l1", (o, v)), de.synth_tensor("l2", (o, o, v, v))
+    fsp = de.synth_tensor("fsp", (n, n))
+
+    def evaluate(a2):
+        out = []
+        r = cc.tupdate(t1, a2, fsp=fsp, alpha=1e-3)
+        out += [x.clone() for x in r]
+        del r
+        r = cc.lupdate(t1, a2, l1, l2, fsp=fsp)
+        out += [x.clone() for x in r]
+        del r
+        g = cc.gamma(t1, a2, l1, l2)
+        out.append(g.clone())
+        del g
+        out.append(torch.as_tensor(float(cc.energy(t1, a2, fsp))))
+        return out
+
+    assert lib.ecw_ctx_set_graphs(de._h, 0) == 0
+    direct = evaluate(t2)
+    assert lib.ecw_ctx_set_graphs(de._h, 1) == 0
+    hits, caps = ctypes.c_int64(0), ctypes.c_int64(0)
+    runs = [evaluate(t2) for _ in range(4)]
+    assert lib.ecw_ctx_graph_stats(de._h, ctypes.byref(hits), ctypes.byref(caps)) == 0
+    assert caps.value >= 3 and hits.value >= 3, (hits.value, caps.value)       # tupdate / lupdate / gamma graphs, replayed
+    for r in runs:
+        for x, y in zip(direct, r):
+            assert torch.equal(x.cpu(), y.cpu())
+    # other amplitudes at another address: never a stale replay
+    t2b = (t2 * 1.25).contiguous()
+    lib.ecw_ctx_set_graphs(de._h, 0)
+    want = evaluate(t2b)
+    lib.ecw_ctx_set_graphs(de._h, 1)
+    got = evaluate(t2b)
+    for x, y in zip(want, got):
+        assert torch.equal(x.cpu(), y.cpu())
+    assert not torch.equal(want[1].cpu(), direct[1].cpu())
