@@ -392,6 +392,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries ONE JSON line: no NCCL banner ("NCCL version ..." is printed to stdout at NCCL_DEBUG=VERSION)
+        os.environ["NCCL_DEBUG"] = os.environ.get("ECW_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     o, v = args.nocc, args.nvir
     n = o + v
@@ -535,6 +537,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    gh, gc = ctypes.c_int64(0), ctypes.c_int64(0)
+    lib.ecw_ctx_graph_stats(de._h, ctypes.byref(gh), ctypes.byref(gc))
+    graph_stats = {"replays": gh.value, "captures": gc.value,
+                   "note": "one GPU: a call whose plan and pointer arguments were seen before is one cudaGraphLaunch of the "
+                           "same kernels (include/ecw_b200.h, ecw_ctx_set_graphs); gpu_launches counts the kernels"}
     anti = alpha is None
     launches = sum(cc.plan_launches(f, alpha, False, anti) for f in ("tupdate", "lupdate"))
     launches += cc.plan_launches("gamma") + cc.plan_launches("energy") + 3   # + antisymmetry checks
@@ -626,6 +633,7 @@ def run_ours(args):
                                 "rdm1, the experimental potential and the dressed Fock resident on the GPU; only "
                                 "Delta, vmax, the energy and the convergence distance (4 doubles) cross PCIe"},
         "parts": parts,
+        "cuda_graphs": graph_stats,
         "gpu_launches": int(launches * args.steps),
         "roofline": roofline,
     }
