@@ -376,6 +376,117 @@ def time_ccs(ecw, torch, o=24, v=240, reps=5):
     return out
 
 
+def config5_ladder(ecw, torch, dist, rank, world, reps=3):
+    """BASELINE.json configs[4] — "nocc=60 nvir=800, vvvv ladder sharded at 2/4/8 B200": the packed particle-particle
+    ladder (CCSD.py:305) R[ij_p, ab_p] = sum_{cd_p} tau_p[ij_p, cd_p] vvvv_p[ab_p, cd_p] at (60, 800) with the digit planes
+    of vvvv_p (613 GB) row-sharded over the packed virtual pair index, through the same C entry points the residual
+    plans use (ecw_eris_vvvv_planes, ecw_ozaki_split, ecw_ozaki_gemm) plus an NCCL all-gather of the result.  The whole
+    residual at this shape does not fit 8 x 180 GB with the current lowering; this is the sharded
+    ladder on its own.  Returns a dict (extra key `config5` of the bench line); never raises."""
+    from ecw_cc_b200 import lib
+    from ecw_cc_b200.eris import SYNTH_KIND
+    o, v, ns = 60, 800, 6
+    if os.environ.get("ECW_CONFIG5_SHAPE"):                     # smoke runs of this leg on a small shape
+        o, v = (int(x) for x in os.environ["ECW_CONFIG5_SHAPE"].split(","))
+    po, pv = o * (o - 1) // 2, v * (v - 1) // 2
+    nshmax = (pv + world - 1) // world
+    out = {"nocc": o, "nvir": v, "n_gpus": world, "what": "packed pp-ladder (CCSD.py:305) with vvvv planes row-sharded"}
+    try:
+        torch.cuda.empty_cache()
+        free, total = torch.cuda.mem_get_info()
+        need = ns * nshmax * pv * 1.01 + 8.0 * po * pv * 2.8 + 8.0 * po * nshmax * (world + 1) + 2.5e9
+        out["per_rank_gb"] = {"vvvv_planes": ns * nshmax * pv / 1e9, "tau_fp64_and_planes": 8.0 * po * pv * 1.75 / 1e9,
+                              "result_shard_gathered_full": 8.0 * po * (nshmax * (world + 1) + pv) / 1e9,
+                              "needed": need / 1e9, "free": free / 1e9}
+        if need > 0.95 * free:
+            out["skipped"] = "needs %.0f GB per rank, %.0f GB free" % (need / 1e9, free / 1e9)
+            return out
+        t0 = time.perf_counter()
+        de = ecw.DeviceEris(o, v, rank=rank, world=world, gemm="int8", int8_digits=ns)
+        n0, nsh = de._shard_rows()
+        chunk_rows = max(128, min(4096, (1 << 28) // pv // 128 * 128))
+        tmp = torch.empty(chunk_rows * pv, dtype=torch.float64, device="cuda")
+
+        def rows(r0, nr):
+            if lib.ecw_synth_tensor(SYNTH_KIND["vvvv_p"], tmp.data_ptr(), o, v, n0 + r0, nr, 0.01, de.stream()) != 0:
+                raise RuntimeError("ecw_synth_tensor(vvvv_p rows) failed")
+            return tmp
+        de._cut_vvvv_planes(rows, chunk_rows)
+        torch.cuda.synchronize()
+        out["setup_s"] = time.perf_counter() - t0
+        st = de.stream()
+        g = torch.Generator(device="cuda").manual_seed(20260)          # the same operand on every rank
+        tau = (torch.rand((po, pv), generator=g, dtype=torch.float64, device="cuda") - 0.5) * 0.04
+        pb = torch.empty(int(lib.ecw_ozaki_plane_bytes(po, pv, ns)), dtype=torch.int8, device="cuda")
+        sb = torch.empty(int(lib.ecw_ozaki_stat_elems(po)), dtype=torch.float64, device="cuda")
+        cr = torch.zeros((po, nshmax), dtype=torch.float64, device="cuda")
+        full = torch.empty((world, po, nshmax), dtype=torch.float64, device="cuda")
+        res = torch.empty((po, pv), dtype=torch.float64, device="cuda")
+        pa, sa = de.buf["vvvv_oz"], de.buf["vvvv_ozs"]
+
+        def gemm():
+            if lib.ecw_ozaki_gemm(pa.data_ptr(), sa.data_ptr(), pb.data_ptr(), sb.data_ptr(), nsh, po, pv, cr.data_ptr(),
+                                  1, nshmax, 1.0, 0.0, ns, st) != 0:
+                raise RuntimeError("ecw_ozaki_gemm failed")
+
+        def step():
+            if lib.ecw_ozaki_split(tau.data_ptr(), po, pv, pv, 1, ns, pb.data_ptr(), sb.data_ptr(), st) != 0:
+                raise RuntimeError("ecw_ozaki_split failed")
+            gemm()
+            if world > 1:
+                dist.all_gather_into_tensor(full, cr)
+                res.copy_(full.permute(1, 0, 2).reshape(po, world * nshmax)[:, :pv])
+            else:
+                res.copy_(cr[:, :pv])
+
+        step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gemm()
+        g1.record()
+        torch.cuda.synchronize()
+        gemm_ms = g0.elapsed_time(g1)
+        # spot check against FP64 arithmetic: three columns of this rank's shard from regenerated FP64 vvvv rows
+        worst = 0.0
+        row = torch.empty(pv, dtype=torch.float64, device="cuda")
+        for m in (0, nsh // 2, nsh - 1):
+            if lib.ecw_synth_tensor(SYNTH_KIND["vvvv_p"], row.data_ptr(), o, v, n0 + m, 1, 0.01, st) != 0:
+                raise RuntimeError("ecw_synth_tensor failed")
+            ref = tau @ row
+            worst = max(worst, float((res[:, n0 + m] - ref).abs().max()))
+        if world > 1:
+            t = torch.tensor([ms, gemm_ms, worst], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, gemm_ms, worst = float(t[0]), float(t[1]), float(t[2])
+        flops = 2.0 * po * pv * float(pv)
+        out.update({"ladder_ms": ms, "ladder_gemm_ms": gemm_ms, "ladders_per_sec": 1e3 / ms,
+                    "fp64_equivalent_tflops_all_gpus": flops / ms / 1e9,
+                    "fp64_equivalent_tflops_per_gpu_gemm_only": flops * (nsh / float(pv)) / gemm_ms / 1e9,
+                    "launch": "%dx%dx%d per rank (M = vvvv rows of the shard, N = P_o, K = P_v)" % (nsh, po, pv),
+                    "max_abs_err_vs_fp64_3_columns_per_rank": worst,
+                    "timed": "digit cut of tau_p + INT8 product on the shard + ncclAllGather of the result + layout copy, "
+                             "%d repetitions, max over ranks" % reps})
+        del de, tmp, tau, pb, sb, cr, full, res, pa, sa
+        torch.cuda.empty_cache()
+    except Exception as exc:                                    # never lose the bench line over this extra key
+        out["error"] = repr(exc)[:300]
+        try:
+            torch.cuda.empty_cache()
+        except Exception:
+            pass
+    return out
+
+
 def np_copy(x):
     import numpy as np
     return np.array(x, copy=True)
@@ -532,6 +643,8 @@ def run_ours(args):
         step_dev()
         torch.cuda.synchronize()
         per_step = lib.ecw_ctx_nccl_ops(de._h) - before
+    # BASELINE.json configs[4] beside the 8-GPU line (or on request): the sharded vvvv ladder at (60, 800)
+    c5 = config5_ladder(ecw, torch, dist, rank, world) if (args.config5 or (world == 8 and (o, v) == (40, 400))) else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -637,6 +750,8 @@ def run_ours(args):
         "gpu_launches": int(launches * args.steps),
         "roofline": roofline,
     }
+    if c5 is not None:
+        line["config5"] = c5
     if world == 1:
         try:
             line["parts_ccs"] = time_ccs(ecw, torch)
@@ -660,6 +775,7 @@ def main():
     ap.add_argument("--nvir", type=int, default=400)
     ap.add_argument("--alpha", type=float, default=None, help="L1 coefficient (default: none, as Main.CCSD_GS)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config5", action="store_true", help="add the sharded (60,800) vvvv ladder as extra key config5 (default: at 8 GPUs)")
     ap.add_argument("--gemm", default=None, choices=["int8", "dmma"], help="GEMM engine (default: int8)")
     ap.add_argument("--int8-digits", type=int, default=None, help="base-256 digits of the INT8 engine (default: from the integral magnitudes, 6 for the benchmark)")
     args = ap.parse_args()
