@@ -503,8 +503,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries ONE JSON line: no NCCL banner ("NCCL version ..." is printed to stdout at NCCL_DEBUG=VERSION)
-        os.environ["NCCL_DEBUG"] = os.environ.get("ECW_NCCL_DEBUG", "WARN")
+        # stdout carries ONE JSON line: NCCL's own output ("NCCL version ..." at NCCL_DEBUG >= VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     o, v = args.nocc, args.nvir
     n = o + v
@@ -643,13 +643,7 @@ def run_ours(args):
         step_dev()
         torch.cuda.synchronize()
         per_step = lib.ecw_ctx_nccl_ops(de._h) - before
-    # BASELINE.json configs[4] beside the 8-GPU line (or on request): the sharded vvvv ladder at (60, 800)
-    c5 = config5_ladder(ecw, torch, dist, rank, world) if (args.config5 or (world == 8 and (o, v) == (40, 400))) else None
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
+    # what the line needs from the container (cheap; before it may be dropped)
     gh, gc = ctypes.c_int64(0), ctypes.c_int64(0)
     lib.ecw_ctx_graph_stats(de._h, ctypes.byref(gh), ctypes.byref(gc))
     graph_stats = {"replays": gh.value, "captures": gc.value,
@@ -660,6 +654,22 @@ def run_ours(args):
     launches += cc.plan_launches("gamma") + cc.plan_launches("energy") + 3   # + antisymmetry checks
     exec_flops = (cc.plan_flops("tupdate", alpha, False, anti) + cc.plan_flops("lupdate", alpha, False, anti)
                   + cc.plan_flops("gamma") + cc.plan_flops("energy"))
+    own_nccl = de.own_nccl
+    # BASELINE.json configs[4] beside the 8-GPU line (or on request): the sharded vvvv ladder at (60, 800).  Every
+    # measurement of the line itself is done: the (40,400) container and amplitudes go first (the ladder's shard of the
+    # vvvv planes alone is 77 GB per rank at 8 GPUs).
+    c5 = None
+    if args.config5 or (world == 8 and (o, v) == (40, 400)):
+        import gc as _gc
+        solver = sout = cc = de = t1 = t2 = l1 = l2 = fsp = h = None
+        _gc.collect()
+        torch.cuda.empty_cache()
+        c5 = config5_ladder(ecw, torch, dist, rank, world)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     peak = measure_fp64_peak(torch)
     evals_per_s = args.steps * world / (ms_dev / 1e3) if world == 1 else args.steps / (ms_dev / 1e3)
     e2e_per_s = e2e_steps / (ms_e2e / 1e3)
@@ -721,7 +731,7 @@ def run_ours(args):
                    "nocc": o, "nvir": v, "alpha": alpha, "parallelism": "1 GPU" if world == 1 else "vshard%d" % world,
                    "collectives": None if world == 1 else (
                        ("ncclAllGather / grouped ncclSend+ncclRecv enqueued by the library's executor on its own "
-                        "communicator, %d per step" % per_step) if de.own_nccl else "torch.distributed (host-driven)"),
+                        "communicator, %d per step" % per_step) if own_nccl else "torch.distributed (host-driven)"),
                    "gemm_engine": ("int8 tcgen05 (%d digits) for the large GEMMs, FP64 DMMA for the rest" % ns) if ns
                    else "FP64 DMMA",
                    "l2_policy": "inputs larger than L2 (the packed vvvv, %.1f GB, is streamed every step)"
