@@ -501,10 +501,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries ONE JSON line: whatever libraries print to file descriptor 1 during the run (NCCL's version banner at
+    # NCCL_DEBUG >= VERSION, ...) is sent to stderr; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's own output ("NCCL version ..." at NCCL_DEBUG >= VERSION) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     o, v = args.nocc, args.nvir
     n = o + v
@@ -770,7 +773,9 @@ def run_ours(args):
     if not args.no_cpu and world == 1:
         # this repo's path at the CPU shapes first (GPU still warm), then the CPU leg itself on the host cores
         line["cpu_baseline"] = cpu_baseline(o, v, same_shape_gpu(ecw, torch, CPU_SHAPES))
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
+    os.close(out_fd)
     if world > 1:
         dist.destroy_process_group()
 
