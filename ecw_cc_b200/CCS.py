@@ -4,8 +4,11 @@ terms), EOM-like right/left excited-state residuals for H + Vexp, and the four r
 
 Same names, argument order, tuple layouts and in-place quirks as the reference, so the unchanged
 `Solver_GS.Solver_CCS` / `Solver_ES.Solver_ES` loops drive it.  Every arithmetic operation runs on
-the device through the primitive ops of the C ABI (`ecw_op_*`: contraction engine + FP64
-tensor-core GEMM, strided axpby, denominators, dot).  Only canonical integral blocks are kept on
+the device: the four intermediate builders (everything that reads an integral block) are single calls
+of the C ABI — `ecw_ccs_t1inter / l1inter / r1inter / esl1inter`, cached plans replayed as CUDA graphs
+(csrc/ccs_plan.cpp) — and the singles-sized updates are sequences of the primitive ops (`ecw_op_*`:
+contraction engine + FP64 tensor-core GEMM, strided axpby, denominators, dot) with the reference's
+host-side scalar logic between them.  Only canonical integral blocks are kept on
 the device; the reference's other blocks follow from Eris.py:128:
     ovvo[jabi] = -ovov_ph[iajb]   voov[bija] = -ovov_ph[jbia]   oovo[kjbi] = -ooov[kjib]
     vovv[bica] = -ovvv[ibca]      with ovov_ph[(ia),(nf)] = ovov[naif].
@@ -14,7 +17,7 @@ device, so the update that follows does not upload them again.
 """
 import numpy as np
 
-from ._lib import EcwError, ECW_HAS_ALPHA, ECW_SUBDIFF_SINGLES
+from ._lib import lib, EcwError, ECW_HAS_ALPHA, ECW_SUBDIFF_SINGLES
 from .devops import DevOps, _scalar
 from .eris import DeviceEris
 
@@ -79,6 +82,43 @@ class Gccs(object):
         t.dev = {"W": W_dev, "host_id": id(host_items[w_index])}
         return t
 
+    def _inter(self, func, ts, fsp, vm=None, e_term=True):
+        """One of the four intermediate builders as ONE call of the C ABI (ecw_ccs_t1inter / l1inter / r1inter /
+        esl1inter: a cached plan, replayed as a CUDA graph).  The arguments go through persistent device blocks so that
+        the pointers the library sees never change; returns (F [n,n] device, W [v,o,o,v] device or None, X [o,v] device
+        or None, scalar or None) — F and X are views of the persistent blocks (read them before the next call), W is a
+        fresh tensor (it is cached for the update that follows)."""
+        ops = self.ops
+        torch = ops.torch
+        e = self.eris
+        o, v = self.nocc, self.nvir
+        n = o + v
+        st = getattr(self, "_ccs_blocks", None)
+        if st is None:
+            mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=e.device)      # noqa: E731
+            st = self._ccs_blocks = dict(ts=mk(o, v), fsp=mk(n, n), vm=mk(n, n), F=mk(n, n), W=mk(v, o, o, v), X=mk(o, v),
+                                         e=mk(1))
+        st["ts"].copy_(ops.to_dev(ts))
+        st["fsp"].copy_(e.fock_dev if fsp is None else ops.to_dev(fsp))
+        if vm is not None:
+            st["vm"].copy_(ops.to_dev(vm))
+        p = lambda k: st[k].data_ptr()                                                           # noqa: E731
+        if func == "t1":
+            e.execute("ccs_t1inter", 0, lambda: lib.ecw_ccs_t1inter(e._h, p("ts"), p("fsp"), p("F"), e.stream()),
+                      "ecw_ccs_t1inter")
+            return st["F"], None, None, None
+        if func == "l1":
+            fl = 1 if e_term else 0
+            e.execute("ccs_l1inter", fl, lambda: lib.ecw_ccs_l1inter(e._h, p("ts"), p("fsp"), fl, p("F"), p("W"), p("e"),
+                                                                      e.stream()), "ecw_ccs_l1inter")
+            return st["F"], st["W"].clone(), None, (ops.scalar(st["e"]) if e_term else 0.)
+        name = {"r1": "ccs_r1inter", "esl1": "ccs_esl1inter"}[func]
+        fn = lib.ecw_ccs_r1inter if func == "r1" else lib.ecw_ccs_esl1inter
+        fl = 1 if vm is not None else 0
+        e.execute(name, fl, lambda: fn(e._h, p("ts"), p("fsp"), (p("vm") if vm is not None else None), p("F"), p("W"),
+                                       p("X"), p("e"), e.stream()), "ecw_" + name)
+        return st["F"], st["W"].clone(), st["X"], ops.scalar(st["e"])
+
     # ------------------------------------------------------------------ energy (CCS.py:226-249)
     def energy_ccs(self, ts, fsp, rsn=None, r0n=None, vn=None):
         ops = self.ops
@@ -110,18 +150,9 @@ class Gccs(object):
     # ------------------------------------------------------------------ T1 (CCS.py:271-440)
     def T1inter(self, ts, fsp):
         ops = self.ops
-        d_ts = ops.to_dev(ts)
-        foo, fov, fvo, fvv = self._f(fsp)
-        Fai = ops.copy(fvo)
-        ops.contract('jb,iajb->ai', d_ts, self._ovov_ph, alpha=-1.0, out=Fai, beta=1.0)      # 'jb,jabi->ai' ovvo
-        Fab = ops.copy(fvv)
-        ops.contract('jb,ja->ab', fov, d_ts, alpha=-1.0, out=Fab, beta=1.0)
-        ops.contract('jc,jacb->ab', d_ts, self._ovvv, out=Fab, beta=1.0)
-        Fji = ops.copy(foo)
-        ops.contract('kb,kjib->ji', d_ts, self._ooov, alpha=-1.0, out=Fji, beta=1.0)         # 'kb,kjbi->ji' oovo
-        tmp = ops.contract('kc,jkcb->jb', d_ts, self._oovv)
-        ops.contract('ib,jb->ji', d_ts, tmp, alpha=-1.0, out=Fji, beta=1.0)
-        return ops.to_host(Fab), ops.to_host(Fji), ops.to_host(Fai)
+        o = self.nocc
+        F, _, _, _ = self._inter("t1", ts, fsp)
+        return ops.to_host(F[o:, o:]), ops.to_host(F[:o, :o]), ops.to_host(F[o:, :o])     # Fab, Fji, Fai
 
     def _t1(self, d_ts, Fab, Fji, Fai):
         ops = self.ops
@@ -183,27 +214,9 @@ class Gccs(object):
     # ------------------------------------------------------------------ Lambda1 (CCS.py:490-698)
     def L1inter(self, ts, fsp, E_term=True):
         ops = self.ops
-        d_ts = ops.to_dev(ts)
-        foo, fov, fvo, fvv = self._f(fsp)
-        Fba = ops.copy(fvv)
-        ops.contract('ja,jb->ba', fov, d_ts, alpha=-1.0, out=Fba, beta=1.0)
-        ops.contract('jbca,jc->ba', self._ovvv, d_ts, out=Fba, beta=1.0)
-        tmp = ops.contract('jkca,jc->ka', self._oovv, d_ts)
-        ops.contract('ka,kb->ba', tmp, d_ts, alpha=-1.0, out=Fba, beta=1.0)
-        Fij = ops.copy(foo)
-        ops.contract('ib,jb->ij', fov, d_ts, out=Fij, beta=1.0)
-        ops.contract('kijb,kb->ij', self._ooov, d_ts, alpha=-1.0, out=Fij, beta=1.0)         # 'kibj,kb->ij' oovo
-        tmp = ops.contract('kibc,kb->ic', self._oovv, d_ts)
-        ops.contract('ic,jc->ij', tmp, d_ts, out=Fij, beta=1.0)
-        W = ops.copy(self._ovov_ph, 'jbia->bija', alpha=-1.0)                                 # voov
-        ops.contract('kija,kb->bija', self._ooov, d_ts, alpha=-1.0, out=W, beta=1.0)
-        tmp = ops.contract('kica,kb->icab', self._oovv, d_ts)
-        ops.contract('icab,jc->bija', tmp, d_ts, alpha=-1.0, out=W, beta=1.0)
-        ops.contract('ibca,jc->bija', self._ovvv, d_ts, alpha=-1.0, out=W, beta=1.0)         # 'bica,jc->bija' vovv
-        Fia = ops.copy(fov)
-        ops.contract('jiba,jb->ia', self._oovv, d_ts, out=Fia, beta=1.0)
-        E = (-ops.dot(d_ts, fov) - 0.5 * ops.dot(d_ts, self._G(d_ts))) if E_term else 0.
-        host = (ops.to_host(Fia), ops.to_host(Fba), ops.to_host(Fij), ops.to_host(W), E)
+        o = self.nocc
+        F, W, _, E = self._inter("l1", ts, fsp, e_term=E_term)
+        host = (ops.to_host(F[:o, o:]), ops.to_host(F[o:, o:]), ops.to_host(F[:o, :o]), ops.to_host(W), E)   # Fia, Fba, Fij
         return self._pack(host, W, 3)
 
     def _l1(self, d_ls, Fia, Fba, Fij, W, E):
@@ -271,55 +284,10 @@ class Gccs(object):
     # ------------------------------------------------------------------ ES right (CCS.py:774-1158)
     def R1inter(self, ts, fsp, vm):
         ops = self.ops
-        o, v = self.nocc, self.nvir
-        d_ts = ops.to_dev(ts)
-        foo, fov, fvo, fvv = self._f(self.fock if fsp is None else fsp)
-        Fab = ops.copy(fvv)
-        ops.contract('ja,jb->ab', d_ts, fov, alpha=-1.0, out=Fab, beta=1.0)
-        ops.contract('jc,jacb->ab', d_ts, self._ovvv, out=Fab, beta=1.0)
-        x = ops.contract('jc,jkcb->kb', d_ts, self._oovv)                                    # 'jc,ka,jkcb->ab'
-        ops.contract('ka,kb->ab', d_ts, x, alpha=-1.0, out=Fab, beta=1.0)
-        Fji = ops.copy(foo)
-        ops.contract('ib,jb->ji', d_ts, fov, out=Fji, beta=1.0)
-        ops.contract('kb,kjib->ji', d_ts, self._ooov, alpha=-1.0, out=Fji, beta=1.0)         # oovo
-        y = ops.contract('kb,kjbc->jc', d_ts, self._oovv)                                    # 'kb,ic,kjbc->ji'
-        ops.contract('ic,jc->ji', d_ts, y, out=Fji, beta=1.0)
-        W = ops.copy(self._ovov_ph, 'iakc->akic', alpha=-1.0)                                 # voov[akic]
-        ops.contract('ib,kabc->akic', d_ts, self._ovvv, alpha=-1.0, out=W, beta=1.0)         # vovv[akbc]
-        z = ops.contract('ib,jkbc->ijkc', d_ts, self._oovv)                                  # 'ib,ja,jkbc->akic'
-        ops.contract('ja,ijkc->akic', d_ts, z, alpha=-1.0, out=W, beta=1.0)
-        ops.contract('ja,jkic->akic', d_ts, self._ooov, alpha=-1.0, out=W, beta=1.0)
-        G = self._G(d_ts)
-        Er = ops.dot(d_ts, fov) + 0.5 * ops.dot(d_ts, G)
-        Zab = ops.copy(fvv)
-        ops.contract('ja,jb->ab', d_ts, fov, alpha=-1.0, out=Zab, beta=1.0)
-        Zji = ops.copy(foo)
-        ops.contract('kb,kjib->ji', d_ts, self._ooov, alpha=-1.0, out=Zji, beta=1.0)
-        tmp = ops.contract('ic,jkbc->ijkb', d_ts, self._oovv)
-        ops.contract('kb,ijkb->ji', d_ts, tmp, alpha=-1.0, out=Zji, beta=1.0)
-        Zai = ops.copy(fvo)
-        ops.contract('jb,iajb->ai', d_ts, self._ovov_ph, alpha=-1.0, out=Zai, beta=1.0)      # ovvo
-        u = ops.contract('jabc,ic->jabi', self._ovvv, d_ts)                                  # 'jb,ic,jabc->ai'
-        ops.contract('jb,jabi->ai', d_ts, u, out=Zai, beta=1.0)
-        Tia = ops.copy(Zai, 'ai->ia')
-        ops.contract('ib,ab->ia', d_ts, Zab, out=Tia, beta=1.0)
-        ops.contract('ja,ji->ia', d_ts, Zji, alpha=-1.0, out=Tia, beta=1.0)
-        if vm is None:
-            Pia = ops.fill(ops.empty(o, v), 0.0)
-        else:
-            mv = ops.copy(ops.to_dev(vm), alpha=-1.0)
-            v_vo, v_vv, v_oo = mv[o:, :o], mv[o:, o:], mv[:o, :o]
-            P = ops.copy(v_vo)
-            ops.contract('ab,ib->ai', v_vv, d_ts, out=P, beta=1.0)
-            # literal 'ii,ja,ib->ai' (CCS.py:869): v_oo[ii] * (sum_j ts[ja]) * (sum_b ts[ib])
-            ones_o, ones_v = ops.fill(ops.empty(o), 1.0), ops.fill(ops.empty(v), 1.0)
-            col = ops.contract('ja,j->a', d_ts, ones_o)
-            row = ops.contract('ib,b->i', d_ts, ones_v)
-            diag = self.ops.torch.as_strided(v_oo, (o,), (v_oo.stride(0) + v_oo.stride(1),))
-            drow = ops.mul(1.0, diag, row, 0.0, ops.empty(o))
-            ops.contract('a,i->ai', col, drow, alpha=-1.0, out=P, beta=1.0)
-            Pia = ops.copy(P, 'ai->ia')
-        host = (ops.to_host(Fab), ops.to_host(Fji), ops.to_host(W), Er, ops.to_host(Tia), ops.to_host(Pia))
+        o = self.nocc
+        F, W, X, Er = self._inter("r1", ts, (self.fock if fsp is None else fsp), vm)
+        host = (ops.to_host(F[o:, o:]), ops.to_host(F[:o, :o]), ops.to_host(W), Er, ops.to_host(F[:o, o:]),
+                ops.to_host(X))                                                          # Fab, Fji, Wakic, Er, Tia, Pia
         return self._pack(host, W, 2)
 
     def _r1core(self, d_rs, Fab, Fji, W):
@@ -448,32 +416,10 @@ class Gccs(object):
     # ------------------------------------------------------------------ ES left (CCS.py:1164-1518)
     def es_L1inter(self, ts, fsp, vm):
         ops = self.ops
-        o, v = self.nocc, self.nvir
-        d_ts = ops.to_dev(ts)
-        foo, fov, fvo, fvv = self._f(fsp)
-        Fba = ops.copy(fvv)
-        ops.contract('jb,ja->ba', d_ts, fov, alpha=-1.0, out=Fba, beta=1.0)
-        ops.contract('jc,jbca->ba', d_ts, self._ovvv, out=Fba, beta=1.0)
-        x = ops.contract('jc,jkca->ka', d_ts, self._oovv)                                    # 'jc,kb,jkca->ba'
-        ops.contract('kb,ka->ba', d_ts, x, alpha=-1.0, out=Fba, beta=1.0)
-        Fij = ops.copy(foo)
-        ops.contract('jb,ib->ij', d_ts, fov, out=Fij, beta=1.0)
-        ops.contract('kb,kijb->ij', d_ts, self._ooov, alpha=-1.0, out=Fij, beta=1.0)         # oovo[kibj]
-        y = ops.contract('kb,kibc->ic', d_ts, self._oovv)                                    # 'kb,jc,kibc->ij'
-        ops.contract('jc,ic->ij', d_ts, y, out=Fij, beta=1.0)
-        W = ops.copy(self._ovov_ph, 'jbia->bija', alpha=-1.0)                                 # voov
-        ops.contract('kb,kija->bija', d_ts, self._ooov, alpha=-1.0, out=W, beta=1.0)
-        ops.contract('jc,ibca->bija', d_ts, self._ovvv, alpha=-1.0, out=W, beta=1.0)         # vovv[bica]
-        z = ops.contract('kb,kica->bica', d_ts, self._oovv)                                  # 'jc,kb,kica->bija'
-        ops.contract('jc,bica->bija', d_ts, z, alpha=-1.0, out=W, beta=1.0)
-        El = ops.dot(d_ts, fov) + 0.5 * ops.dot(d_ts, self._G(d_ts))
-        Zia = ops.copy(fov)
-        ops.contract('jb,jiba->ia', d_ts, self._oovv, out=Zia, beta=1.0)
-        if vm is None:
-            P = ops.fill(ops.empty(o, v), 0.0)
-        else:
-            P = ops.copy(ops.to_dev(vm)[:o, o:], alpha=-1.0)
-        host = (ops.to_host(Fba), ops.to_host(Fij), ops.to_host(W), El, ops.to_host(Zia), ops.to_host(P))
+        o = self.nocc
+        F, W, X, El = self._inter("esl1", ts, fsp, vm)
+        host = (ops.to_host(F[o:, o:]), ops.to_host(F[:o, :o]), ops.to_host(W), El, ops.to_host(F[:o, o:]),
+                ops.to_host(X))                                                          # Fba, Fij, W, El, Zia, P
         return self._pack(host, W, 2)
 
     def L0inter(self, ts, fsp, vm):                        # CCS.py:1236-1286

@@ -5,7 +5,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libecw_b200.so")
-_SRC = ["gemm.cu", "gemm_tma.cu", "ewise.cu", "ozaki.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp", "ccsd_plan_slab.cpp"]
+_SRC = ["gemm.cu", "gemm_tma.cu", "ewise.cu", "ozaki.cu", "synth.cu", "capi.cu", "plan.cpp", "ccsd_plan.cpp", "ccsd_plan_slab.cpp",
+        "ccs_plan.cpp"]
 
 ECW_HAS_ALPHA = 1
 ECW_EQUATION = 2
@@ -80,6 +81,10 @@ class _Lib(object):
             "ecw_ctx_set_engine_override": (c_i, [c_p, c_i]),
             "ecw_ctx_set_plan_variant": (c_i, [c_p, c_i]),
             "ecw_ctx_set_int8_splitk": (c_i, [c_p, c_l]),
+            "ecw_ccs_t1inter": (c_i, [c_p, c_p, c_p, c_p, c_p]),
+            "ecw_ccs_l1inter": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
+            "ecw_ccs_r1inter": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+            "ecw_ccs_esl1inter": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
             "ecw_ctx_set_graphs": (c_i, [c_p, c_i]),
             "ecw_ctx_graph_stats": (c_i, [c_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
             "ecw_ctx_test_assume_vvvv_planes": (c_i, [c_p]),

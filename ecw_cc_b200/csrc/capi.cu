@@ -142,6 +142,10 @@ Plan& get_plan(ecw_ctx* c, const std::string& func, int flags) {
   else if (func == "lupdate") (as ? build_ccsd_lupdate : build_ccsd_lupdate_general)(*P, zz, ha, eq);
   else if (func == "gamma") build_ccsd_gamma(*P, zz);
   else if (func == "energy") build_ccsd_energy(*P, zz);
+  else if (func == "ccs_t1inter") build_ccs_t1inter(*P, zz);
+  else if (func == "ccs_l1inter") build_ccs_l1inter(*P, zz, flags & 1);
+  else if (func == "ccs_r1inter") build_ccs_r1inter(*P, zz, flags & 1);
+  else if (func == "ccs_esl1inter") build_ccs_esl1inter(*P, zz, flags & 1);
   else throw Fail("unknown function '" + func + "'");
   Plan& ref = *P;
   c->plans[key] = std::move(P);
@@ -792,6 +796,53 @@ int ecw_ccsd_energy(ecw_ctx* c, const double* t1, const double* t2, const double
     c->copy_scal_to = e_out;
     return run_plan(c, get_plan(c, "energy", 0), 0.0, static_cast<cudaStream_t>(stream), true);
   });
+}
+
+// ---- ECW-CCS intermediates (csrc/ccs_plan.cpp): one cached plan each
+int ecw_ccs_t1inter(ecw_ctx* c, const double* ts, const double* fsp, double* F, void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    c->ptr[S_T1] = const_cast<double*>(ts); c->ptr[S_FSP] = const_cast<double*>(fsp);
+    c->ptr[S_RDM1] = F;
+    return run_plan(c, get_plan(c, "ccs_t1inter", 0), 0.0, static_cast<cudaStream_t>(stream), true);
+  });
+}
+
+int ecw_ccs_l1inter(ecw_ctx* c, const double* ts, const double* fsp, int e_term, double* F, double* W, double* e_out,
+                    void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    c->ptr[S_T1] = const_cast<double*>(ts); c->ptr[S_FSP] = const_cast<double*>(fsp);
+    c->ptr[S_RDM1] = F; c->ptr[S_OUT2] = W;
+    if (e_term) {
+      if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
+      c->copy_scal_to = e_out;
+    }
+    return run_plan(c, get_plan(c, "ccs_l1inter", e_term ? 1 : 0), 0.0, static_cast<cudaStream_t>(stream), true);
+  });
+}
+
+static int ccs_es_inter(ecw_ctx* c, const char* func, const double* ts, const double* fsp, const double* vm, double* F,
+                        double* W, double* X, double* e_out, void* stream) {
+  return guarded_rc(c, [&] {
+    require_device();
+    if (!c->ptr[S_SCAL]) throw Fail("slot 'scal' is not bound");
+    c->ptr[S_T1] = const_cast<double*>(ts); c->ptr[S_FSP] = const_cast<double*>(fsp);
+    c->ptr[S_FOCK] = const_cast<double*>(vm);
+    c->ptr[S_RDM1] = F; c->ptr[S_OUT2] = W; c->ptr[S_OUT1] = X;
+    c->copy_scal_to = e_out;
+    return run_plan(c, get_plan(c, func, vm ? 1 : 0), 0.0, static_cast<cudaStream_t>(stream), true);
+  });
+}
+
+int ecw_ccs_r1inter(ecw_ctx* c, const double* ts, const double* fsp, const double* vm, double* F, double* W, double* X,
+                    double* e_out, void* stream) {
+  return ccs_es_inter(c, "ccs_r1inter", ts, fsp, vm, F, W, X, e_out, stream);
+}
+
+int ecw_ccs_esl1inter(ecw_ctx* c, const double* ts, const double* fsp, const double* vm, double* F, double* W, double* X,
+                      double* e_out, void* stream) {
+  return ccs_es_inter(c, "ccs_esl1inter", ts, fsp, vm, F, W, X, e_out, stream);
 }
 
 int ecw_antisym_defect(const double* x, int nocc, int nvir, double* out, void* stream) {

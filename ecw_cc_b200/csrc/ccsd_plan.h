@@ -43,5 +43,10 @@ void build_ccsd_tupdate_general(Plan& P, const Sizes& z, int has_alpha, int equa
 void build_ccsd_lupdate_general(Plan& P, const Sizes& z, int has_alpha, int equation);
 void build_ccsd_gamma(Plan& P, const Sizes& z);
 void build_ccsd_energy(Plan& P, const Sizes& z);
+// ECW-CCS intermediates (csrc/ccs_plan.cpp; CCS.py:271-312, :490-537, :774-872, :1164-1234)
+void build_ccs_t1inter(Plan& P, const Sizes& z);
+void build_ccs_l1inter(Plan& P, const Sizes& z, int e_term);
+void build_ccs_r1inter(Plan& P, const Sizes& z, int has_vm);
+void build_ccs_esl1inter(Plan& P, const Sizes& z, int has_vm);
 
 }  // namespace ecw

@@ -150,6 +150,25 @@ int ecw_ccsd_gamma(ecw_ctx* ctx, const double* t1, const double* t2, const doubl
 /* GCC.energy(t1,t2,fsp) — CCSD.py:224-242.  e_out: one device double. */
 int ecw_ccsd_energy(ecw_ctx* ctx, const double* t1, const double* t2, const double* fsp, double* e_out,
                     void* stream);
+/* ---- ECW-CCS intermediates (replace Gccs.T1inter / L1inter / R1inter / es_L1inter, CCS.py:271-312, :490-537,
+ * :774-872, :1164-1234) ------------------------------------------------------------
+ * One cached plan — one call, and on one GPU one CUDA-graph launch — per function: everything of a CCS ground- or
+ * excited-state iteration that reads an integral block.  ts [o,v], fsp [n,n], vm [n,n] (the state potential, or null:
+ * Pia / P = 0).  Results: F [n,n], whose blocks carry the one-body intermediates
+ *     t1inter:   vv = Fab, oo = Fji, vo = Fai            l1inter:   ov = Fia, vv = Fba, oo = Fij
+ *     r1inter:   vv = Fab, oo = Fji, ov = Tia            esl1inter: vv = Fba, oo = Fij, ov = Zia
+ * (other blocks zero); W [v,o,o,v] = Wbija / Wakic; X [o,v] = Pia / P; e_out[0] = E / Er / El on the device
+ * (l1inter: written only when e_term != 0, CCS.py:490 `E_term`).  The singles-sized updates that consume them
+ * (tsupdate, lsupdate, rsupdate, es_lsupdate, r0 / l0) are sequences of the primitive ops below with host-side
+ * scalars between them (ecw_cc_b200/CCS.py). */
+int ecw_ccs_t1inter(ecw_ctx* ctx, const double* ts, const double* fsp, double* F, void* stream);
+int ecw_ccs_l1inter(ecw_ctx* ctx, const double* ts, const double* fsp, int e_term, double* F, double* W, double* e_out,
+                    void* stream);
+int ecw_ccs_r1inter(ecw_ctx* ctx, const double* ts, const double* fsp, const double* vm, double* F, double* W, double* X,
+                    double* e_out, void* stream);
+int ecw_ccs_esl1inter(ecw_ctx* ctx, const double* ts, const double* fsp, const double* vm, double* F, double* W, double* X,
+                      double* e_out, void* stream);
+
 /* out[0] = max |x[ijab]+x[jiab]|, |x[ijab]+x[ijba]| over a doubles amplitude, out[1] = max |x| (two device doubles). */
 int ecw_antisym_defect(const double* x, int nocc, int nvir, double* out, void* stream);
 /* utilities.subdiff(eq,var,alpha) — utilities.py:26-73 (element-wise, any shape). */
