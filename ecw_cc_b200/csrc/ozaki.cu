@@ -15,7 +15,7 @@
 //       P = sum_k Da Db  ~  sum_{p+q <= NS+1} 256^-(p+q) (A_p . B_q^T)      (triangular truncation),
 //       t_r = sum_k X[r,k] / s_r  (FP64 row sums, taken while looking for the row maximum).
 //   Every int8 product A_p . B_q^T is exact in the int32 accumulator (|d d'| <= 2^14; the accumulators
-//   are drained to FP64 every 8192 k, at most NS products each: < 2^31).  Worst-case error: representation
+//   are drained to FP64 every oz_kflush(NS) k, at most NS products each: < 2^31).  Worst-case error: representation
 //   4 K 256^-NS + truncation (NS-1) K 256^-NS, relative to sA_m sB_n (< 4 max|A_m| max|B_n|): for NS = 6
 //   that is 2^-44.8 K sA sB; observed 1e-14 at 8192^3 on N(0,1) data — the size of the rounding error of a
 //   DMMA/FMA dot product of that length.
@@ -55,7 +55,11 @@ namespace {
 
 constexpr int OZ_BK = 32;        // k per stage = K of one kind::i8 MMA
 constexpr int OZ_TM = 128;       // tile rows  (MMA M)
-constexpr int OZ_KFLUSH = 8192;  // int32 accumulators are drained to FP64 every OZ_KFLUSH k (8 * 2^13 * 2^14 <= 2^30)
+// int32 accumulators are drained to FP64 every oz_kflush(NS) k.  The accumulator of weight NS-1 sums NS digit products
+// per k, each at most 128 * 128 = 2^14 in magnitude: NS * K * 2^14 < 2^31 needs K < 2^17 / NS.  8192 keeps a factor of
+// two of headroom for every digit count (16384 is admissible up to seven digits and was measured: no gain — the drain
+// is ~1 % of a chunk; tests/test_gpu_int8.py::test_int8_accumulator_headroom runs the all-(-128) worst case).
+__host__ __device__ constexpr int oz_kflush(int) { return 8192; }
 constexpr int OZ_SMEM_MAX = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(OzGemmParams p) {
   const int64_t tiles_mn = tiles_m * tiles_n;
   const int64_t ntiles = tiles_mn * p.bt.batch;
   const int nkb = p.bt.nkb > 0 ? (int)p.bt.nkb : (int)((p.K + OZ_BK - 1) / OZ_BK);
-  constexpr int KB_FLUSH = OZ_KFLUSH / OZ_BK;
+  constexpr int KB_FLUSH = oz_kflush(NS) / OZ_BK;
   const int nchunk = (nkb + KB_FLUSH - 1) / KB_FLUSH;
 
   if (tid == 0) {

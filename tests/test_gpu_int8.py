@@ -218,3 +218,26 @@ def test_ovvv_plane_sets_bit_exact(ecw):
         got = de.buf[name + "s"].cpu().numpy()
         assert np.array_equal(got[: st.size // (2 + K1 if K1 > 1 else 2)], st[: st.size // (2 + K1 if K1 > 1 else 2)])
         assert np.abs(got - st).max() < 1e-13, name
+
+
+@pytest.mark.parametrize("ns", [6, 7, 8])
+def test_int8_accumulator_headroom(ecw, ns):
+    """Worst case of the int32 accumulators: every digit of both operands is -128 (x = -(1 - 2^-49) s_r), so each of
+    the up to NS products per k adds +2^14 and nothing cancels between the drains to FP64 (csrc/ozaki.cu, oz_kflush).  K spans several drains; the result must be the exact K x^2
+    to FP64 rounding."""
+    import torch
+    lib = ecw.lib
+    st = torch.cuda.current_stream().cuda_stream
+    M, N, K = 130, 90, 40000
+    x = -(1.0 - 2.0 ** -49)
+    A = torch.full((M, K), x, dtype=torch.float64, device="cuda")
+    B = torch.full((N, K), x, dtype=torch.float64, device="cuda")
+    pa, sa = _split(ecw, A, ns)
+    pb, sb = _split(ecw, B, ns)
+    assert int(pa[:1024].to(torch.int64).max()) == -128          # k-block 0, digit 0, rows 0..31: every digit is -128
+    C = torch.zeros((M, N), dtype=torch.float64, device="cuda")
+    assert lib.ecw_ozaki_gemm(pa.data_ptr(), sa.data_ptr(), pb.data_ptr(), sb.data_ptr(), M, N, K, C.data_ptr(), N, 1,
+                              1.0, 0.0, ns, st) == 0
+    want = K * x * x
+    # representation error of x with NS digits: |delta| <= 256^-NS per element, twice K of them at |x| ~ 1
+    assert float((C - want).abs().max()) <= 2.5 * K * 256.0 ** -ns + 1e-9
